@@ -1,0 +1,42 @@
+// fp_api_ops.cu — C-ABI entry points that expose single operators (used by the parity tests to
+// bisect the pipeline layer by layer; the product entry points live in fp_api.cu).
+#include "../../include/fpose.h"
+#include "fp_common.cuh"
+#include "fp_gemm.cuh"
+
+namespace fp {
+const char* get_last_error();
+}
+
+extern "C" {
+
+const char* fp_last_error(void) { return fp::get_last_error(); }
+
+unsigned long long fp_launch_count(void) { return fp::g_launch_count; }
+
+int fp_op_gemm_layer(const fp_gemm_layer_t* l, void* stream) {
+  if (!l) {
+    fp::set_last_error("fp_op_gemm_layer: null layer");
+    return -1;
+  }
+  fp::GemmLayer L;
+  L.kind = l->kind;
+  L.n_img = l->n_img;
+  L.Hin = l->Hin;
+  L.Win = l->Win;
+  L.Cin = l->Cin;
+  L.Cout = l->Cout;
+  L.in = l->in;
+  L.w = l->w;
+  L.bias = l->bias;
+  L.res = l->res;
+  L.res_ld = l->res_ld;
+  L.out = l->out;
+  L.out_ld = l->out_ld;
+  L.out_split = l->out_split;
+  L.post_add = l->post_add;
+  L.relu = l->relu;
+  return fp::gemm_layer_launch(L, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,473 @@
+// fp_gemm.cu — tcgen05 / TMA implicit-GEMM tile kernel for every dense contraction on the hot
+// path: the 15 convolutions of RefineNet / ScoreNetMultiPair's encoders and the linear layers of
+// their attention heads.
+//
+// Replaces (reference, via torch -> cuDNN / cuBLAS under fp16 autocast):
+//   learning/models/network_modules.py:37-50   ConvBNReLU          (conv + folded BN + ReLU)
+//   learning/models/network_modules.py:73-111  ResnetBasicBlock    (conv,BN,ReLU,conv,BN,+id,ReLU)
+//   learning/models/refine_network.py:80-92    encodeA / encodeAB / pos_embed / linear layers
+//   learning/models/score_network.py:60-74     encoderA / encoderAB / att projections
+//
+// Design (B200-first, no library GEMM):
+//   * D[128 x BN] tiles, fp16 operands, fp32 accumulators in TMEM (double buffered, 2 x BN columns).
+//   * Warp-specialised persistent CTA (one per SM): warp 0 = TMA producer, warp 1 = single-thread
+//     tcgen05.mma issuer, warps 2..5 = epilogue (TMEM -> registers -> +bias/+residual/ReLU/+PE ->
+//     fp16 NHWC stores).  smem ring of STAGES x (A 16 KB + B BN*128 B), 128-byte swizzle.
+//   * The convolution is an *implicit* GEMM: the A tile for k-block (tap, 64-channel chunk) is one
+//     5-D TMA box over the NHWC activation tensor, displaced by the tap offset; out-of-bounds
+//     coordinates are zero-filled by the TMA unit, which implements the zero padding.  Stride-2
+//     convolutions use a (2C, W/2, 2, H/2, N) view of the same memory so that every tap is again a
+//     dense box; the 7x7/s2 stem reads a spatially pre-padded 8-channel image through an
+//     overlapping-stride view (64 contiguous fp16 = 8 pixels x 8 channels per output pixel and
+//     filter row).  No im2col buffer is ever materialised.
+#include "fp_gemm.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "fp_common.cuh"
+
+namespace fp {
+
+unsigned long long g_launch_count = 0;
+
+static thread_local char t_last_error[1024] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_last_error, sizeof(t_last_error), fmt, ap);
+  va_end(ap);
+}
+const char* get_last_error() { return t_last_error; }
+
+struct GemmParams {
+  int lg_bw, lg_bh;  // tile rows m -> (nn, ii, jj): jj = m & (bw-1), ii = (m >> lg_bw) & (bh-1)
+  int bw, bh, bn;
+  int tiles_w, tiles_h, tiles_n, n_tiles_n, total_tiles;
+  int num_kb, chunks_per_tap;
+  int dim_w, dim_h, dim_n;
+  short tap_off[9][5];
+  int Ho, Wo, n_img, Cout;
+  const float* bias;
+  const __half* res;
+  int res_ld;
+  __half* out;
+  int out_ld;
+  int out_split;
+  const float* post_add;
+  int relu;
+};
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
+constexpr int kThreads = 192;
+
+template <int BN>
+struct TileCfg {
+  static constexpr int kBBytes = BN * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+    gemm_tile_kernel(const __grid_constant__ CUtensorMap map_a,
+                     const __grid_constant__ CUtensorMap map_b, const __grid_constant__ GemmParams p) {
+  using Cfg = TileCfg<BN>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  uint64_t* full = bars;                 // [S]
+  uint64_t* empty = bars + S;            // [S]
+  uint64_t* tmem_full = bars + 2 * S;    // [2]
+  uint64_t* tmem_empty = bars + 2 * S + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles_n;
+        const int m_tile = tile / p.n_tiles_n;
+        const int tw = m_tile % p.tiles_w;
+        const int th = (m_tile / p.tiles_w) % p.tiles_h;
+        const int tn = m_tile / (p.tiles_w * p.tiles_h);
+        int base[5] = {0, 0, 0, 0, 0};
+        base[p.dim_w] += tw * p.bw;
+        if (p.dim_h >= 0) base[p.dim_h] += th * p.bh;
+        if (p.dim_n >= 0) base[p.dim_n] += tn * p.bn;
+        int tap = 0, chunk = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+          tma_load_5d(&map_a, &full[stage], sa, base[0] + p.tap_off[tap][0] + chunk * kBlockK,
+                      base[1] + p.tap_off[tap][1], base[2] + p.tap_off[tap][2],
+                      base[3] + p.tap_off[tap][3], base[4] + p.tap_off[tap][4]);
+          tma_load_2d(&map_b, &full[stage], sb, kb * kBlockK, n_tile * BN);
+          if (++chunk == p.chunks_per_tap) {
+            chunk = 0;
+            ++tap;
+          }
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BN);
+      int stage = 0, phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const int acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + kABytes;
+          const uint64_t da = umma_desc_sw128(sa);
+          const uint64_t db = umma_desc_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 fp16 = 32 B along K inside the 128 B swizzle atom: +2 in (addr >> 4) units
+            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                     (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
+          if (kb == p.num_kb - 1) umma_commit(&tmem_full[acc]);
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp may read
+    const int row = quarter * 32 + lane;
+    const int jj = row & (p.bw - 1);
+    const int ii = (row >> p.lg_bw) & (p.bh - 1);
+    const int nn = row >> (p.lg_bw + p.lg_bh);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int acc_phase = (it >> 1) & 1;
+      const int n_tile = tile % p.n_tiles_n;
+      const int m_tile = tile / p.n_tiles_n;
+      const int tw = m_tile % p.tiles_w;
+      const int th = (m_tile / p.tiles_w) % p.tiles_h;
+      const int tn = m_tile / (p.tiles_w * p.tiles_h);
+      const int n = tn * p.bn + nn, i = th * p.bh + ii, j = tw * p.bw + jj;
+      const bool valid = (n < p.n_img) && (i < p.Ho) && (j < p.Wo);
+      int n_o = n, coff = 0;
+      if (p.out_split > 0) {
+        n_o = n % p.out_split;
+        coff = (n / p.out_split) * p.Cout;
+      }
+      const size_t pix = (size_t)(n * p.Ho + i) * p.Wo + j;
+      const size_t pix_o = (size_t)(n_o * p.Ho + i) * p.Wo + j;
+      __half* outp = p.out + pix_o * p.out_ld + coff + n_tile * BN;
+      const __half* resp = p.res ? p.res + pix * p.res_ld + n_tile * BN : nullptr;
+      const float* pap = p.post_add ? p.post_add + (size_t)(i * p.Wo + j) * p.Cout + n_tile * BN : nullptr;
+      const float* bp = p.bias + n_tile * BN;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c, v);
+        tmem_ld_wait();
+        if (valid) {
+          uint4 rv[4];
+          if (resp) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rv[q] = __ldg(reinterpret_cast<const uint4*>(resp + c) + q);
+          }
+          uint32_t o[16];
+#pragma unroll
+          for (int k = 0; k < 32; k += 2) {
+            float a0 = __uint_as_float(v[k]) + __ldg(bp + c + k);
+            float a1 = __uint_as_float(v[k + 1]) + __ldg(bp + c + k + 1);
+            if (resp) {
+              const __half2 r2 = reinterpret_cast<const __half2*>(rv)[k >> 1];
+              const float2 rf = __half22float2(r2);
+              a0 += rf.x;
+              a1 += rf.y;
+            }
+            if (p.relu) {
+              a0 = fmaxf(a0, 0.f);
+              a1 = fmaxf(a1, 0.f);
+            }
+            if (pap) {
+              a0 += __ldg(pap + c + k);
+              a1 += __ldg(pap + c + k + 1);
+            }
+            o[k >> 1] = pack_half2(a0, a1);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            reinterpret_cast<uint4*>(outp + c)[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  FP_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+  }
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
+                  bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FP_REQUIRE(r == CUDA_SUCCESS,
+             "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u]",
+             (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+             (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+             (unsigned long long)(rank > 4 ? dims[4] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0,
+             rank > 3 ? box[3] : 0, rank > 4 ? box[4] : 0);
+  return 0;
+}
+
+static int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+static int g_num_sms = 0;
+
+template <int BN>
+static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = TileCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FP_CUDA_OK(cudaFuncSetAttribute(gemm_tile_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    FP_CUDA_OK(cudaGetDevice(&dev));
+    FP_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
+  gemm_tile_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ma, mb, p);
+  ++g_launch_count;
+  FP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  CUtensorMap ma, mb;
+  const uint64_t E = 2;  // bytes per fp16
+  int Ho, Wo, taps, ktot;
+  int BN;
+  uint64_t dims[5], str[4];
+  uint32_t box[5];
+
+  switch (L.kind) {
+    case LK_LINEAR: {
+      FP_REQUIRE(L.Cin % 64 == 0, "LINEAR: K=%d not a multiple of 64", L.Cin);
+      Ho = 1;
+      Wo = L.Win;
+      taps = 1;
+      p.chunks_per_tap = L.Cin / 64;
+      p.bw = 128; p.bh = 1; p.bn = 1;
+      p.dim_w = 1; p.dim_h = -1; p.dim_n = -1;
+      dims[0] = L.Cin; dims[1] = L.Win; dims[2] = 1; dims[3] = 1; dims[4] = 1;
+      str[0] = L.Cin * E; str[1] = str[0] * L.Win; str[2] = str[1]; str[3] = str[1];
+      box[0] = 64; box[1] = 128; box[2] = 1; box[3] = 1; box[4] = 1;
+      p.tiles_w = (L.Win + 127) / 128; p.tiles_h = 1; p.tiles_n = 1;
+      break;
+    }
+    case LK_CONV3_S1: {
+      FP_REQUIRE(L.Cin % 64 == 0, "CONV3_S1: Cin=%d not a multiple of 64", L.Cin);
+      Ho = L.Hin; Wo = L.Win;
+      taps = 9;
+      p.chunks_per_tap = L.Cin / 64;
+      if (Wo % 8 == 0 && Ho % 8 == 0) { p.bw = 8; p.bh = 8; p.bn = 2; }
+      else if (Wo % 4 == 0 && Ho % 4 == 0) { p.bw = 4; p.bh = 4; p.bn = 8; }
+      else FP_REQUIRE(false, "CONV3_S1: unsupported spatial size %dx%d", Ho, Wo);
+      p.dim_w = 1; p.dim_h = 2; p.dim_n = 3;
+      dims[0] = L.Cin; dims[1] = L.Win; dims[2] = L.Hin; dims[3] = L.n_img; dims[4] = 1;
+      str[0] = L.Cin * E; str[1] = str[0] * L.Win; str[2] = str[1] * L.Hin; str[3] = str[2] * L.n_img;
+      box[0] = 64; box[1] = p.bw; box[2] = p.bh; box[3] = p.bn; box[4] = 1;
+      for (int r = 0; r < 3; ++r)
+        for (int s = 0; s < 3; ++s) {
+          p.tap_off[r * 3 + s][1] = (short)(s - 1);
+          p.tap_off[r * 3 + s][2] = (short)(r - 1);
+        }
+      p.tiles_w = Wo / p.bw; p.tiles_h = Ho / p.bh; p.tiles_n = (L.n_img + p.bn - 1) / p.bn;
+      break;
+    }
+    case LK_CONV3_S2: {
+      FP_REQUIRE(L.Cin % 64 == 0, "CONV3_S2: Cin=%d not a multiple of 64", L.Cin);
+      FP_REQUIRE(L.Hin % 2 == 0 && L.Win % 2 == 0, "CONV3_S2: odd input size");
+      Ho = L.Hin / 2; Wo = L.Win / 2;
+      taps = 9;
+      p.chunks_per_tap = L.Cin / 64;
+      if (Wo % 8 == 0 && Ho % 8 == 0) { p.bw = 8; p.bh = 8; p.bn = 2; }
+      else if (Wo % 4 == 0 && Ho % 4 == 0) { p.bw = 4; p.bh = 4; p.bn = 8; }
+      else FP_REQUIRE(false, "CONV3_S2: unsupported output size %dx%d", Ho, Wo);
+      p.dim_w = 1; p.dim_h = 3; p.dim_n = 4;
+      // view (N, H, W, C) as (N, H/2, 2, W/2, [2, C]): every (tap, chunk) is a dense box
+      dims[0] = 2 * L.Cin; dims[1] = Wo; dims[2] = 2; dims[3] = Ho; dims[4] = L.n_img;
+      str[0] = 2 * L.Cin * E; str[1] = (uint64_t)L.Win * L.Cin * E; str[2] = 2 * str[1];
+      str[3] = (uint64_t)L.Hin * L.Win * L.Cin * E;
+      box[0] = 64; box[1] = p.bw; box[2] = 1; box[3] = p.bh; box[4] = p.bn;
+      for (int r = 0; r < 3; ++r)
+        for (int s = 0; s < 3; ++s) {
+          const int t = r * 3 + s;
+          // input row 2i + r - 1: r=0 -> (i-1, phase 1), r=1 -> (i, 0), r=2 -> (i, 1)
+          p.tap_off[t][0] = (short)((s == 1 ? 0 : 1) * L.Cin);
+          p.tap_off[t][1] = (short)(s == 0 ? -1 : 0);
+          p.tap_off[t][2] = (short)(r == 1 ? 0 : 1);
+          p.tap_off[t][3] = (short)(r == 0 ? -1 : 0);
+        }
+      p.tiles_w = Wo / p.bw; p.tiles_h = Ho / p.bh; p.tiles_n = (L.n_img + p.bn - 1) / p.bn;
+      break;
+    }
+    case LK_CONV7_S2: {
+      FP_REQUIRE(L.Cin == 8, "CONV7_S2: input must be channel-padded to 8");
+      FP_REQUIRE(L.Hin % 16 == 0 && L.Win % 32 == 0, "CONV7_S2: unsupported size");
+      Ho = L.Hin / 2; Wo = L.Win / 2;
+      taps = 7;
+      p.chunks_per_tap = 1;
+      p.bw = 16; p.bh = 8; p.bn = 1;
+      p.dim_w = 1; p.dim_h = 2; p.dim_n = 4;
+      const uint64_t Hp = L.Hin + 6, Wp = L.Win + 8;
+      // per (output pixel, filter row r): 64 contiguous fp16 = input pixels 2j..2j+7 (8 ch each) of
+      // padded row 2i + r.  Overlapping strides: j advances 2 pixels (32 B), i advances 2 rows.
+      dims[0] = 64; dims[1] = Wo; dims[2] = Ho; dims[3] = 7; dims[4] = L.n_img;
+      str[0] = 2 * 8 * E; str[1] = 2 * Wp * 8 * E; str[2] = Wp * 8 * E; str[3] = Hp * Wp * 8 * E;
+      box[0] = 64; box[1] = 16; box[2] = 8; box[3] = 1; box[4] = 1;
+      for (int r = 0; r < 7; ++r) p.tap_off[r][3] = (short)r;
+      p.tiles_w = Wo / 16; p.tiles_h = Ho / 8; p.tiles_n = L.n_img;
+      break;
+    }
+    default:
+      FP_REQUIRE(false, "unknown layer kind %d", L.kind);
+  }
+  ktot = (L.kind == LK_CONV7_S2) ? 7 * 64 : taps * L.Cin;
+  p.num_kb = ktot / 64;
+  p.lg_bw = ilog2(p.bw);
+  p.lg_bh = ilog2(p.bh);
+
+  if (L.Cout % 256 == 0) BN = 256;
+  else if (L.Cout % 128 == 0) BN = 128;
+  else if (L.Cout % 64 == 0) BN = 64;
+  else FP_REQUIRE(false, "Cout=%d must be a multiple of 64", L.Cout);
+  p.n_tiles_n = L.Cout / BN;
+  p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles_n;
+  p.Ho = Ho; p.Wo = Wo; p.n_img = L.n_img; p.Cout = L.Cout;
+  p.bias = L.bias;
+  p.res = reinterpret_cast<const __half*>(L.res);
+  p.res_ld = L.res_ld;
+  p.out = reinterpret_cast<__half*>(L.out);
+  p.out_ld = L.out_ld;
+  p.out_split = L.out_split;
+  p.post_add = L.post_add;
+  p.relu = L.relu;
+  FP_REQUIRE(L.out_ld % 8 == 0 && (!L.res || L.res_ld % 8 == 0), "out_ld / res_ld must be multiples of 8");
+  if (p.total_tiles == 0) return 0;
+
+  int rc = encode_map(&ma, L.in, 5, dims, str, box);
+  if (rc) return rc;
+  uint64_t wd[2] = {(uint64_t)ktot, (uint64_t)L.Cout};
+  uint64_t ws[1] = {(uint64_t)ktot * E};
+  uint32_t wb[2] = {64, (uint32_t)BN};
+  rc = encode_map(&mb, L.w, 2, wd, ws, wb);
+  if (rc) return rc;
+
+  switch (BN) {
+    case 256: return launch_bn<256>(ma, mb, p, stream);
+    case 128: return launch_bn<128>(ma, mb, p, stream);
+    default: return launch_bn<64>(ma, mb, p, stream);
+  }
+}
+
+}  // namespace fp
