@@ -1,0 +1,631 @@
+// fp_api.cu — the product C ABI (include/fpose.h): context, weights, mesh, frame, and the per-frame
+// hot loop (crops -> encoder -> heads -> pose update, K times; then scoring) enqueued on one stream
+// with no host synchronisation.
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/fpose.h"
+#include "fp_attn.cuh"
+#include "fp_common.cuh"
+#include "fp_crop.cuh"
+#include "fp_depth.cuh"
+#include "fp_gemm.cuh"
+
+namespace fp {
+const char* get_last_error();
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+static int dev_alloc(DevBuf& b, size_t bytes, bool zero = false) {
+  if (b.bytes >= bytes && b.p) return 0;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.bytes = 0;
+  FP_CUDA_OK(cudaMalloc(&b.p, bytes));
+  b.bytes = bytes;
+  if (zero) FP_CUDA_OK(cudaMemset(b.p, 0, bytes));
+  return 0;
+}
+
+struct Tensor {
+  void* p = nullptr;
+  int dtype = 0;  // 0 = f32, 1 = f16
+  long long numel = 0;
+};
+
+struct Net {
+  std::map<std::string, Tensor> t;
+  bool loaded = false;
+  const __half* h(const char* name) const { return reinterpret_cast<const __half*>(t.at(name).p); }
+  const float* f(const char* name) const { return reinterpret_cast<const float*>(t.at(name).p); }
+};
+
+constexpr int S = 160;
+constexpr int T = 400;
+constexpr size_t kCropImg = (size_t)(S + 6) * (S + 8) * 8;  // fp16 elements per padded crop image
+
+}  // namespace fp
+
+struct fp_ctx {
+  int device = 0;
+  fp::Net net[2];  // 0 = refiner, 1 = scorer
+  // mesh
+  fp::DevBuf vpos, vnrm, vuv, vcol, faces, tex;
+  int V = 0, F = 0, Ht = 0, Wt = 0;
+  bool has_tex = false, has_mesh = false;
+  float diameter = 0.f, crop_ratio = 1.2f, rot_normalizer = 0.3490658503988659f;
+  // frame
+  fp::DevBuf rgb_raw, rgba, depth_raw, depth_a, depth_b, xyz;
+  const float* depth_cur = nullptr;
+  float K[9] = {0};
+  int H = 0, W = 0;
+  bool has_frame = false;
+  // workspaces (sized for cap_n hypotheses)
+  int cap_n = 0;
+  fp::DevBuf crops, act0, a1, a2, a3, ab0, ab1, ab2, c0, c1, c2, tok, qkv, att, x1pre, x1, ff, x2pre;
+  fp::DevBuf head_out, poses_a, poses_b, feats, tail_qkv, tail_attn, tail_proj, scores, best;
+  int tail_cap = 0;
+  float lin_b_host = 0.f;  // scorer linear.bias, kept on the host so the tail launch never syncs
+};
+
+namespace fp {
+
+static int ensure_capacity(fp_ctx* c, int N) {
+  if (N <= c->cap_n) return 0;
+  const size_t n = (size_t)N;
+  int rc = 0;
+  // the crop buffer is zeroed once: the 3-pixel border is never written afterwards
+  rc |= dev_alloc(c->crops, 2 * n * kCropImg * 2, true);
+  rc |= dev_alloc(c->act0, 2 * n * 80 * 80 * 64 * 2);
+  rc |= dev_alloc(c->a1, 2 * n * 1600 * 128 * 2);
+  rc |= dev_alloc(c->a2, 2 * n * 1600 * 128 * 2);
+  rc |= dev_alloc(c->a3, 2 * n * 1600 * 128 * 2);
+  rc |= dev_alloc(c->ab0, n * 1600 * 256 * 2);
+  rc |= dev_alloc(c->ab1, n * 1600 * 256 * 2);
+  rc |= dev_alloc(c->ab2, n * 1600 * 256 * 2);
+  rc |= dev_alloc(c->c0, n * T * 512 * 2);
+  rc |= dev_alloc(c->c1, n * T * 512 * 2);
+  rc |= dev_alloc(c->c2, n * T * 512 * 2);
+  rc |= dev_alloc(c->tok, n * T * 512 * 2);
+  rc |= dev_alloc(c->qkv, n * T * 3072 * 2);
+  rc |= dev_alloc(c->att, 2 * n * T * 512 * 2);
+  rc |= dev_alloc(c->x1pre, n * T * 512 * 2);
+  rc |= dev_alloc(c->x1, n * T * 512 * 2);
+  rc |= dev_alloc(c->ff, n * T * 512 * 2);
+  rc |= dev_alloc(c->x2pre, n * T * 512 * 2);
+  rc |= dev_alloc(c->head_out, 2 * n * 3 * 4);
+  rc |= dev_alloc(c->poses_a, n * 16 * 4);
+  rc |= dev_alloc(c->poses_b, n * 16 * 4);
+  rc |= dev_alloc(c->feats, n * 512 * 4);
+  if (rc) return -2;
+  c->cap_n = N;
+  return 0;
+}
+
+static int ensure_tail(fp_ctx* c, int L) {
+  if (L <= c->tail_cap) return 0;
+  int rc = 0;
+  rc |= dev_alloc(c->tail_qkv, (size_t)L * 1536 * 4);
+  rc |= dev_alloc(c->tail_attn, (size_t)L * 512 * 4);
+  rc |= dev_alloc(c->tail_proj, (size_t)L * 512 * 4);
+  rc |= dev_alloc(c->scores, (size_t)L * 4);
+  rc |= dev_alloc(c->best, 16);
+  if (rc) return -2;
+  c->tail_cap = L;
+  return 0;
+}
+
+static GemmLayer mk(int kind, int n_img, int H, int W, int Cin, int Cout, const void* in, const __half* w,
+                    const float* b, void* out, int relu, const void* res = nullptr, int out_ld = 0, int out_split = 0,
+                    const float* post_add = nullptr) {
+  GemmLayer L;
+  L.kind = kind;
+  L.n_img = n_img;
+  L.Hin = H;
+  L.Win = W;
+  L.Cin = Cin;
+  L.Cout = Cout;
+  L.in = in;
+  L.w = w;
+  L.bias = b;
+  L.res = res;
+  L.res_ld = Cout;
+  L.out = out;
+  L.out_ld = out_ld ? out_ld : Cout;
+  L.out_split = out_split;
+  L.post_add = post_add;
+  L.relu = relu;
+  return L;
+}
+
+#define FP_TRY(expr)         \
+  do {                       \
+    int _rc = (expr);        \
+    if (_rc) return _rc;     \
+  } while (0)
+
+// crops [2N][166][168][8] -> tokens [N][400][512] (+ positional embedding)
+static int run_encoder(fp_ctx* c, const Net& net, const __half* crops, int N, cudaStream_t st) {
+  char wn[32], bn[32];
+  auto W = [&](int i) { snprintf(wn, sizeof wn, "enc.%d.w", i); return net.h(wn); };
+  auto B = [&](int i) { snprintf(bn, sizeof bn, "enc.%d.b", i); return net.f(bn); };
+  const int M = 2 * N;
+  FP_TRY(gemm_layer_launch(mk(LK_CONV7_S2, M, S, S, 8, 64, crops, W(0), B(0), c->act0.p, 1), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S2, M, 80, 80, 64, 128, c->act0.p, W(1), B(1), c->a1.p, 1), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, M, 40, 40, 128, 128, c->a1.p, W(2), B(2), c->a2.p, 1), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, M, 40, 40, 128, 128, c->a2.p, W(3), B(3), c->a3.p, 1, c->a1.p), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, M, 40, 40, 128, 128, c->a3.p, W(4), B(4), c->a2.p, 1), st));
+  // last encodeA layer writes straight into the 256-channel concat buffer (refine_network.py:85)
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, M, 40, 40, 128, 128, c->a2.p, W(5), B(5), c->ab0.p, 1, c->a3.p, 256, N), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, N, 40, 40, 256, 256, c->ab0.p, W(6), B(6), c->ab1.p, 1), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, N, 40, 40, 256, 256, c->ab1.p, W(7), B(7), c->ab2.p, 1, c->ab0.p), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, N, 40, 40, 256, 256, c->ab2.p, W(8), B(8), c->ab1.p, 1), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, N, 40, 40, 256, 256, c->ab1.p, W(9), B(9), c->ab0.p, 1, c->ab2.p), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S2, N, 40, 40, 256, 512, c->ab0.p, W(10), B(10), c->c0.p, 1), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, N, 20, 20, 512, 512, c->c0.p, W(11), B(11), c->c1.p, 1), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, N, 20, 20, 512, 512, c->c1.p, W(12), B(12), c->c2.p, 1, c->c0.p), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, N, 20, 20, 512, 512, c->c2.p, W(13), B(13), c->c1.p, 1), st));
+  FP_TRY(gemm_layer_launch(
+      mk(LK_CONV3_S1, N, 20, 20, 512, 512, c->c1.p, W(14), B(14), c->tok.p, 1, c->c2.p, 0, 0, net.f("pe")), st));
+  return 0;
+}
+
+// tokens -> (trans, rot) raw network outputs, [2][N][3] fp32 in head_out
+static int run_refine_heads(fp_ctx* c, const Net& net, int N, cudaStream_t st) {
+  const int M = N * T;
+  // both heads' in_proj as one GEMM: [M,512] x [3072,512]^T
+  FP_TRY(gemm_layer_launch(mk(LK_LINEAR, 1, 1, M, 512, 3072, c->tok.p, net.h("heads.in_w"), net.f("heads.in_b"), c->qkv.p, 0), st));
+  AttnParams ap;
+  ap.qkv = reinterpret_cast<const __half*>(c->qkv.p);
+  ap.ld = 3072;
+  ap.q_off = 0;
+  ap.k_off = 512;
+  ap.v_off = 1024;
+  ap.group_col_stride = 1536;
+  ap.n_groups = 2;
+  ap.out = reinterpret_cast<__half*>(c->att.p);
+  ap.ld_out = 512;
+  ap.out_group_stride = (size_t)M * 512;
+  ap.B = N;
+  ap.T = T;
+  ap.n_heads = 4;
+  ap.scale = 0.08838834764831845f;
+  FP_TRY(attn_core_launch(ap, st));
+  for (int g = 0; g < 2; ++g) {
+    char nm[48];
+    auto H = [&](const char* s) { snprintf(nm, sizeof nm, "head%d.%s", g, s); return net.h(nm); };
+    auto Fp = [&](const char* s) { snprintf(nm, sizeof nm, "head%d.%s", g, s); return net.f(nm); };
+    const __half* att_g = reinterpret_cast<const __half*>(c->att.p) + (size_t)g * M * 512;
+    const __half* w;
+    const float* b;
+    w = H("out_w"); b = Fp("out_b");
+    FP_TRY(gemm_layer_launch(mk(LK_LINEAR, 1, 1, M, 512, 512, att_g, w, b, c->x1pre.p, 0, c->tok.p), st));
+    const float* g1 = Fp("ln1_g");
+    const float* b1 = Fp("ln1_b");
+    FP_TRY(layernorm_launch(reinterpret_cast<const __half*>(c->x1pre.p), reinterpret_cast<__half*>(c->x1.p), g1, b1, M, st));
+    w = H("ff1_w"); b = Fp("ff1_b");
+    FP_TRY(gemm_layer_launch(mk(LK_LINEAR, 1, 1, M, 512, 512, c->x1.p, w, b, c->ff.p, 1), st));
+    w = H("ff2_w"); b = Fp("ff2_b");
+    FP_TRY(gemm_layer_launch(mk(LK_LINEAR, 1, 1, M, 512, 512, c->ff.p, w, b, c->x2pre.p, 0, c->x1.p), st));
+    const float* g2 = Fp("ln2_g");
+    const float* b2 = Fp("ln2_b");
+    const float* fw = Fp("fin_w");
+    const float* fb = Fp("fin_b");
+    FP_TRY(head_final_launch(reinterpret_cast<const __half*>(c->x2pre.p), g2, b2, fw, fb,
+                             reinterpret_cast<float*>(c->head_out.p) + (size_t)g * N * 3, N, T, 3, st));
+  }
+  return 0;
+}
+
+// tokens -> per-hypothesis 512-d features (score_network.py:72-74)
+static int run_score_feats(fp_ctx* c, const Net& net, int N, float* feats, cudaStream_t st) {
+  const int M = N * T;
+  FP_TRY(gemm_layer_launch(mk(LK_LINEAR, 1, 1, M, 512, 1536, c->tok.p, net.h("att.in_w"), net.f("att.in_b"), c->qkv.p, 0), st));
+  AttnParams ap;
+  ap.qkv = reinterpret_cast<const __half*>(c->qkv.p);
+  ap.ld = 1536;
+  ap.q_off = 0;
+  ap.k_off = 512;
+  ap.v_off = 1024;
+  ap.group_col_stride = 0;
+  ap.n_groups = 1;
+  ap.out = reinterpret_cast<__half*>(c->att.p);
+  ap.ld_out = 512;
+  ap.out_group_stride = 0;
+  ap.B = N;
+  ap.T = T;
+  ap.n_heads = 4;
+  ap.scale = 0.08838834764831845f;
+  FP_TRY(attn_core_launch(ap, st));
+  FP_TRY(token_mean_proj_launch(reinterpret_cast<const __half*>(c->att.p), net.h("att.out_w"), net.f("att.out_b"), feats,
+                                N, T, st));
+  return 0;
+}
+
+static int make_crops(fp_ctx* c, const float* poses, int N, int mode, float* dbg, float* win, cudaStream_t st) {
+  FP_REQUIRE(c->has_mesh, "no mesh: call fp_set_mesh first");
+  FP_REQUIRE(c->has_frame, "no frame: call fp_set_frame first");
+  CropParams p;
+  p.poses = poses;
+  p.N = N;
+  p.fx = c->K[0];
+  p.fy = c->K[4];
+  p.cx = c->K[2];
+  p.cy = c->K[5];
+  p.H = c->H;
+  p.W = c->W;
+  p.r3 = (float)((double)c->diameter * (double)c->crop_ratio / 2.0);
+  p.inv_radius = 1.0f / (c->diameter / 2.0f);
+  p.znear = 0.001f;
+  p.vpos = reinterpret_cast<const float*>(c->vpos.p);
+  p.vnrm = reinterpret_cast<const float*>(c->vnrm.p);
+  p.vuv = c->has_tex ? reinterpret_cast<const float*>(c->vuv.p) : nullptr;
+  p.vcol = c->has_tex ? nullptr : reinterpret_cast<const float*>(c->vcol.p);
+  p.faces = reinterpret_cast<const int*>(c->faces.p);
+  p.F = c->F;
+  p.tex = c->has_tex ? reinterpret_cast<const uchar4*>(c->tex.p) : nullptr;
+  p.Ht = c->Ht;
+  p.Wt = c->Wt;
+  p.rgb = reinterpret_cast<const uchar4*>(c->rgba.p);
+  p.xyz_map = reinterpret_cast<const float*>(c->xyz.p);
+  p.depth = c->depth_cur;
+  p.mode = mode;
+  p.crops = reinterpret_cast<__half*>(c->crops.p);
+  p.dbg = dbg;
+  p.win_out = win;
+  return crop_launch(p, st);
+}
+
+}  // namespace fp
+
+using namespace fp;
+
+extern "C" {
+
+int fp_create(fp_ctx** out) {
+  if (!out) {
+    set_last_error("fp_create: null output");
+    return -1;
+  }
+  int dev = 0;
+  FP_CUDA_OK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  FP_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  FP_REQUIRE(prop.major == 10, "libfpose targets sm_100a (B200); device %d is sm_%d%d", dev, prop.major, prop.minor);
+  fp_ctx* c = new fp_ctx();
+  c->device = dev;
+  *out = c;
+  return 0;
+}
+
+int fp_destroy(fp_ctx* c) {
+  if (!c) return 0;
+  for (auto& net : c->net)
+    for (auto& kv : net.t) cudaFree(kv.second.p);
+  DevBuf* bufs[] = {&c->vpos, &c->vnrm, &c->vuv, &c->vcol, &c->faces, &c->tex, &c->rgb_raw, &c->rgba, &c->depth_raw,
+                    &c->depth_a, &c->depth_b, &c->xyz, &c->crops, &c->act0, &c->a1, &c->a2, &c->a3, &c->ab0, &c->ab1,
+                    &c->ab2, &c->c0, &c->c1, &c->c2, &c->tok, &c->qkv, &c->att, &c->x1pre, &c->x1, &c->ff, &c->x2pre,
+                    &c->head_out, &c->poses_a, &c->poses_b, &c->feats, &c->tail_qkv, &c->tail_attn, &c->tail_proj,
+                    &c->scores, &c->best};
+  for (DevBuf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  delete c;
+  return 0;
+}
+
+int fp_set_config(fp_ctx* c, float crop_ratio, float rot_normalizer) {
+  FP_REQUIRE(c, "null ctx");
+  c->crop_ratio = crop_ratio;
+  c->rot_normalizer = rot_normalizer;
+  return 0;
+}
+
+int fp_load_network(fp_ctx* c, int which, const fp_tensor_t* tensors, int n) {
+  FP_REQUIRE(c && tensors, "fp_load_network: null argument");
+  FP_REQUIRE(which == 0 || which == 1, "fp_load_network: which must be 0 (refiner) or 1 (scorer)");
+  Net& net = c->net[which];
+  for (auto& kv : net.t) cudaFree(kv.second.p);
+  net.t.clear();
+  net.loaded = false;
+  for (int i = 0; i < n; ++i) {
+    const fp_tensor_t& t = tensors[i];
+    FP_REQUIRE(t.name && t.data && t.numel > 0, "fp_load_network: bad tensor #%d", i);
+    Tensor d;
+    d.dtype = t.dtype;
+    d.numel = t.numel;
+    const size_t bytes = (size_t)t.numel * (t.dtype == 1 ? 2 : 4);
+    FP_CUDA_OK(cudaMalloc(&d.p, bytes));
+    FP_CUDA_OK(cudaMemcpy(d.p, t.data, bytes, cudaMemcpyHostToDevice));
+    net.t[t.name] = d;
+    if (which == 1 && std::string(t.name) == "lin.b" && t.dtype == 0) c->lin_b_host = *reinterpret_cast<const float*>(t.data);
+  }
+  // verify that everything the execution plan needs is present, with the right size
+  std::vector<std::pair<std::string, long long>> need;
+  const int cin[15] = {0, 64, 128, 128, 128, 128, 256, 256, 256, 256, 256, 512, 512, 512, 512};
+  const int cout[15] = {64, 128, 128, 128, 128, 128, 256, 256, 256, 256, 512, 512, 512, 512, 512};
+  for (int i = 0; i < 15; ++i) {
+    const long long k = i == 0 ? 7 * 64 : 9LL * cin[i];
+    need.push_back({"enc." + std::to_string(i) + ".w", k * cout[i]});
+    need.push_back({"enc." + std::to_string(i) + ".b", cout[i]});
+  }
+  need.push_back({"pe", 400LL * 512});
+  if (which == 0) {
+    need.push_back({"heads.in_w", 3072LL * 512});
+    need.push_back({"heads.in_b", 3072});
+    for (int g = 0; g < 2; ++g) {
+      const std::string h = "head" + std::to_string(g) + ".";
+      for (const char* s : {"out_w", "ff1_w", "ff2_w"}) need.push_back({h + s, 512LL * 512});
+      for (const char* s : {"out_b", "ff1_b", "ff2_b", "ln1_g", "ln1_b", "ln2_g", "ln2_b"}) need.push_back({h + s, 512});
+      need.push_back({h + "fin_w", 3LL * 512});
+      need.push_back({h + "fin_b", 3});
+    }
+  } else {
+    need.push_back({"att.in_w", 1536LL * 512});
+    need.push_back({"att.in_b", 1536});
+    need.push_back({"att.out_w", 512LL * 512});
+    need.push_back({"att.out_b", 512});
+    need.push_back({"cross.in_w", 1536LL * 512});
+    need.push_back({"cross.in_b", 1536});
+    need.push_back({"cross.out_w", 512LL * 512});
+    need.push_back({"cross.out_b", 512});
+    need.push_back({"lin.w", 512});
+    need.push_back({"lin.b", 1});
+  }
+  for (auto& nd : need) {
+    auto it = net.t.find(nd.first);
+    FP_REQUIRE(it != net.t.end(), "fp_load_network: tensor '%s' missing", nd.first.c_str());
+    FP_REQUIRE(it->second.numel == nd.second, "fp_load_network: tensor '%s' has %lld elements, expected %lld",
+               nd.first.c_str(), it->second.numel, nd.second);
+  }
+  net.loaded = true;
+  return 0;
+}
+
+int fp_set_mesh(fp_ctx* c, int V, int F, const float* pos, const float* nrm, const float* uv, const float* vcol,
+                const int* faces, const unsigned char* tex_rgb, int Ht, int Wt, float diameter) {
+  FP_REQUIRE(c && pos && nrm && faces, "fp_set_mesh: null argument");
+  FP_REQUIRE(V > 0 && F > 0 && diameter > 0.f, "fp_set_mesh: empty mesh");
+  FP_REQUIRE((uv && tex_rgb && Ht > 0 && Wt > 0) || vcol, "fp_set_mesh: need (uv + texture) or vertex colours");
+  for (int i = 0; i < 3 * F; ++i) FP_REQUIRE(faces[i] >= 0 && faces[i] < V, "fp_set_mesh: face index out of range");
+  c->has_mesh = false;
+  FP_TRY(dev_alloc(c->vpos, (size_t)V * 12));
+  FP_TRY(dev_alloc(c->vnrm, (size_t)V * 12));
+  FP_TRY(dev_alloc(c->faces, (size_t)F * 12));
+  FP_CUDA_OK(cudaMemcpy(c->vpos.p, pos, (size_t)V * 12, cudaMemcpyHostToDevice));
+  FP_CUDA_OK(cudaMemcpy(c->vnrm.p, nrm, (size_t)V * 12, cudaMemcpyHostToDevice));
+  FP_CUDA_OK(cudaMemcpy(c->faces.p, faces, (size_t)F * 12, cudaMemcpyHostToDevice));
+  c->has_tex = (uv && tex_rgb);
+  if (c->has_tex) {
+    FP_TRY(dev_alloc(c->vuv, (size_t)V * 8));
+    FP_CUDA_OK(cudaMemcpy(c->vuv.p, uv, (size_t)V * 8, cudaMemcpyHostToDevice));
+    std::vector<unsigned char> rgba((size_t)Ht * Wt * 4);
+    for (size_t i = 0; i < (size_t)Ht * Wt; ++i) {
+      rgba[4 * i] = tex_rgb[3 * i];
+      rgba[4 * i + 1] = tex_rgb[3 * i + 1];
+      rgba[4 * i + 2] = tex_rgb[3 * i + 2];
+      rgba[4 * i + 3] = 255;
+    }
+    FP_TRY(dev_alloc(c->tex, rgba.size()));
+    FP_CUDA_OK(cudaMemcpy(c->tex.p, rgba.data(), rgba.size(), cudaMemcpyHostToDevice));
+    c->Ht = Ht;
+    c->Wt = Wt;
+  } else {
+    FP_TRY(dev_alloc(c->vcol, (size_t)V * 12));
+    FP_CUDA_OK(cudaMemcpy(c->vcol.p, vcol, (size_t)V * 12, cudaMemcpyHostToDevice));
+  }
+  c->V = V;
+  c->F = F;
+  c->diameter = diameter;
+  c->has_mesh = true;
+  return 0;
+}
+
+int fp_set_frame(fp_ctx* c, const unsigned char* rgb, const float* depth, const float* K, int H, int W, int flags,
+                 float zfar, void* stream) {
+  FP_REQUIRE(c && rgb && depth && K, "fp_set_frame: null argument");
+  FP_REQUIRE(H > 0 && W > 0, "fp_set_frame: empty frame");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t npix = (size_t)H * W;
+  c->has_frame = false;
+  FP_TRY(dev_alloc(c->rgba, npix * 4));
+  FP_TRY(dev_alloc(c->depth_a, npix * 4));
+  FP_TRY(dev_alloc(c->depth_b, npix * 4));
+  FP_TRY(dev_alloc(c->xyz, npix * 12));
+  const unsigned char* rgb_dev = rgb;
+  const float* depth_dev = depth;
+  if (!(flags & FP_FRAME_ON_DEVICE)) {
+    FP_TRY(dev_alloc(c->rgb_raw, npix * 3));
+    FP_TRY(dev_alloc(c->depth_raw, npix * 4));
+    FP_CUDA_OK(cudaMemcpyAsync(c->rgb_raw.p, rgb, npix * 3, cudaMemcpyHostToDevice, st));
+    FP_CUDA_OK(cudaMemcpyAsync(c->depth_raw.p, depth, npix * 4, cudaMemcpyHostToDevice, st));
+    rgb_dev = reinterpret_cast<const unsigned char*>(c->rgb_raw.p);
+    depth_dev = reinterpret_cast<const float*>(c->depth_raw.p);
+  }
+  for (int i = 0; i < 9; ++i) c->K[i] = K[i];
+  c->H = H;
+  c->W = W;
+  FP_TRY(rgb_to_rgba_launch(rgb_dev, reinterpret_cast<uchar4*>(c->rgba.p), (int)npix, st));
+  if (flags & FP_FRAME_FILTER_DEPTH) {
+    // estimater.py:173-174: erode_depth(radius=2) then bilateral_filter_depth(radius=2)
+    FP_TRY(erode_depth_launch(depth_dev, reinterpret_cast<float*>(c->depth_a.p), H, W, 2, 0.001f, 0.8f, 100.f, st));
+    FP_TRY(bilateral_depth_launch(reinterpret_cast<const float*>(c->depth_a.p), reinterpret_cast<float*>(c->depth_b.p), H,
+                                  W, 2, 100.f, 2.f, 100000.f, st));
+    c->depth_cur = reinterpret_cast<const float*>(c->depth_b.p);
+  } else {
+    FP_CUDA_OK(cudaMemcpyAsync(c->depth_b.p, depth_dev, npix * 4, cudaMemcpyDeviceToDevice, st));
+    c->depth_cur = reinterpret_cast<const float*>(c->depth_b.p);
+  }
+  FP_TRY(depth_to_xyz_launch(c->depth_cur, reinterpret_cast<float*>(c->xyz.p), H, W, K[0], K[4], K[2], K[5], zfar, st));
+  c->has_frame = true;
+  return 0;
+}
+
+int fp_get_depth(fp_ctx* c, float* depth_out_dev, float* xyz_out_dev, void* stream) {
+  FP_REQUIRE(c && c->has_frame, "fp_get_depth: no frame");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t npix = (size_t)c->H * c->W;
+  if (depth_out_dev) FP_CUDA_OK(cudaMemcpyAsync(depth_out_dev, c->depth_cur, npix * 4, cudaMemcpyDeviceToDevice, st));
+  if (xyz_out_dev) FP_CUDA_OK(cudaMemcpyAsync(xyz_out_dev, c->xyz.p, npix * 12, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int fp_make_crops(fp_ctx* c, const float* poses, int N, int mode, void* crops_out, float* dbg_out, float* win_out,
+                  void* stream) {
+  FP_REQUIRE(c && poses && N >= 0, "fp_make_crops: bad argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (N == 0) return 0;
+  FP_TRY(ensure_capacity(c, N));
+  FP_TRY(make_crops(c, poses, N, mode, dbg_out, win_out, st));
+  if (crops_out)
+    FP_CUDA_OK(cudaMemcpyAsync(crops_out, c->crops.p, 2 * (size_t)N * kCropImg * 2, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int fp_op_refine_net(fp_ctx* c, const void* crops, int N, float* trans_out, float* rot_out, void* stream) {
+  FP_REQUIRE(c && crops && trans_out && rot_out, "fp_op_refine_net: null argument");
+  FP_REQUIRE(c->net[0].loaded, "refiner weights not loaded");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (N == 0) return 0;
+  FP_TRY(ensure_capacity(c, N));
+  FP_TRY(run_encoder(c, c->net[0], reinterpret_cast<const __half*>(crops), N, st));
+  FP_TRY(run_refine_heads(c, c->net[0], N, st));
+  const float* ho = reinterpret_cast<const float*>(c->head_out.p);
+  FP_CUDA_OK(cudaMemcpyAsync(trans_out, ho, (size_t)N * 12, cudaMemcpyDeviceToDevice, st));
+  FP_CUDA_OK(cudaMemcpyAsync(rot_out, ho + (size_t)N * 3, (size_t)N * 12, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int fp_op_score_feats(fp_ctx* c, const void* crops, int N, float* feats_out, void* stream) {
+  FP_REQUIRE(c && crops && feats_out, "fp_op_score_feats: null argument");
+  FP_REQUIRE(c->net[1].loaded, "scorer weights not loaded");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (N == 0) return 0;
+  FP_TRY(ensure_capacity(c, N));
+  FP_TRY(run_encoder(c, c->net[1], reinterpret_cast<const __half*>(crops), N, st));
+  FP_TRY(run_score_feats(c, c->net[1], N, feats_out, st));
+  return 0;
+}
+
+int fp_op_tokens(fp_ctx* c, int which, const void* crops, int N, void* tokens_out, void* stream) {
+  FP_REQUIRE(c && crops && tokens_out && (which == 0 || which == 1), "fp_op_tokens: bad argument");
+  FP_REQUIRE(c->net[which].loaded, "weights not loaded");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (N == 0) return 0;
+  FP_TRY(ensure_capacity(c, N));
+  FP_TRY(run_encoder(c, c->net[which], reinterpret_cast<const __half*>(crops), N, st));
+  FP_CUDA_OK(cudaMemcpyAsync(tokens_out, c->tok.p, (size_t)N * T * 512 * 2, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int fp_refine(fp_ctx* c, const float* poses_in, int N, int iterations, float* poses_out, float* last_trans,
+              float* last_rot, void* stream) {
+  FP_REQUIRE(c && poses_in && poses_out && N >= 0 && iterations >= 0, "fp_refine: bad argument");
+  FP_REQUIRE(c->net[0].loaded, "refiner weights not loaded");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (N == 0) return 0;
+  FP_TRY(ensure_capacity(c, N));
+  float* cur = reinterpret_cast<float*>(c->poses_a.p);
+  float* nxt = reinterpret_cast<float*>(c->poses_b.p);
+  FP_CUDA_OK(cudaMemcpyAsync(cur, poses_in, (size_t)N * 64, cudaMemcpyDeviceToDevice, st));
+  const float* ho = reinterpret_cast<const float*>(c->head_out.p);
+  for (int it = 0; it < iterations; ++it) {
+    FP_TRY(make_crops(c, cur, N, 0, nullptr, nullptr, st));
+    FP_TRY(run_encoder(c, c->net[0], reinterpret_cast<const __half*>(c->crops.p), N, st));
+    FP_TRY(run_refine_heads(c, c->net[0], N, st));
+    const bool last = it == iterations - 1;
+    FP_TRY(pose_update_launch(cur, ho, ho + (size_t)N * 3, nxt, last ? last_trans : nullptr, last ? last_rot : nullptr, N,
+                              c->diameter / 2.0f, c->rot_normalizer, st));
+    float* t = cur;
+    cur = nxt;
+    nxt = t;
+  }
+  FP_CUDA_OK(cudaMemcpyAsync(poses_out, cur, (size_t)N * 64, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int fp_score_features(fp_ctx* c, const float* poses, int N, float* feats_out, void* stream) {
+  FP_REQUIRE(c && poses && feats_out && N >= 0, "fp_score_features: bad argument");
+  FP_REQUIRE(c->net[1].loaded, "scorer weights not loaded");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (N == 0) return 0;
+  FP_TRY(ensure_capacity(c, N));
+  FP_TRY(make_crops(c, poses, N, 1, nullptr, nullptr, st));
+  FP_TRY(run_encoder(c, c->net[1], reinterpret_cast<const __half*>(c->crops.p), N, st));
+  FP_TRY(run_score_feats(c, c->net[1], N, feats_out, st));
+  return 0;
+}
+
+int fp_score_tail(fp_ctx* c, const float* feats, int L, float* scores_out, int* best_out, void* stream) {
+  FP_REQUIRE(c && feats && scores_out && L >= 0, "fp_score_tail: bad argument");
+  FP_REQUIRE(c->net[1].loaded, "scorer weights not loaded");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (L == 0) return 0;
+  FP_TRY(ensure_tail(c, L));
+  const Net& net = c->net[1];
+  ScoreTailParams p;
+  p.feats = feats;
+  p.L = L;
+  p.w_in = net.h("cross.in_w");
+  p.b_in = net.f("cross.in_b");
+  p.w_out = net.h("cross.out_w");
+  p.b_out = net.f("cross.out_b");
+  p.w_lin = net.f("lin.w");
+  p.b_lin = c->lin_b_host;
+  p.offset = 100.f;
+  p.qkv = reinterpret_cast<float*>(c->tail_qkv.p);
+  p.attn = reinterpret_cast<float*>(c->tail_attn.p);
+  p.proj = reinterpret_cast<float*>(c->tail_proj.p);
+  p.scores = scores_out;
+  p.best = best_out;
+  return score_tail_launch(p, st);
+}
+
+int fp_score(fp_ctx* c, const float* poses, int N, float* scores_out, int* best_out, void* stream) {
+  FP_REQUIRE(c && poses && scores_out && N >= 0, "fp_score: bad argument");
+  if (N == 0) return 0;
+  FP_TRY(ensure_capacity(c, N));
+  FP_TRY(fp_score_features(c, poses, N, reinterpret_cast<float*>(c->feats.p), stream));
+  return fp_score_tail(c, reinterpret_cast<const float*>(c->feats.p), N, scores_out, best_out, stream);
+}
+
+int fp_register(fp_ctx* c, const float* poses_host, int N, int iterations, float* poses_out_host, float* scores_out_host,
+                int* best_out_host, void* stream) {
+  FP_REQUIRE(c && poses_host && poses_out_host && scores_out_host && best_out_host && N > 0, "fp_register: bad argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  FP_TRY(ensure_capacity(c, N));
+  FP_TRY(ensure_tail(c, N));
+  // poses_b is the loop's ping-pong partner; stage the input in `feats`' neighbour: use tail_proj as scratch
+  float* pin = reinterpret_cast<float*>(c->tail_proj.p);  // >= N*512 floats
+  float* pout = pin + (size_t)N * 16;
+  FP_CUDA_OK(cudaMemcpyAsync(pin, poses_host, (size_t)N * 64, cudaMemcpyHostToDevice, st));
+  FP_TRY(fp_refine(c, pin, N, iterations, pout, nullptr, nullptr, stream));
+  // keep the refined poses out of the tail's scratch: copy to poses_b's idle half (poses_a/b are free now)
+  float* refined = reinterpret_cast<float*>(c->poses_b.p);
+  FP_CUDA_OK(cudaMemcpyAsync(refined, pout, (size_t)N * 64, cudaMemcpyDeviceToDevice, st));
+  FP_TRY(fp_score(c, refined, N, reinterpret_cast<float*>(c->scores.p), reinterpret_cast<int*>(c->best.p), stream));
+  FP_CUDA_OK(cudaMemcpyAsync(poses_out_host, refined, (size_t)N * 64, cudaMemcpyDeviceToHost, st));
+  FP_CUDA_OK(cudaMemcpyAsync(scores_out_host, c->scores.p, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+  FP_CUDA_OK(cudaMemcpyAsync(best_out_host, c->best.p, 4, cudaMemcpyDeviceToHost, st));
+  FP_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int fp_op_depth_filter(const float* depth_dev, float* out_dev, int H, int W, int which, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  FP_REQUIRE(depth_dev && out_dev && H > 0 && W > 0, "fp_op_depth_filter: bad argument");
+  if (which == 0) return erode_depth_launch(depth_dev, out_dev, H, W, 2, 0.001f, 0.8f, 100.f, st);
+  return bilateral_depth_launch(depth_dev, out_dev, H, W, 2, 100.f, 2.f, 100000.f, st);
+}
+
+int fp_op_pose_update(const float* poses_in, const float* trans, const float* rot, float* poses_out, int N,
+                      float mesh_diameter, float rot_normalizer, void* stream) {
+  FP_REQUIRE(poses_in && trans && rot && poses_out, "fp_op_pose_update: null argument");
+  return pose_update_launch(poses_in, trans, rot, poses_out, nullptr, nullptr, N, mesh_diameter / 2.0f, rot_normalizer,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,560 @@
+// fp_attn.cu — the non-GEMM parts of the transformer heads and the scorer tail.
+//
+//   attn_core_kernel     softmax(Q K^T / sqrt(128)) V for T = 400 tokens, 4 heads of 128
+//                        (nn.MultiheadAttention inside nn.TransformerEncoderLayer, refine_network.py:56-70;
+//                        score_network.py:53, :72).  Flash-style, one CTA per (sequence, head): K and V
+//                        of the head live in shared memory, each warp owns 16-query-row tiles.
+//                        Tensor-core path here is mma.sync m16n8k16 (2.7 % of the network FLOPs); the
+//                        projections around it run on the tcgen05 kernel (fp_gemm.cu).
+//   layernorm_kernel     row LayerNorm over 512 channels (norm1 of the encoder layer; the residual add is
+//                        fused in the producing GEMM's epilogue).
+//   head_final_kernel    norm2 -> mean over the 400 tokens -> Linear(512, 3)  (refine_network.py:89-90;
+//                        the mean commutes with the final linear layer).
+//   token_mean_proj      scorer: mean over tokens of the attention output, then out_proj (score_network.py:72-74).
+//   cross_attn_kernel    scorer: attention across the L pose hypotheses (score_network.py:85-86).
+//   score_linear_kernel  Linear(512,1) + first-max argmax (score_network.py:88, predict_score.py:196,
+//                        estimater.py:226).
+//   pose_update_kernel   predict_pose_refine.py:195-231 + Utils.py:848-855 + pytorch3d so3_exp_map.
+#include "fp_attn.cuh"
+
+#include <mma.h>
+
+#include "fp_common.cuh"
+#include "fp_gemm.cuh"
+
+namespace fp {
+
+// ------------------------------------------------------------------------------------------------
+// attention core
+// ------------------------------------------------------------------------------------------------
+constexpr int kT = 400;            // tokens (20 x 20)
+constexpr int kDh = 128;           // head dim
+constexpr int kKvStride = 136;     // halfs per smem row (272 B): conflict-free ldmatrix
+constexpr int kKeyBlock = 80;      // keys per online-softmax step
+constexpr int kAttnWarps = 8;
+constexpr int kAttnSmem = 2 * kT * kKvStride * 2;
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src));
+}
+
+__global__ void __launch_bounds__(kAttnWarps * 32, 1) attn_core_kernel(const AttnParams p) {
+  extern __shared__ __align__(16) uint8_t attn_smem[];
+  __half* sK = reinterpret_cast<__half*>(attn_smem);
+  __half* sV = sK + kT * kKvStride;
+  const int b = blockIdx.x, h = blockIdx.y, g = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const __half* qkv = p.qkv + (size_t)b * kT * p.ld + (size_t)g * p.group_col_stride + h * kDh;
+  const __half* gq = qkv + p.q_off;
+  const __half* gk = qkv + p.k_off;
+  const __half* gv = qkv + p.v_off;
+
+  // stage K, V of this (sequence, head) in shared memory
+  for (int c = tid; c < kT * 16; c += kAttnWarps * 32) {
+    const int row = c >> 4, ch = c & 15;
+    cp_async16(sK + row * kKvStride + ch * 8, gk + (size_t)row * p.ld + ch * 8);
+    cp_async16(sV + row * kKvStride + ch * 8, gv + (size_t)row * p.ld + ch * 8);
+  }
+  asm volatile("cp.async.commit_group;");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  const int gq_row = lane >> 2, tq = lane & 3;
+  const float sl2 = p.scale * 1.4426950408889634f;  // softmax scale folded into exp2
+  __half* outp = p.out + (size_t)g * p.out_group_stride + (size_t)b * kT * p.ld_out + h * kDh;
+
+  for (int rt = warp; rt < kT / 16; rt += kAttnWarps) {
+    const int row0 = rt * 16;
+    // Q fragments for the 8 k-steps
+    uint32_t qf[8][4];
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const __half* q0 = gq + (size_t)(row0 + gq_row) * p.ld + kk * 16 + tq * 2;
+      const __half* q1 = q0 + (size_t)8 * p.ld;
+      qf[kk][0] = __ldg(reinterpret_cast<const uint32_t*>(q0));
+      qf[kk][1] = __ldg(reinterpret_cast<const uint32_t*>(q1));
+      qf[kk][2] = __ldg(reinterpret_cast<const uint32_t*>(q0 + 8));
+      qf[kk][3] = __ldg(reinterpret_cast<const uint32_t*>(q1 + 8));
+    }
+    float o[16][4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+    for (int kb = 0; kb < kT; kb += kKeyBlock) {
+      float s[kKeyBlock / 8][4];
+#pragma unroll
+      for (int i = 0; i < kKeyBlock / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+#pragma unroll
+        for (int nt = 0; nt < kKeyBlock / 16; ++nt) {
+          uint32_t kf[4];
+          const int key = kb + nt * 16 + (lane & 7) + ((lane >> 4) << 3);
+          const int col = kk * 16 + (((lane >> 3) & 1) << 3);
+          ldmatrix_x4(kf, sK + key * kKvStride + col);
+          mma_16816(s[2 * nt], qf[kk], kf[0], kf[1]);
+          mma_16816(s[2 * nt + 1], qf[kk], kf[2], kf[3]);
+        }
+      }
+      // online softmax (rows gq_row and gq_row + 8)
+      float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < kKeyBlock / 8; ++i) {
+        bm0 = fmaxf(bm0, fmaxf(s[i][0], s[i][1]));
+        bm1 = fmaxf(bm1, fmaxf(s[i][2], s[i][3]));
+      }
+      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+      const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);
+      const float c0 = exp2f((m0 - nm0) * sl2), c1 = exp2f((m1 - nm1) * sl2);
+      m0 = nm0;
+      m1 = nm1;
+      float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < kKeyBlock / 8; ++i) {
+        s[i][0] = exp2f((s[i][0] - m0) * sl2);
+        s[i][1] = exp2f((s[i][1] - m0) * sl2);
+        s[i][2] = exp2f((s[i][2] - m1) * sl2);
+        s[i][3] = exp2f((s[i][3] - m1) * sl2);
+        rs0 += s[i][0] + s[i][1];
+        rs1 += s[i][2] + s[i][3];
+      }
+      l0 = l0 * c0 + rs0;
+      l1 = l1 * c1 + rs1;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        o[i][0] *= c0;
+        o[i][1] *= c0;
+        o[i][2] *= c1;
+        o[i][3] *= c1;
+      }
+      // O += P V
+#pragma unroll
+      for (int ks = 0; ks < kKeyBlock / 16; ++ks) {
+        uint32_t pf[4];
+        pf[0] = pack_half2(s[2 * ks][0], s[2 * ks][1]);
+        pf[1] = pack_half2(s[2 * ks][2], s[2 * ks][3]);
+        pf[2] = pack_half2(s[2 * ks + 1][0], s[2 * ks + 1][1]);
+        pf[3] = pack_half2(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+        const int key = kb + ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) {
+          uint32_t vf[4];
+          ldmatrix_x4_trans(vf, sV + key * kKvStride + dt * 16 + ((lane >> 4) << 3));
+          mma_16816(o[2 * dt], pf, vf[0], vf[1]);
+          mma_16816(o[2 * dt + 1], pf, vf[2], vf[3]);
+        }
+      }
+    }
+    // finish: row sums across the quad, normalise, store
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float il0 = 1.f / l0, il1 = 1.f / l1;
+    __half* o0 = outp + (size_t)(row0 + gq_row) * p.ld_out + tq * 2;
+    __half* o1 = o0 + (size_t)8 * p.ld_out;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      *reinterpret_cast<uint32_t*>(o0 + i * 8) = pack_half2(o[i][0] * il0, o[i][1] * il0);
+      *reinterpret_cast<uint32_t*>(o1 + i * 8) = pack_half2(o[i][2] * il1, o[i][3] * il1);
+    }
+  }
+}
+
+int attn_core_launch(const AttnParams& p, cudaStream_t stream) {
+  FP_REQUIRE(p.T == kT && p.n_heads == 4, "attention core is specialised for T=400, 4 heads of 128 (got T=%d)", p.T);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FP_CUDA_OK(cudaFuncSetAttribute(attn_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    attr_set = true;
+  }
+  if (p.B == 0) return 0;
+  dim3 grid(p.B, p.n_heads, p.n_groups);
+  attn_core_kernel<<<grid, kAttnWarps * 32, kAttnSmem, stream>>>(p);
+  ++g_launch_count;
+  FP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm helpers: one warp per 512-channel row, 16 channels per lane
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_row16(const __half* row, int lane, float (&v)[16]) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(row + lane * 16));
+  const uint4 b = __ldg(reinterpret_cast<const uint4*>(row + lane * 16) + 1);
+  const __half2* ha = reinterpret_cast<const __half2*>(&a);
+  const __half2* hb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(ha[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+    const float2 g = __half22float2(hb[i]);
+    v[8 + 2 * i] = g.x;
+    v[8 + 2 * i + 1] = g.y;
+  }
+}
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+__device__ __forceinline__ void ln_row16(float (&v)[16], const float* gamma, const float* beta, int lane, float eps) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.f / 512.f);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float d = v[i] - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / 512.f) + eps);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = (v[i] - mean) * rstd * __ldg(gamma + lane * 16 + i) + __ldg(beta + lane * 16 + i);
+}
+
+__global__ void layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, int rows, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float v[16];
+  load_row16(x + (size_t)row * 512, lane, v);
+  ln_row16(v, gamma, beta, lane, eps);
+  uint32_t o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = pack_half2(v[2 * i], v[2 * i + 1]);
+  uint4* dst = reinterpret_cast<uint4*>(y + (size_t)row * 512 + lane * 16);
+  dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+  dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+int layernorm_launch(const __half* x, __half* y, const float* gamma, const float* beta, int rows, cudaStream_t stream) {
+  if (rows == 0) return 0;
+  layernorm_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, y, gamma, beta, rows, 1e-5f);
+  ++g_launch_count;
+  FP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// norm2 -> token mean -> Linear(512, out_dim<=8).  One CTA (8 warps) per sequence.
+__global__ void __launch_bounds__(256) head_final_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float* __restrict__ out, int T,
+                                                         int out_dim, float eps) {
+  __shared__ float acc[8][512];
+  __shared__ float meanv[512];
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = 0.f;
+  for (int t = warp; t < T; t += 8) {
+    float v[16];
+    load_row16(x + ((size_t)b * T + t) * 512, lane, v);
+    ln_row16(v, gamma, beta, lane, eps);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] += v[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[warp][lane * 16 + i] = a[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 512; c += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += acc[k][c];
+    meanv[c] = s / (float)T;
+  }
+  __syncthreads();
+  if (warp < out_dim) {
+    float s = 0.f;
+    for (int c = lane; c < 512; c += 32) s += meanv[c] * __ldg(w + warp * 512 + c);
+    s = warp_sum(s);
+    if (lane == 0) out[b * out_dim + warp] = s + bias[warp];
+  }
+}
+
+int head_final_launch(const __half* x, const float* gamma, const float* beta, const float* w, const float* bias,
+                      float* out, int B, int T, int out_dim, cudaStream_t stream) {
+  FP_REQUIRE(out_dim <= 8, "head_final: out_dim %d > 8", out_dim);
+  if (B == 0) return 0;
+  head_final_kernel<<<B, 256, 0, stream>>>(x, gamma, beta, w, bias, out, T, out_dim, 1e-5f);
+  ++g_launch_count;
+  FP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// scorer: feat[b] = out_proj(mean_t attn[b, t, :])   (mean commutes with the linear projection)
+__global__ void __launch_bounds__(256) token_mean_proj_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
+                                                              const float* __restrict__ bias, float* __restrict__ out,
+                                                              int T) {
+  __shared__ float acc[8][512];
+  __shared__ float meanv[512];
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = 0.f;
+  for (int t = warp; t < T; t += 8) {
+    float v[16];
+    load_row16(x + ((size_t)b * T + t) * 512, lane, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] += v[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[warp][lane * 16 + i] = a[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 512; c += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += acc[k][c];
+    meanv[c] = s / (float)T;
+  }
+  __syncthreads();
+  // 512 outputs, one warp per output row at a time
+  for (int o = warp; o < 512; o += 8) {
+    float v[16];
+    load_row16(w + (size_t)o * 512, lane, v);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += v[i] * meanv[lane * 16 + i];
+    s = warp_sum(s);
+    if (lane == 0) out[(size_t)b * 512 + o] = s + bias[o];
+  }
+}
+
+int token_mean_proj_launch(const __half* x, const __half* w, const float* bias, float* out, int B, int T,
+                           cudaStream_t stream) {
+  if (B == 0) return 0;
+  token_mean_proj_kernel<<<B, 256, 0, stream>>>(x, w, bias, out, T);
+  ++g_launch_count;
+  FP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scorer tail: attention across the L hypotheses (fp32 SIMT; 0.3 GFLOP total)
+// ------------------------------------------------------------------------------------------------
+// y[l, :] = in_proj(x[l, :]) : [L][512] fp32 -> [L][1536] fp32.  One CTA per row.
+__global__ void __launch_bounds__(256) rowwise_linear_kernel(const float* __restrict__ x, const __half* __restrict__ w,
+                                                             const float* __restrict__ bias, float* __restrict__ y,
+                                                             int n_out) {
+  __shared__ float xs[512];
+  const int l = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = threadIdx.x; c < 512; c += 256) xs[c] = x[(size_t)l * 512 + c];
+  __syncthreads();
+  for (int o = warp; o < n_out; o += 8) {
+    float v[16];
+    load_row16(w + (size_t)o * 512, lane, v);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += v[i] * xs[lane * 16 + i];
+    s = warp_sum(s);
+    if (lane == 0) y[(size_t)l * n_out + o] = s + bias[o];
+  }
+}
+
+// one CTA per query hypothesis, one warp per head
+__global__ void __launch_bounds__(128) cross_attn_kernel(const float* __restrict__ qkv, float* __restrict__ out, int L,
+                                                         float scale) {
+  extern __shared__ float sc[];  // [4][L]
+  const int q = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s = sc + h * L;
+  const float* qv = qkv + (size_t)q * 1536 + h * 128;
+  float qr[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) qr[i] = qv[lane * 4 + i];
+  float mx = -INFINITY;
+  for (int k = 0; k < L; ++k) {
+    const float4 kv = *reinterpret_cast<const float4*>(qkv + (size_t)k * 1536 + 512 + h * 128 + lane * 4);
+    float d = qr[0] * kv.x + qr[1] * kv.y + qr[2] * kv.z + qr[3] * kv.w;
+    d = warp_sum(d) * scale;
+    if (lane == 0) s[k] = d;
+    mx = fmaxf(mx, d);
+  }
+  __syncwarp();
+  float sum = 0.f;
+  for (int k = lane; k < L; k += 32) {
+    const float e = expf(s[k] - mx);
+    s[k] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  float o[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = 0; k < L; ++k) {
+    const float pk = s[k];
+    const float4 vv = *reinterpret_cast<const float4*>(qkv + (size_t)k * 1536 + 1024 + h * 128 + lane * 4);
+    o[0] += pk * vv.x;
+    o[1] += pk * vv.y;
+    o[2] += pk * vv.z;
+    o[3] += pk * vv.w;
+  }
+  const float inv = 1.f / sum;
+  float* op = out + (size_t)q * 512 + h * 128 + lane * 4;
+  op[0] = o[0] * inv;
+  op[1] = o[1] * inv;
+  op[2] = o[2] * inv;
+  op[3] = o[3] * inv;
+}
+
+// scores[l] = w . x[l] + b (+ offset);  then best = first index of the maximum
+__global__ void __launch_bounds__(1024) score_linear_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            float bias, float offset, float* __restrict__ scores,
+                                                            int* __restrict__ best, int L) {
+  __shared__ float sv[1024];
+  __shared__ int si[1024];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int l = warp; l < L; l += 32) {
+    float s = 0.f;
+    for (int c = lane; c < 512; c += 32) s += x[(size_t)l * 512 + c] * __ldg(w + c);
+    s = warp_sum(s);
+    if (lane == 0) scores[l] = s + bias + offset;
+  }
+  __syncthreads();
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int l = threadIdx.x; l < L; l += 1024) {
+    const float v = scores[l];
+    if (v > bv || (v == bv && l < bi)) {
+      bv = v;
+      bi = l;
+    }
+  }
+  sv[threadIdx.x] = bv;
+  si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int st = 512; st > 0; st >>= 1) {
+    if (threadIdx.x < st) {
+      const float ov = sv[threadIdx.x + st];
+      const int oi = si[threadIdx.x + st];
+      if (ov > sv[threadIdx.x] || (ov == sv[threadIdx.x] && oi < si[threadIdx.x])) {
+        sv[threadIdx.x] = ov;
+        si[threadIdx.x] = oi;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && best) *best = si[0];
+}
+
+int score_tail_launch(const ScoreTailParams& p, cudaStream_t stream) {
+  if (p.L == 0) return 0;
+  FP_REQUIRE(p.L <= 4096, "score tail: L=%d too large", p.L);
+  rowwise_linear_kernel<<<p.L, 256, 0, stream>>>(p.feats, p.w_in, p.b_in, p.qkv, 1536);
+  cross_attn_kernel<<<p.L, 128, 4 * p.L * sizeof(float), stream>>>(p.qkv, p.attn, p.L, 0.08838834764831845f);
+  rowwise_linear_kernel<<<p.L, 256, 0, stream>>>(p.attn, p.w_out, p.b_out, p.proj, 512);
+  score_linear_kernel<<<1, 1024, 0, stream>>>(p.proj, p.w_lin, p.b_lin, p.offset, p.scores, p.best, p.L);
+  g_launch_count += 4;
+  FP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pose update
+// ------------------------------------------------------------------------------------------------
+__global__ void pose_update_kernel(const float* __restrict__ pose_in, const float* __restrict__ trans,
+                                   const float* __restrict__ rot, float* __restrict__ pose_out,
+                                   float* __restrict__ trans_delta_out, float* __restrict__ rot_delta_out, int N,
+                                   float trans_scale, float rot_normalizer) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* A = pose_in + (size_t)n * 16;
+  // trans_delta = output['trans'] * (mesh_diameter / 2)   (normalize_xyz, predict_pose_refine.py:199,228-229)
+  const float td[3] = {trans[n * 3] * trans_scale, trans[n * 3 + 1] * trans_scale, trans[n * 3 + 2] * trans_scale};
+  // rot: so3_exp_map(tanh(rot) * rot_normalizer).T   (predict_pose_refine.py:220-222; pytorch3d eps = 1e-4)
+  const float vx = tanhf(rot[n * 3]) * rot_normalizer, vy = tanhf(rot[n * 3 + 1]) * rot_normalizer,
+              vz = tanhf(rot[n * 3 + 2]) * rot_normalizer;
+  const float nrm = vx * vx + vy * vy + vz * vz;
+  const float th = sqrtf(fmaxf(nrm, 1e-4f));
+  const float ith = 1.f / th;
+  const float f1 = ith * sinf(th);
+  const float f2 = ith * ith * (1.f - cosf(th));
+  // K = hat(v), K2 = K*K
+  const float K[9] = {0.f, -vz, vy, vz, 0.f, -vx, -vy, vx, 0.f};
+  float K2[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) K2[i * 3 + j] = K[i * 3] * K[j] + K[i * 3 + 1] * K[3 + j] + K[i * 3 + 2] * K[6 + j];
+  float Rd[9];  // transposed exponential
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Rd[j * 3 + i] = f1 * K[i * 3 + j] + f2 * K2[i * 3 + j] + (i == j ? 1.f : 0.f);
+  float* B = pose_out + (size_t)n * 16;
+  float Rn[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Rn[i * 3 + j] = Rd[i * 3] * A[j] + Rd[i * 3 + 1] * A[4 + j] + Rd[i * 3 + 2] * A[8 + j];
+  const float t0 = A[3] + td[0], t1 = A[7] + td[1], t2 = A[11] + td[2];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    B[i * 4 + 0] = Rn[i * 3 + 0];
+    B[i * 4 + 1] = Rn[i * 3 + 1];
+    B[i * 4 + 2] = Rn[i * 3 + 2];
+  }
+  B[3] = t0;
+  B[7] = t1;
+  B[11] = t2;
+  B[12] = 0.f;
+  B[13] = 0.f;
+  B[14] = 0.f;
+  B[15] = 1.f;
+  if (trans_delta_out) {
+    trans_delta_out[n * 3] = td[0];
+    trans_delta_out[n * 3 + 1] = td[1];
+    trans_delta_out[n * 3 + 2] = td[2];
+  }
+  if (rot_delta_out) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) rot_delta_out[n * 9 + i] = Rd[i];
+  }
+}
+
+int pose_update_launch(const float* pose_in, const float* trans, const float* rot, float* pose_out,
+                       float* trans_delta_out, float* rot_delta_out, int N, float trans_scale, float rot_normalizer,
+                       cudaStream_t stream) {
+  if (N == 0) return 0;
+  pose_update_kernel<<<(N + 127) / 128, 128, 0, stream>>>(pose_in, trans, rot, pose_out, trans_delta_out, rot_delta_out,
+                                                          N, trans_scale, rot_normalizer);
+  ++g_launch_count;
+  FP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// fp32 [rows][cols] -> fp16
+__global__ void f32_to_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __float2half_rn(x[i]);
+}
+int f32_to_f16_launch(const float* x, __half* y, size_t n, cudaStream_t stream) {
+  if (n == 0) return 0;
+  f32_to_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, y, n);
+  ++g_launch_count;
+  FP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace fp

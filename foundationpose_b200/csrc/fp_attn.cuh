@@ -1,0 +1,52 @@
+// fp_attn.cuh — launchers of the non-GEMM transformer / scorer-tail / pose-update kernels.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace fp {
+
+struct AttnParams {
+  const __half* qkv;  // [B*T][ld]; q at q_off + h*128, k at k_off + h*128, v at v_off + h*128
+  int ld;
+  int q_off, k_off, v_off;
+  int group_col_stride;  // groups (e.g. trans / rot head) are further column blocks of the same rows
+  int n_groups;
+  __half* out;  // [group][B*T][ld_out], head h at column h*128
+  int ld_out;
+  size_t out_group_stride;
+  int B, T, n_heads;
+  float scale;  // 1/sqrt(head_dim)
+};
+int attn_core_launch(const AttnParams& p, cudaStream_t stream);
+
+int layernorm_launch(const __half* x, __half* y, const float* gamma, const float* beta, int rows, cudaStream_t stream);
+int head_final_launch(const __half* x, const float* gamma, const float* beta, const float* w, const float* bias,
+                      float* out, int B, int T, int out_dim, cudaStream_t stream);
+int token_mean_proj_launch(const __half* x, const __half* w, const float* bias, float* out, int B, int T,
+                           cudaStream_t stream);
+
+struct ScoreTailParams {
+  const float* feats;  // [L][512]
+  int L;
+  const __half* w_in;   // att_cross.in_proj_weight  [1536][512]
+  const float* b_in;    // [1536]
+  const __half* w_out;  // att_cross.out_proj.weight [512][512]
+  const float* b_out;
+  const float* w_lin;   // linear.weight [512]
+  float b_lin;
+  float offset;         // +100 of predict_score.py:207
+  float* qkv;           // workspace [L][1536]
+  float* attn;          // workspace [L][512]
+  float* proj;          // workspace [L][512]
+  float* scores;        // out [L]
+  int* best;            // out, optional
+};
+int score_tail_launch(const ScoreTailParams& p, cudaStream_t stream);
+
+int pose_update_launch(const float* pose_in, const float* trans, const float* rot, float* pose_out,
+                       float* trans_delta_out, float* rot_delta_out, int N, float trans_scale, float rot_normalizer,
+                       cudaStream_t stream);
+int f32_to_f16_launch(const float* x, __half* y, size_t n, cudaStream_t stream);
+
+}  // namespace fp

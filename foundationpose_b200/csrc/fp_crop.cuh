@@ -1,0 +1,41 @@
+// fp_crop.cuh — parameters of the fused crop producer (fp_crop.cu).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace fp {
+
+struct CropParams {
+  const float* poses;  // [N][16] row-major ob_in_cam
+  int N;
+  float fx, fy, cx, cy;
+  int H, W;
+  float r3;          // mesh_diameter * crop_ratio / 2 (Utils.py:603)
+  float inv_radius;  // 1 / (mesh_diameter / 2)       (h5_dataset.py:96)
+  float znear;
+  // mesh (device)
+  const float* vpos;   // [V][3]
+  const float* vnrm;   // [V][3]
+  const float* vuv;    // [V][2] (v already flipped, Utils.py:117) or null
+  const float* vcol;   // [V][3] in 0..1 or null
+  const int* faces;    // [F][3]
+  int F;
+  const uchar4* tex;   // [Ht][Wt] RGBA8 or null
+  int Ht, Wt;
+  // frame (device)
+  const uchar4* rgb;     // [H][W] RGBA8
+  const float* xyz_map;  // [H][W][3]   (mode 0)
+  const float* depth;    // [H][W]      (mode 1)
+  int mode;              // 0 = refiner crops, 1 = scorer crops
+  // outputs
+  __half* crops;   // [2N][166][168][8] fp16: images 0..N-1 = rendered (A), N..2N-1 = observed (B)
+  float* dbg;      // optional [N][2][160][160][6] fp32 copy of the normalised crops
+  float* win_out;  // optional [N][4] = (left, top, sx, sy)
+};
+
+int crop_launch(const CropParams& p, cudaStream_t stream);
+int rgb_to_rgba_launch(const unsigned char* rgb, uchar4* out, int npix, cudaStream_t stream);
+int depth_to_xyz_launch(const float* depth, float* xyz, int H, int W, float fx, float fy, float cx, float cy,
+                        float zfar, cudaStream_t stream);
+
+}  // namespace fp

@@ -1,0 +1,10 @@
+// fp_depth.cuh — launchers of the depth pre-processing kernels (fp_depth.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace fp {
+int erode_depth_launch(const float* depth, float* out, int H, int W, int radius, float diff_thres, float ratio_thres,
+                       float zfar, cudaStream_t stream);
+int bilateral_depth_launch(const float* depth, float* out, int H, int W, int radius, float zfar, float sigmaD,
+                           float sigmaR, cudaStream_t stream);
+}  // namespace fp

@@ -1,0 +1,154 @@
+"""Synthetic inputs of the benchmark / tests: a textured ellipsoid mesh, a 640x480
+RGB-D frame of it in front of a textured plane, and seeded weights (weights.random_state_dict).
+
+Everything is numpy on the host and deterministic for a given seed; no file IO, no network.
+The frame is produced analytically (ray / ellipsoid intersection), not by any renderer, so it does
+not depend on the code under test.
+"""
+import numpy as np
+
+
+class _Visual:
+    def __init__(self, uv, image):
+        self.uv = uv
+        self.image = image  # uint8 (Ht, Wt, 3)
+        self.vertex_colors = None
+
+
+class SimpleMesh:
+    """Minimal stand-in for the trimesh.Trimesh attributes the hot path reads
+    (Utils.py:104-130: vertices, faces, vertex_normals, visual.uv, visual.material.image)."""
+
+    def __init__(self, vertices, faces, vertex_normals, uv=None, texture=None, vertex_colors=None):
+        self.vertices = np.asarray(vertices, dtype=np.float64)
+        self.faces = np.asarray(faces, dtype=np.int64)
+        self.vertex_normals = np.asarray(vertex_normals, dtype=np.float64)
+        self.visual = _Visual(uv, texture)
+        self.visual.vertex_colors = vertex_colors
+
+    def copy(self):
+        return SimpleMesh(self.vertices.copy(), self.faces.copy(), self.vertex_normals.copy(),
+                          None if self.visual.uv is None else self.visual.uv.copy(), self.visual.image,
+                          self.visual.vertex_colors)
+
+
+def icosphere(subdivisions):
+    """Unit icosphere: V = 10 * 4^s + 2 vertices, F = 20 * 4^s faces."""
+    t = (1.0 + 5.0 ** 0.5) / 2.0
+    v = np.array([[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t], [0, -1, -t], [0, 1, -t],
+                  [t, 0, -1], [t, 0, 1], [-t, 0, -1], [-t, 0, 1]], dtype=np.float64)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    f = np.array([[0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11], [1, 5, 9], [5, 11, 4], [11, 10, 2],
+                  [10, 7, 6], [7, 1, 8], [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8], [3, 8, 9], [4, 9, 5], [2, 4, 11],
+                  [6, 2, 10], [8, 6, 7], [9, 8, 1]], dtype=np.int64)
+    verts = [tuple(x) for x in v]
+    for _ in range(subdivisions):
+        cache = {}
+        new_f = []
+
+        def mid(a, b):
+            key = (min(a, b), max(a, b))
+            if key not in cache:
+                m = (np.array(verts[a]) + np.array(verts[b])) / 2.0
+                m /= np.linalg.norm(m)
+                verts.append(tuple(m))
+                cache[key] = len(verts) - 1
+            return cache[key]
+
+        for a, b, c in f:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            new_f += [[a, ab, ca], [b, bc, ab], [c, ca, bc], [ab, bc, ca]]
+        f = np.array(new_f, dtype=np.int64)
+    return np.array(verts, dtype=np.float64), f
+
+
+RADII = np.array([0.05, 0.03, 0.095])  # 0.10 x 0.06 x 0.19 m, roughly a mustard bottle
+
+
+def sphere_uv(q):
+    """Spherical UV of unit directions q (..., 3) -> (..., 2) in [0, 1]."""
+    u = np.arctan2(q[..., 1], q[..., 0]) / (2 * np.pi) + 0.5
+    v = np.arccos(np.clip(q[..., 2], -1, 1)) / np.pi
+    return np.stack([u, v], -1)
+
+
+def make_texture(seed=0, size=1024, block=16):
+    rng = np.random.default_rng(seed)
+    low = rng.integers(0, 256, size=(size // block, size // block, 3), dtype=np.uint8)
+    return np.ascontiguousarray(np.repeat(np.repeat(low, block, 0), block, 1))
+
+
+def make_mesh(subdivisions=5, tex_seed=0, tex_size=1024):
+    q, f = icosphere(subdivisions)
+    verts = q * RADII
+    nrm = q / RADII
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    uv = sphere_uv(q)
+    return SimpleMesh(verts, f, nrm, uv=uv, texture=make_texture(tex_seed, tex_size))
+
+
+def mesh_diameter(vertices):
+    """Largest pairwise vertex distance (Utils.py:559-574 without the random sub-sampling)."""
+    v = np.asarray(vertices, dtype=np.float64)
+    if len(v) > 4000:
+        rng = np.random.default_rng(0)
+        v = v[rng.choice(len(v), 4000, replace=False)]
+    d2 = ((v[None] - v[:, None]) ** 2).sum(-1)
+    return float(np.sqrt(d2.max()))
+
+
+DEFAULT_K = np.array([[615.0, 0, 320.0], [0, 615.0, 240.0], [0, 0, 1.0]])
+
+
+def random_rotation(seed):
+    rng = np.random.default_rng(seed)
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def make_scene(mesh_texture, pose, K=DEFAULT_K, H=480, W=640, plane_z=1.2, seed=1, depth_noise=0.001):
+    """Analytic RGB-D frame: ellipsoid (radii RADII, texture via spherical UV) at `pose` (4x4 ob_in_cam)
+    in front of a textured plane at z = plane_z.  Returns rgb uint8 (H,W,3), depth float32 (H,W), mask bool."""
+    rng = np.random.default_rng(seed)
+    vs, us = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    d = np.stack([(us - K[0, 2]) / K[0, 0], (vs - K[1, 2]) / K[1, 1], np.ones_like(us, dtype=np.float64)], -1)
+    R, t = pose[:3, :3], pose[:3, 3]
+    o_ob = -R.T @ t
+    d_ob = d @ R  # rows: R^T d
+    so, sd = o_ob / RADII, d_ob / RADII
+    a = (sd * sd).sum(-1)
+    b = 2 * (sd * so).sum(-1)
+    c = (so * so).sum() - 1.0
+    disc = b * b - 4 * a * c
+    hit = disc > 0
+    s = np.where(hit, (-b - np.sqrt(np.maximum(disc, 0))) / (2 * a), 0.0)
+    hit &= s > 0
+    depth = np.full((H, W), plane_z, dtype=np.float64)
+    depth[hit] = s[hit]
+    # colours
+    bg = make_texture(seed + 100, 512, 32)
+    bu = ((d[..., 0] * plane_z * 400).astype(np.int64)) % 512
+    bv = ((d[..., 1] * plane_z * 400).astype(np.int64)) % 512
+    rgb = bg[bv, bu].copy()
+    p_ob = o_ob + d_ob * s[..., None]
+    uv = sphere_uv(p_ob / RADII / np.maximum(np.linalg.norm(p_ob / RADII, axis=-1, keepdims=True), 1e-9))
+    Ht, Wt = mesh_texture.shape[:2]
+    tx = np.clip((uv[..., 0] * Wt).astype(np.int64), 0, Wt - 1)
+    ty = np.clip(((1.0 - uv[..., 1]) * Ht).astype(np.int64), 0, Ht - 1)  # trimesh uv: v = 0 is the image bottom
+    rgb[hit] = mesh_texture[ty, tx][hit]
+    depth = depth + rng.normal(0, depth_noise, size=depth.shape)
+    return rgb.astype(np.uint8), depth.astype(np.float32), hit
+
+
+def default_scene(subdivisions=5, seed=0):
+    """Mesh, GT pose, K and frame of BASELINE.json configs[1] ("model-based register")."""
+    mesh = make_mesh(subdivisions)
+    pose = np.eye(4)
+    pose[:3, :3] = random_rotation(seed)
+    pose[:3, 3] = [0.0, 0.0, 0.6]
+    rgb, depth, mask = make_scene(mesh.visual.image, pose)
+    return mesh, pose, DEFAULT_K.copy(), rgb, depth, mask

@@ -62,6 +62,89 @@ typedef struct fp_gemm_layer {
 /* Runs one layer: out = act(in (*) w + bias [+ res]) [+ post_add]. */
 int fp_op_gemm_layer(const fp_gemm_layer_t* layer, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------ */
+/* product path                                                                               */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct fp_ctx fp_ctx;
+
+/* Creates a context on the current CUDA device (must be sm_100).  Replaces the implicit global
+ * state of the reference predictors (`.cuda()` modules, nvdiffrast `RasterizeCudaContext`,
+ * estimater.py:29-41, :166-171). */
+int fp_create(fp_ctx** ctx);
+int fp_destroy(fp_ctx* ctx);
+
+/* crop_ratio (predict_pose_refine.py:117-118) and rot_normalizer (cfg['rot_normalizer'], :221). */
+int fp_set_config(fp_ctx* ctx, float crop_ratio, float rot_normalizer);
+
+/* One named host tensor of a packed network (see foundationpose_b200/engine.py for the packing:
+ * BatchNorm folded, conv weights K-major fp16).  dtype: 0 = float32, 1 = float16. */
+typedef struct fp_tensor {
+  const char* name;
+  const void* data; /* HOST pointer */
+  int dtype;
+  long long numel;
+} fp_tensor_t;
+
+/* which: 0 = RefineNet (predict_pose_refine.py:133-143 `load_state_dict`), 1 = ScoreNetMultiPair
+ * (predict_score.py:146-156).  Copies to device memory owned by the context; validates names/sizes. */
+int fp_load_network(fp_ctx* ctx, int which, const fp_tensor_t* tensors, int n);
+
+/* Replaces Utils.py:104-130 `make_mesh_tensors` (HOST pointers; uv already v-flipped as in :117;
+ * texture uint8 RGB [Ht][Wt][3]; pass uv = tex = NULL and vcol (float 0..1, [V][3]) for
+ * vertex-coloured meshes).  diameter = estimater.py:54. */
+int fp_set_mesh(fp_ctx* ctx, int V, int F, const float* pos, const float* nrm, const float* uv, const float* vcol,
+                const int* faces, const unsigned char* tex_rgb, int Ht, int Wt, float diameter);
+
+#define FP_FRAME_ON_DEVICE 1    /* rgb/depth are device pointers (default: host, copied on `stream`) */
+#define FP_FRAME_FILTER_DEPTH 2 /* erode_depth + bilateral_filter_depth (estimater.py:173-174, :257-258) */
+/* Uploads one RGB-D frame (rgb uint8 [H][W][3], depth float32 [H][W] metres, K row-major 3x3), runs
+ * the depth filters (Utils.py:304-395) and depth2xyzmap (Utils.py:399-438; zfar as in :426, use
+ * INFINITY for register()).  Asynchronous on `stream`. */
+int fp_set_frame(fp_ctx* ctx, const unsigned char* rgb, const float* depth, const float* K, int H, int W, int flags,
+                 float zfar, void* stream);
+/* Copies the filtered depth [H][W] and/or the xyz map [H][W][3] to device buffers (test hook). */
+int fp_get_depth(fp_ctx* ctx, float* depth_out_dev, float* xyz_out_dev, void* stream);
+
+/* make_crop_data_batch (predict_pose_refine.py:25-89 for mode 0, predict_score.py:56-114 for mode 1):
+ * poses [N][16] device.  Fills the context's crop buffer; optionally copies it to crops_out
+ * (fp16 [2N][166][168][8]: images 0..N-1 rendered, N..2N-1 observed), an fp32 copy of the
+ * normalised crops to dbg_out ([N][2][160][160][6]) and the crop windows to win_out
+ * ([N][4] = left, top, sx, sy of tf_to_crop). */
+int fp_make_crops(fp_ctx* ctx, const float* poses, int N, int mode, void* crops_out, float* dbg_out, float* win_out,
+                  void* stream);
+
+/* PoseRefinePredictor.predict (predict_pose_refine.py:149-239) without the host round trips: poses
+ * in/out are DEVICE [N][16]; last_trans [N][3] / last_rot [N][9] (optional) receive
+ * `last_trans_update` / `last_rot_update` (:238-239). */
+int fp_refine(fp_ctx* ctx, const float* poses_in, int N, int iterations, float* poses_out, float* last_trans,
+              float* last_rot, void* stream);
+
+/* ScorePredictor.predict (predict_score.py:160-214): scores_out DEVICE [N] (= logits + 100),
+ * best_out DEVICE int (first index of the maximum = ids[0] of estimater.py:226). */
+int fp_score(fp_ctx* ctx, const float* poses, int N, float* scores_out, int* best_out, void* stream);
+/* The two halves of fp_score, split where the hypothesis batch shards across GPUs: per-hypothesis
+ * features (score_network.py:60-74), then — after an all-gather of the [N][512] features — the
+ * cross-hypothesis attention + linear + argmax (score_network.py:84-88). */
+int fp_score_features(fp_ctx* ctx, const float* poses, int N, float* feats_out, void* stream);
+int fp_score_tail(fp_ctx* ctx, const float* feats, int L, float* scores_out, int* best_out, void* stream);
+
+/* Hot loop of FoundationPose.register (estimater.py:203-235) with HOST buffers: uploads the N
+ * start poses, refines `iterations` times, scores, and returns refined poses [N][16], scores [N]
+ * and the best index.  Synchronises `stream` before returning. */
+int fp_register(fp_ctx* ctx, const float* poses_host, int N, int iterations, float* poses_out_host,
+                float* scores_out_host, int* best_out_host, void* stream);
+
+/* parity-test hooks on pre-built crops (fp16 [2N][166][168][8], device) */
+int fp_op_refine_net(fp_ctx* ctx, const void* crops, int N, float* trans_out, float* rot_out, void* stream);
+int fp_op_score_feats(fp_ctx* ctx, const void* crops, int N, float* feats_out, void* stream);
+int fp_op_tokens(fp_ctx* ctx, int which, const void* crops, int N, void* tokens_out, void* stream);
+/* which: 0 = erode_depth (Utils.py:359-395), 1 = bilateral_filter_depth (Utils.py:304-356) */
+int fp_op_depth_filter(const float* depth_dev, float* out_dev, int H, int W, int which, void* stream);
+/* egocentric_delta_pose_to_pose with the refiner's output decoding (predict_pose_refine.py:195-231) */
+int fp_op_pose_update(const float* poses_in, const float* trans, const float* rot, float* poses_out, int N,
+                      float mesh_diameter, float rot_normalizer, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

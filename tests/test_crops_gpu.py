@@ -1,0 +1,132 @@
+"""GPU parity of the fused crop producer (csrc/fp_crop.cu) and the depth filters (csrc/fp_depth.cu)
+against the CPU oracle (oracle/geometry.py, raster.py, pipeline.py).
+
+Bars:
+  * crop window (integer-valued edges): bit-exact;
+  * raster coverage / triangle choice: the oracle uses the same fixed-point rule, so rendered-crop
+    validity masks must agree on >= 99.9 % of pixels (a vertex whose projection differs in the last
+    fp32 bit may flip a 1/256-px snap);
+  * values on agreeing pixels: 2e-4 abs (fp32 interpolation order differs), rgb 2e-3;
+  * observed crop (nearest/bilinear resampling): >= 99.8 % of pixels within tolerance (nearest-neighbour
+    ties at x.5 are decided by the last bit of kornia's coordinate chain);
+  * depth filters: 1e-6 abs.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def scene():
+    from foundationpose_b200 import synth
+    from foundationpose_b200.engine import Engine
+    from oracle import pipeline
+
+    mesh = synth.make_mesh(3)
+    pose = np.eye(4)
+    pose[:3, :3] = synth.random_rotation(0)
+    pose[:3, 3] = [0.02, -0.01, 0.6]
+    rgb, depth, mask = synth.make_scene(mesh.visual.image, pose)
+    d = synth.mesh_diameter(mesh.vertices)
+    mt = pipeline.mesh_tensors(mesh)
+    e = Engine()
+    e.set_mesh(mt["pos"], mt["normals"], mt["faces"], d, uv=mt["uv"], tex=mt["tex"])
+    poses = np.stack([pose, pose, pose, pose]).astype(np.float32)
+    poses[1, :3, 3] += [0.01, 0.0, 0.02]
+    poses[2, :3, :3] = synth.random_rotation(7)
+    poses[3, :3, 3] = [0.25, 0.18, 0.5]  # partially outside the frame
+    return dict(e=e, mesh=mesh, mt=mt, rgb=rgb, depth=depth, K=synth.DEFAULT_K, d=d, poses=poses)
+
+
+def _compare(got, ref, what, min_agree, atol):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    ok = (got - ref).abs() <= atol
+    frac = ok.float().mean().item()
+    assert frac >= min_agree, f"{what}: only {frac * 100:.3f}% of values within {atol}"
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_crops_match_oracle(scene, mode):
+    from oracle import geometry, pipeline
+
+    e = scene["e"]
+    e.set_frame(scene["rgb"], scene["depth"], scene["K"], filter_depth=False)
+    _, dbg, win = e.make_crops(scene["poses"], mode=mode, want_dbg=True)
+    xyz = geometry.depth2xyzmap(scene["depth"], scene["K"])
+    A, B, owin = pipeline.make_crops(scene["poses"], scene["mt"], scene["rgb"], scene["depth"], xyz, scene["K"], scene["d"], mode)
+    w = win.cpu().numpy()
+    np.testing.assert_array_equal(w[:, 0], owin["left"])
+    np.testing.assert_array_equal(w[:, 1], owin["top"])
+    np.testing.assert_array_equal(w[:, 2], owin["sx"])
+    np.testing.assert_array_equal(w[:, 3], owin["sy"])
+    gA = dbg[:, 0].permute(0, 3, 1, 2)  # (N,6,160,160)
+    gB = dbg[:, 1].permute(0, 3, 1, 2)
+    # coverage of the rendered crop
+    cov_g = (gA[:, 3:].abs().sum(1) > 0).cpu()
+    cov_o = A[:, 3:].abs().sum(1) > 0
+    agree = (cov_g == cov_o).float().mean().item()
+    assert agree >= 0.999, f"raster coverage agreement {agree}"
+    both = (cov_g & cov_o)[:, None].expand(-1, 3, -1, -1)
+    assert ((gA[:, 3:].cpu() - A[:, 3:]).abs()[both] <= 2e-4).float().mean().item() >= 0.9995
+    assert ((gA[:, :3].cpu() - A[:, :3]).abs()[both] <= 2e-3).float().mean().item() >= 0.999
+    _compare(gB[:, :3], B[:, :3], "observed rgb", 0.998, 2e-3)
+    _compare(gB[:, 3:], B[:, 3:], "observed xyz", 0.998, 2e-4)
+
+
+def test_fp16_crop_buffer_layout(scene):
+    """The fp16 NHWC(8) buffer the stem convolution reads: interior = crops, border = zeros."""
+    e = scene["e"]
+    e.set_frame(scene["rgb"], scene["depth"], scene["K"], filter_depth=False)
+    crops, dbg, _ = e.make_crops(scene["poses"], mode=0, want_dbg=True)
+    N = len(scene["poses"])
+    assert crops.shape == (2 * N, 166, 168, 8)
+    inner = crops[:, 3:163, 3:163, :6].float()
+    ref = torch.cat([dbg[:, 0], dbg[:, 1]], 0)
+    assert (inner - ref).abs().max().item() <= 2e-3
+    assert crops[:, :3].abs().max().item() == 0 and crops[:, 163:].abs().max().item() == 0
+    assert crops[:, :, :3].abs().max().item() == 0 and crops[:, :, 163:].abs().max().item() == 0
+    assert crops[..., 6:].abs().max().item() == 0
+
+
+def test_depth_filters(scene):
+    from foundationpose_b200.engine import op_depth_filter
+    from oracle import geometry
+
+    depth = scene["depth"].copy()
+    rng = np.random.default_rng(3)
+    depth[rng.random(depth.shape) < 0.05] = 0  # holes
+    depth[100:110, 200:260] += 0.05  # a step
+    dg = torch.from_numpy(depth).cuda()
+    er = op_depth_filter(dg, 0)
+    ref_er = geometry.erode_depth(depth)
+    np.testing.assert_allclose(er.cpu().numpy(), ref_er, atol=1e-6, rtol=0)
+    bl = op_depth_filter(er, 1)
+    ref_bl = geometry.bilateral_filter_depth(ref_er)
+    np.testing.assert_allclose(bl.cpu().numpy(), ref_bl, atol=2e-6, rtol=0)
+
+
+def test_set_frame_filters_and_xyz(scene):
+    from oracle import geometry
+
+    e = scene["e"]
+    e.set_frame(scene["rgb"], scene["depth"], scene["K"], filter_depth=True)
+    d, xyz = e.get_depth()
+    ref = geometry.bilateral_filter_depth(geometry.erode_depth(scene["depth"]))
+    np.testing.assert_allclose(d.cpu().numpy(), ref, atol=2e-6, rtol=0)
+    np.testing.assert_allclose(xyz.cpu().numpy(), geometry.depth2xyzmap(ref, scene["K"]), atol=1e-6, rtol=0)
+
+
+def test_pose_update(scene):
+    from foundationpose_b200.engine import op_pose_update
+    from oracle import geometry
+
+    g = torch.Generator().manual_seed(2)
+    poses = torch.from_numpy(scene["poses"]).clone()
+    trans = torch.randn(4, 3, generator=g) * 0.3
+    rot = torch.randn(4, 3, generator=g)
+    rot[0] = 0  # exercises the eps clamp of so3_exp_map
+    out = op_pose_update(poses.cuda(), trans.cuda(), rot.cuda(), scene["d"], 0.3490658503988659)
+    ref, _, _ = geometry.pose_update(poses, trans, rot, scene["d"], 0.3490658503988659)
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), atol=2e-6, rtol=0)
