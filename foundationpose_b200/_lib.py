@@ -66,3 +66,20 @@ def check(rc, what=""):
 
 def launch_count():
     return int(lib.fp_launch_count())
+
+
+lib.fp_prof_enable.argtypes = [C.c_int]
+lib.fp_prof_enable.restype = C.c_int
+lib.fp_prof_collect.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+lib.fp_prof_collect.restype = C.c_int
+
+
+def prof_enable(on):
+    check(lib.fp_prof_enable(1 if on else 0), "fp_prof_enable")
+
+
+def prof_collect(kind):
+    """-> (total_ms, total_work, launches) of kernel `kind` (0 = implicit GEMM [FLOPs], 1 = crop [bytes])."""
+    ms, work, n = C.c_double(), C.c_double(), C.c_int()
+    check(lib.fp_prof_collect(kind, C.byref(ms), C.byref(work), C.byref(n)), "fp_prof_collect")
+    return ms.value, work.value, n.value

@@ -569,9 +569,9 @@ int fp_score_tail(fp_ctx* c, const float* feats, int L, float* scores_out, int* 
   ScoreTailParams p;
   p.feats = feats;
   p.L = L;
-  p.w_in = net.h("cross.in_w");
+  p.w_in = net.f("cross.in_w");
   p.b_in = net.f("cross.in_b");
-  p.w_out = net.h("cross.out_w");
+  p.w_out = net.f("cross.out_w");
   p.b_out = net.f("cross.out_b");
   p.w_lin = net.f("lin.w");
   p.b_lin = c->lin_b_host;

@@ -6,6 +6,7 @@
 
 namespace fp {
 const char* get_last_error();
+int prof_collect(int kind, double* total_ms, double* total_work, int* launches);
 }
 
 extern "C" {
@@ -13,6 +14,19 @@ extern "C" {
 const char* fp_last_error(void) { return fp::get_last_error(); }
 
 unsigned long long fp_launch_count(void) { return fp::g_launch_count; }
+
+int fp_prof_enable(int on) {
+  fp::g_prof_on = on != 0;
+  return 0;
+}
+
+int fp_prof_collect(int kind, double* total_ms, double* total_work, int* launches) {
+  if (!total_ms || !total_work || !launches) {
+    fp::set_last_error("fp_prof_collect: null output");
+    return -1;
+  }
+  return fp::prof_collect(kind, total_ms, total_work, launches);
+}
 
 int fp_op_gemm_layer(const fp_gemm_layer_t* l, void* stream) {
   if (!l) {

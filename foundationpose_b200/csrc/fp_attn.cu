@@ -214,6 +214,16 @@ __device__ __forceinline__ void load_row16(const __half* row, int lane, float (&
     v[8 + 2 * i + 1] = g.y;
   }
 }
+__device__ __forceinline__ void load_row16(const float* row, int lane, float (&v)[16]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(row + lane * 16) + q);
+    v[4 * q] = a.x;
+    v[4 * q + 1] = a.y;
+    v[4 * q + 2] = a.z;
+    v[4 * q + 3] = a.w;
+  }
+}
 __device__ __forceinline__ float warp_sum(float x) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
@@ -356,7 +366,7 @@ int token_mean_proj_launch(const __half* x, const __half* w, const float* bias, 
 // scorer tail: attention across the L hypotheses (fp32 SIMT; 0.3 GFLOP total)
 // ------------------------------------------------------------------------------------------------
 // y[l, :] = in_proj(x[l, :]) : [L][512] fp32 -> [L][1536] fp32.  One CTA per row.
-__global__ void __launch_bounds__(256) rowwise_linear_kernel(const float* __restrict__ x, const __half* __restrict__ w,
+__global__ void __launch_bounds__(256) rowwise_linear_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ bias, float* __restrict__ y,
                                                              int n_out) {
   __shared__ float xs[512];

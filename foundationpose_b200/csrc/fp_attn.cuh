@@ -29,9 +29,9 @@ int token_mean_proj_launch(const __half* x, const __half* w, const float* bias, 
 struct ScoreTailParams {
   const float* feats;  // [L][512]
   int L;
-  const __half* w_in;   // att_cross.in_proj_weight  [1536][512]
+  const float* w_in;    // att_cross.in_proj_weight  [1536][512] (fp32: the tail decides the argmax)
   const float* b_in;    // [1536]
-  const __half* w_out;  // att_cross.out_proj.weight [512][512]
+  const float* w_out;   // att_cross.out_proj.weight [512][512]
   const float* b_out;
   const float* w_lin;   // linear.weight [512]
   float b_lin;

@@ -361,7 +361,10 @@ int crop_launch(const CropParams& p, cudaStream_t stream) {
     attr_set = true;
   }
   if (p.N == 0) return 0;
+  // algorithmic bytes: the two 6-channel fp16 crops each hypothesis produces
+  prof_mark_begin(1, (double)p.N * 2.0 * 6.0 * S * S * 2.0, stream);
   crop_kernel<<<p.N, kCropThreads, kZbufBytes, stream>>>(p);
+  prof_mark_end(stream);
   ++g_launch_count;
   FP_CUDA_OK(cudaGetLastError());
   return 0;

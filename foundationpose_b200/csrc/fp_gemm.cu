@@ -26,12 +26,61 @@
 #include <string.h>
 
 #include <mutex>
+#include <vector>
 
 #include "fp_common.cuh"
 
 namespace fp {
 
 unsigned long long g_launch_count = 0;
+bool g_prof_on = false;
+
+struct ProfRec {
+  cudaEvent_t e0, e1;
+  double work;
+  int kind;
+};
+static std::vector<ProfRec> g_prof_recs;
+
+void prof_mark_begin(int kind, double work, cudaStream_t stream) {
+  if (!g_prof_on) return;
+  ProfRec r;
+  r.kind = kind;
+  r.work = work;
+  cudaEventCreate(&r.e0);
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, stream);
+  g_prof_recs.push_back(r);
+}
+void prof_mark_end(cudaStream_t stream) {
+  if (!g_prof_on || g_prof_recs.empty()) return;
+  cudaEventRecord(g_prof_recs.back().e1, stream);
+}
+// sums and clears the records of `kind`; synchronises the device
+int prof_collect(int kind, double* total_ms, double* total_work, int* launches) {
+  FP_CUDA_OK(cudaDeviceSynchronize());
+  double ms = 0, work = 0;
+  int n = 0;
+  std::vector<ProfRec> keep;
+  for (auto& r : g_prof_recs) {
+    if (r.kind != kind) {
+      keep.push_back(r);
+      continue;
+    }
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    ms += t;
+    work += r.work;
+    ++n;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof_recs.swap(keep);
+  *total_ms = ms;
+  *total_work = work;
+  *launches = n;
+  return 0;
+}
 
 static thread_local char t_last_error[1024] = "";
 void set_last_error(const char* fmt, ...) {
@@ -58,6 +107,7 @@ struct GemmParams {
   int out_split;
   const float* post_add;
   int relu;
+  double alg_flops;  // 2 * M * Cout * K_real of this launch (host-side bookkeeping only)
 };
 
 constexpr int kBlockM = 128;
@@ -333,7 +383,9 @@ static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const GemmPar
     FP_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
+  prof_mark_begin(0, p.alg_flops, stream);
   gemm_tile_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ma, mb, p);
+  prof_mark_end(stream);
   ++g_launch_count;
   FP_CUDA_OK(cudaGetLastError());
   return 0;
@@ -452,6 +504,10 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
   p.out_split = L.out_split;
   p.post_add = L.post_add;
   p.relu = L.relu;
+  {
+    const double k_real = (L.kind == LK_CONV7_S2) ? 7.0 * 7.0 * 6.0 : (double)taps * L.Cin;
+    p.alg_flops = 2.0 * (double)L.n_img * Ho * Wo * L.Cout * k_real;
+  }
   FP_REQUIRE(L.out_ld % 8 == 0 && (!L.res || L.res_ld % 8 == 0), "out_ld / res_ld must be multiples of 8");
   if (p.total_tiles == 0) return 0;
 

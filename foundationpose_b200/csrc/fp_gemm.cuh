@@ -41,4 +41,11 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream);
 // Number of kernel launches issued so far by this library (all kernels), for bench.py.
 extern unsigned long long g_launch_count;
 
+// Optional per-launch device timing (CUDA events on the launching stream) of the two kernels the
+// roofline is reported for: kind 0 = gemm_tile_kernel (work = algorithmic FLOPs), kind 1 = crop_kernel
+// (work = algorithmic output bytes).  Off by default; bench.py turns it on for a dedicated pass.
+void prof_mark_begin(int kind, double work, cudaStream_t stream);
+void prof_mark_end(cudaStream_t stream);
+extern bool g_prof_on;
+
 }  // namespace fp

@@ -112,10 +112,12 @@ def pack_network(sd, kind):
             out[f"head{g}.fin_w"] = f32(sd[f"{h}.1.weight"])
             out[f"head{g}.fin_b"] = f32(sd[f"{h}.1.bias"])
     else:
-        for src, dst in (("att", "att"), ("att_cross", "cross")):
-            out[f"{dst}.in_w"] = h16(sd[f"{src}.in_proj_weight"])
+        # `att` runs on the fp16 tensor-core path; the cross-hypothesis tail stays fp32 end to end
+        # (0.3 GFLOP in total, and it decides the arg-max)
+        for src, dst, cvt in (("att", "att", h16), ("att_cross", "cross", f32)):
+            out[f"{dst}.in_w"] = cvt(sd[f"{src}.in_proj_weight"])
             out[f"{dst}.in_b"] = f32(sd[f"{src}.in_proj_bias"])
-            out[f"{dst}.out_w"] = h16(sd[f"{src}.out_proj.weight"])
+            out[f"{dst}.out_w"] = cvt(sd[f"{src}.out_proj.weight"])
             out[f"{dst}.out_b"] = f32(sd[f"{src}.out_proj.bias"])
         out["lin.w"] = f32(sd["linear.weight"].reshape(-1))
         out["lin.b"] = f32(sd["linear.bias"].reshape(-1))

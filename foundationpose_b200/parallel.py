@@ -1,0 +1,73 @@
+"""Multi-GPU register(): the hypothesis list shards contiguously over the ranks (one process per GPU).
+
+Refinement is per-hypothesis independent (refine_network.py:73-93 has no cross-batch op in eval mode),
+scoring is independent up to the per-hypothesis 512-d feature (score_network.py:60-74) and then couples
+*all* hypotheses through `att_cross` (score_network.py:84-88).  So the only exchange is ONE all-gather of
+[n_local, 512 + 16] floats (feature | refined pose) per rank — NCCL over NVLink/NVSwitch — after which
+every rank runs the identical fp32 tail on the identical gathered buffer and obtains the same scores
+and the same arg-max (bit-exact index agreement across ranks and with the single-GPU run).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n, world, rank):
+    """Contiguous slices whose sizes differ by at most one (252 over 8 -> 32,32,32,32,31,31,31,31)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_counts(n, world):
+    return [shard_bounds(n, world, r)[1] - shard_bounds(n, world, r)[0] for r in range(world)]
+
+
+def gather_rows(local, n_total, group=None):
+    """All-gather row blocks of unequal height: local (n_local, C) -> (n_total, C) on every rank,
+    rows in rank order.  One collective; shards are padded to the largest height."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        assert local.shape[0] == n_total
+        return local
+    world = dist.get_world_size(group)
+    counts = shard_counts(n_total, world)
+    assert local.shape[0] == counts[dist.get_rank(group)], "local shard does not match shard_bounds()"
+    mx = max(counts)
+    C = local.shape[1]
+    send = local.new_zeros(mx, C)
+    send[: local.shape[0]] = local
+    recv = local.new_empty(world * mx, C)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    recv = recv.reshape(world, mx, C)
+    if all(c == mx for c in counts):
+        return recv.reshape(world * mx, C)
+    return torch.cat([recv[r, : counts[r]] for r in range(world)], 0)
+
+
+class ShardedRegister:
+    """register() hot loop over torch.distributed: refine + featurise the local slice, all-gather once,
+    replicate the cross-hypothesis tail."""
+
+    def __init__(self, engine, group=None):
+        self.engine = engine
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def run(self, poses_all, iterations):
+        """poses_all: (N,4,4) identical on every rank (host or device).  Returns refined poses (N,4,4),
+        scores (N,), best index — identical on every rank."""
+        e = self.engine
+        N = len(poses_all)
+        lo, hi = shard_bounds(N, self.world, self.rank)
+        local = torch.as_tensor(poses_all[lo:hi], dtype=torch.float32)
+        if not local.is_cuda:
+            local = local.cuda(non_blocking=True)
+        if hi > lo:
+            refined, _, _ = e.refine(local, iterations)
+            feats = e.score_features(refined)
+            packed = torch.cat([feats, refined.reshape(-1, 16)], 1)
+        else:
+            packed = torch.empty(0, 528, dtype=torch.float32, device="cuda")
+        allp = gather_rows(packed, N, self.group)
+        scores, best = e.score_tail(allp[:, :512].contiguous())
+        return allp[:, 512:].reshape(N, 4, 4), scores, best

@@ -29,6 +29,13 @@ const char* fp_last_error(void);
  * `gpu_launches`). */
 unsigned long long fp_launch_count(void);
 
+/* Per-launch device timing of the two roofline kernels (CUDA events on the launching stream):
+ * kind 0 = tcgen05 implicit-GEMM kernel (work = algorithmic FLOPs), kind 1 = crop producer
+ * (work = algorithmic output bytes).  fp_prof_collect synchronises the device, returns and clears
+ * the sums accumulated since fp_prof_enable(1). */
+int fp_prof_enable(int on);
+int fp_prof_collect(int kind, double* total_ms, double* total_work, int* launches);
+
 /* ------------------------------------------------------------------------------------------ */
 /* single operators (parity-test hooks; the product path below calls the same code)           */
 /* ------------------------------------------------------------------------------------------ */

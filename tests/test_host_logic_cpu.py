@@ -1,0 +1,121 @@
+"""CPU: host-side logic — BN folding / weight packing, hypothesis grid, sharding arithmetic and the
+world_size-2 gather (gloo)."""
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from foundationpose_b200 import hypotheses, packing, synth
+from foundationpose_b200.engine import pack_network
+from foundationpose_b200.parallel import gather_rows, shard_bounds, shard_counts
+from foundationpose_b200.weights import random_state_dict
+
+
+def test_fold_bn_equals_conv_then_bn():
+    torch.manual_seed(0)
+    conv = nn.Conv2d(8, 16, 3, padding=1)
+    bn = nn.BatchNorm2d(16).eval()
+    bn.running_mean.normal_(0, 0.2)
+    bn.running_var.uniform_(0.5, 1.5)
+    bn.weight.data.uniform_(0.5, 1.5)
+    bn.bias.data.normal_(0, 0.2)
+    x = torch.randn(2, 8, 10, 10)
+    w, b = packing.fold_bn(conv.weight, conv.bias, dict(weight=bn.weight, bias=bn.bias, running_mean=bn.running_mean,
+                                                          running_var=bn.running_var, eps=bn.eps))
+    with torch.no_grad():
+        ref = bn(conv(x))
+        got = torch.nn.functional.conv2d(x, w, b, padding=1)
+    assert (ref - got).abs().max() < 1e-5
+
+
+def test_pack_layouts():
+    w = torch.arange(2 * 3 * 3 * 3, dtype=torch.float32).reshape(2, 3, 3, 3)
+    p = packing.pack_conv3(w)
+    assert p.shape == (2, 27) and p.dtype == torch.float16
+    # K order (r, s, c)
+    assert float(p[1, (1 * 3 + 2) * 3 + 1]) == float(w[1, 1, 1, 2])
+    w7 = torch.randn(4, 6, 7, 7)
+    p7 = packing.pack_conv7(w7).float().reshape(4, 7, 8, 8)
+    assert torch.allclose(p7[:, :, :7, :6], w7.permute(0, 2, 3, 1).half().float())
+    assert p7[:, :, 7].abs().max() == 0 and p7[:, :, :, 6:].abs().max() == 0
+    x = torch.rand(2, 6, 160, 160)
+    xp = packing.pad_image_c8(x)
+    assert xp.shape == (2, 166, 168, 8)
+    assert torch.equal(xp[:, 3:163, 3:163, :6], x.permute(0, 2, 3, 1).half())
+    assert xp[:, :3].abs().max() == 0 and xp[..., 6:].abs().max() == 0
+
+
+def test_pack_network_names_and_shapes():
+    r = pack_network(random_state_dict("refine", 0), "refine")
+    assert r["enc.0.w"].shape == (64, 448) and r["enc.14.w"].shape == (512, 4608) and r["heads.in_w"].shape == (3072, 512)
+    assert r["pe"].shape == (400, 512) and r["head1.fin_w"].shape == (3, 512)
+    s = pack_network(random_state_dict("score", 0), "score")
+    assert s["cross.in_w"].dtype == np.float32 and s["att.in_w"].dtype == np.float16 and s["lin.w"].shape == (512,)
+    # use_BN = False checkpoints fold to the plain conv
+    sd = random_state_dict("refine", 0, use_bn=False)
+    r2 = pack_network(sd, "refine")
+    assert np.allclose(r2["enc.1.b"], sd["encodeA.1.net.0.bias"].numpy())
+
+
+def test_rotation_grid_is_252_rigid_poses():
+    g = hypotheses.make_rotation_grid()
+    assert g.shape == (252, 4, 4)
+    R = g[:, :3, :3]
+    assert np.allclose(R @ R.transpose(0, 2, 1), np.eye(3)[None], atol=1e-5)
+    assert np.allclose(np.linalg.det(R), 1, atol=1e-5)
+    # a 2-fold symmetry about z halves the in-plane set
+    sym = np.stack([np.eye(4), np.diag([-1.0, -1.0, 1.0, 1.0])])
+    assert len(hypotheses.make_rotation_grid(symmetry_tfs=sym)) < 252
+
+
+def test_guess_translation_edge_cases():
+    K = synth.DEFAULT_K
+    depth = np.full((480, 640), 0.7, dtype=np.float32)
+    mask = np.zeros((480, 640), dtype=bool)
+    assert np.array_equal(hypotheses.guess_translation(depth, mask, K), np.zeros(3))
+    mask[100:200, 300:400] = True
+    t = hypotheses.guess_translation(depth, mask, K)
+    assert abs(t[2] - 0.7) < 1e-6 and abs(t[0] - (349.5 - 320) / 615 * 0.7) < 1e-6
+    depth[:] = 0
+    assert np.array_equal(hypotheses.guess_translation(depth, mask, K), np.zeros(3))
+
+
+def test_shard_bounds():
+    assert shard_counts(252, 8) == [32, 32, 32, 32, 31, 31, 31, 31]
+    assert shard_counts(252, 1) == [252]
+    assert shard_counts(3, 8) == [1, 1, 1, 0, 0, 0, 0, 0]
+    cover = []
+    for r in range(4):
+        lo, hi = shard_bounds(253, 4, r)
+        cover += list(range(lo, hi))
+    assert cover == list(range(253))
+
+
+def _gather_worker(rank, world, n_total, port, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = torch.arange(n_total * 5, dtype=torch.float32).reshape(n_total, 5)
+    lo, hi = shard_bounds(n_total, world, rank)
+    out = gather_rows(full[lo:hi].clone(), n_total)
+    q.put((rank, torch.equal(out, full)))
+    dist.destroy_process_group()
+
+
+def test_gather_rows_world2_gloo():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    for n_total in (252, 7):
+        q = ctx.Queue()
+        port = 29400 + n_total % 50
+        procs = [ctx.Process(target=_gather_worker, args=(r, 2, n_total, port, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        res = [q.get(timeout=120) for _ in procs]
+        for p in procs:
+            p.join(timeout=60)
+        assert all(ok for _, ok in res), res

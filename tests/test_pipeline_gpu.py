@@ -1,0 +1,140 @@
+"""GPU parity of the end-to-end hot loop (fp_refine / fp_score / FoundationPose.register) against the
+CPU oracle on the same seeded scene, mesh, weights and start poses.
+
+Bars (BASELINE.json north_star): predicted SE(3) delta within 1e-3 (translation in metres, rotation
+matrix entries), selected hypothesis index identical.  At the full 252-hypothesis size the oracle
+is too slow for CI, so size-independent properties are checked instead (determinism, sharding
+invariance, arg-max consistency).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from foundationpose_b200 import synth
+    from foundationpose_b200.engine import Engine
+    from foundationpose_b200.weights import random_state_dict
+    from oracle import pipeline
+
+    mesh = synth.make_mesh(3)
+    pose = np.eye(4)
+    pose[:3, :3] = synth.random_rotation(0)
+    pose[:3, 3] = [0.02, -0.01, 0.6]
+    rgb, depth, mask = synth.make_scene(mesh.visual.image, pose)
+    d = synth.mesh_diameter(mesh.vertices)
+    mt = pipeline.mesh_tensors(mesh)
+    sd_r, sd_s = random_state_dict("refine", 0), random_state_dict("score", 0)
+    e = Engine()
+    e.load_network("refine", sd_r)
+    e.load_network("score", sd_s)
+    e.set_mesh(mt["pos"], mt["normals"], mt["faces"], d, uv=mt["uv"], tex=mt["tex"])
+    e.set_frame(rgb, depth, synth.DEFAULT_K, filter_depth=False)
+    rng = np.random.default_rng(5)
+    poses = np.tile(pose[None], (6, 1, 1)).astype(np.float32)
+    for i in range(1, 6):
+        poses[i, :3, :3] = synth.random_rotation(10 + i) if i % 2 else poses[i, :3, :3]
+        poses[i, :3, 3] += rng.normal(0, 0.01, 3)
+    return dict(e=e, mesh=mesh, mt=mt, rgb=rgb, depth=depth, mask=mask, K=synth.DEFAULT_K, d=d, poses=poses, sd_r=sd_r, sd_s=sd_s, gt=pose)
+
+
+def test_refine_one_iteration_matches_oracle(setup):
+    from oracle import pipeline
+
+    s = setup
+    poses = s["poses"][:4]
+    out, lt, lr = s["e"].refine(poses, 1)
+    ref, rt, rr = pipeline.refine(s["sd_r"], poses, s["mt"], s["rgb"], s["depth"], s["K"], s["d"], 1)
+    np.testing.assert_allclose(lt.cpu().numpy(), rt.numpy(), atol=1e-3, rtol=0)  # metres
+    np.testing.assert_allclose(lr.cpu().numpy(), rr.numpy(), atol=1e-3, rtol=0)
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), atol=1e-3, rtol=0)
+
+
+def test_refine_two_iterations_matches_oracle(setup):
+    from oracle import pipeline
+
+    s = setup
+    poses = s["poses"][:3]
+    out, lt, lr = s["e"].refine(poses, 2)
+    ref, rt, rr = pipeline.refine(s["sd_r"], poses, s["mt"], s["rgb"], s["depth"], s["K"], s["d"], 2)
+    np.testing.assert_allclose(lt.cpu().numpy(), rt.numpy(), atol=1e-3, rtol=0)
+    np.testing.assert_allclose(lr.cpu().numpy(), rr.numpy(), atol=1e-3, rtol=0)
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), atol=2e-3, rtol=0)
+
+
+def test_score_matches_oracle(setup):
+    from oracle import pipeline
+
+    s = setup
+    scores, best = s["e"].score(s["poses"])
+    ref_scores, ref_best = pipeline.score(s["sd_s"], s["poses"], s["mt"], s["rgb"], s["depth"], s["K"], s["d"])
+    got = scores.cpu().numpy()
+    ref = ref_scores.numpy()
+    print("scores", got, ref)
+    np.testing.assert_allclose(got, ref, atol=1e-2, rtol=0)
+    top2 = np.sort(ref)[-2:]
+    if top2[1] - top2[0] > 2e-2:  # index parity is only defined when the oracle's margin exceeds the tolerance
+        assert int(best.item()) == ref_best
+    assert int(best.item()) == int(np.argmax(got))
+
+
+def test_register_properties_full_size(setup):
+    """252 hypotheses x 5 iterations: determinism, sharding invariance, arg-max consistency."""
+    from foundationpose_b200 import hypotheses
+
+    s, e = setup, setup["e"]
+    grid = hypotheses.make_rotation_grid()
+    assert grid.shape == (252, 4, 4)
+    depth = s["depth"]
+    center = hypotheses.guess_translation(depth, s["mask"], s["K"])
+    poses = grid.copy()
+    poses[:, :3, 3] = center
+    p1, _, _ = e.refine(poses, 5)
+    p2, _, _ = e.refine(poses, 5)
+    assert torch.equal(p1, p2), "refine is not deterministic"
+    sc1, b1 = e.score(p1)
+    sc2, b2 = e.score(p1)
+    assert torch.equal(sc1, sc2) and int(b1) == int(b2)
+    assert int(b1) == int(sc1.argmax())
+    # sharded: two halves refined / featurised independently, then one tail on the gathered features
+    h = 126
+    pa, _, _ = e.refine(poses[:h], 5)
+    pb, _, _ = e.refine(poses[h:], 5)
+    assert torch.equal(torch.cat([pa, pb]), p1), "refinement must be per-hypothesis independent"
+    fa = e.score_features(pa).clone()
+    fb = e.score_features(pb).clone()
+    sc3, b3 = e.score_tail(torch.cat([fa, fb]))
+    assert torch.equal(sc3, sc1) and int(b3) == int(b1)
+    # host-buffer entry point agrees with the device one
+    ph, sh, bh = e.register_host(poses, 5)
+    assert torch.equal(ph.cuda(), p1) and bh == int(b1)
+    assert torch.isfinite(sc1).all() and torch.isfinite(p1).all()
+
+
+def test_foundationpose_api(setup):
+    """estimater.FoundationPose.register()/track_one() drop-in surface."""
+    from foundationpose_b200 import synth
+    from foundationpose_b200.estimater import FoundationPose, PoseRefinePredictor, ScorePredictor
+
+    s = setup
+    mesh = s["mesh"]
+    scorer = ScorePredictor(engine=s["e"], state_dict=s["sd_s"])
+    refiner = PoseRefinePredictor(engine=s["e"], state_dict=s["sd_r"])
+    est = FoundationPose(model_pts=mesh.vertices, model_normals=mesh.vertex_normals, mesh=mesh, scorer=scorer, refiner=refiner)
+    with pytest.raises(RuntimeError):
+        est.track_one(rgb=s["rgb"], depth=s["depth"], K=s["K"], iteration=2)
+    pose = est.register(K=s["K"], rgb=s["rgb"], depth=s["depth"], ob_mask=s["mask"], iteration=2)
+    assert pose.shape == (4, 4) and np.isfinite(pose).all()
+    assert est.poses.shape == (252, 4, 4) and est.scores.shape == (252,)
+    assert float(est.scores[0]) == float(est.scores.max())
+    p2 = est.track_one(rgb=s["rgb"], depth=s["depth"], K=s["K"], iteration=2)
+    assert p2.shape == (4, 4) and np.isfinite(p2).all()
+    # empty mask -> identity rotation + zero translation fallback (estimater.py:184-189, :139-141)
+    p3 = est.register(K=s["K"], rgb=s["rgb"], depth=s["depth"], ob_mask=np.zeros_like(s["mask"]), iteration=1)
+    np.testing.assert_array_equal(p3, np.eye(4))
+    # restore the fixture's frame/mesh state for other tests
+    s["e"].set_mesh(s["mt"]["pos"], s["mt"]["normals"], s["mt"]["faces"], s["d"], uv=s["mt"]["uv"], tex=s["mt"]["tex"])
+    s["e"].set_frame(s["rgb"], s["depth"], s["K"], filter_depth=False)
