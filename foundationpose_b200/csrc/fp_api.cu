@@ -1,8 +1,11 @@
 // fp_api.cu — the product C ABI (include/fpose.h): context, weights, mesh, frame, and the per-frame
 // hot loop (crops -> encoder -> heads -> pose update, K times; then scoring) enqueued on one stream
 // with no host synchronisation.
+#include <stdlib.h>
+
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/fpose.h"
@@ -20,8 +23,13 @@ struct DevBuf {
   size_t bytes = 0;
 };
 
+// bumped whenever a device pointer or by-value kernel parameter that a captured CUDA graph may hold
+// changes (re-allocation, new mesh / weights / intrinsics): cached graphs older than this are rebuilt
+static unsigned long long g_epoch = 1;
+
 static int dev_alloc(DevBuf& b, size_t bytes, bool zero = false) {
   if (b.bytes >= bytes && b.p) return 0;
+  ++g_epoch;
   if (b.p) cudaFree(b.p);
   b.p = nullptr;
   b.bytes = 0;
@@ -70,6 +78,16 @@ struct fp_ctx {
   fp::DevBuf head_out, poses_a, poses_b, feats, tail_qkv, tail_attn, tail_proj, scores, best;
   int tail_cap = 0;
   float lin_b_host = 0.f;  // scorer linear.bias, kept on the host so the tail launch never syncs
+  // CUDA graphs of the launch-bound inner loops, keyed by (kind, N, iterations)
+  struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    unsigned long long epoch = 0;
+  };
+  std::map<std::tuple<int, int, int>, GraphEntry> graphs;
+  std::map<std::tuple<int, int, int>, int> graph_nodes;
+  cudaStream_t cap_stream = nullptr;
+  bool use_graphs = true;
+  fp::DevBuf lt_buf, lr_buf, feat_buf, pose_stage;
 };
 
 namespace fp {
@@ -101,6 +119,10 @@ static int ensure_capacity(fp_ctx* c, int N) {
   rc |= dev_alloc(c->poses_a, n * 16 * 4);
   rc |= dev_alloc(c->poses_b, n * 16 * 4);
   rc |= dev_alloc(c->feats, n * 512 * 4);
+  rc |= dev_alloc(c->lt_buf, n * 3 * 4);
+  rc |= dev_alloc(c->lr_buf, n * 9 * 4);
+  rc |= dev_alloc(c->feat_buf, n * 512 * 4);
+  rc |= dev_alloc(c->pose_stage, n * 16 * 4);
   if (rc) return -2;
   c->cap_n = N;
   return 0;
@@ -280,6 +302,51 @@ static int make_crops(fp_ctx* c, const float* poses, int N, int mode, float* dbg
   return crop_launch(p, st);
 }
 
+
+// Runs `body(stream)` — a fixed sequence of kernel launches on ctx-owned buffers — through a cached
+// CUDA graph: first sight of a key runs eagerly (sets function attributes, sizes workspaces), the second
+// captures + instantiates, later calls replay.  Replay removes ~170 launch + 60 tensor-map-encode host
+// calls per register(), which is what bounds track_one() and small per-GPU shards.
+template <class Body>
+static int run_graphed(fp_ctx* c, int kind, int N, int iters, cudaStream_t st, Body body) {
+  if (!c->use_graphs || g_prof_on) return body(st);
+  const auto key = std::make_tuple(kind, N, iters);
+  auto it = c->graphs.find(key);
+  if (it == c->graphs.end()) {
+    c->graphs[key] = fp_ctx::GraphEntry();  // seen once: next call captures
+    return body(st);
+  }
+  fp_ctx::GraphEntry& g = it->second;
+  if (g.exec == nullptr || g.epoch != g_epoch) {
+    if (g.exec) {
+      cudaGraphExecDestroy(g.exec);
+      g.exec = nullptr;
+    }
+    if (!c->cap_stream) FP_CUDA_OK(cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
+    const unsigned long long launches_before = g_launch_count;
+    FP_CUDA_OK(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = body(c->cap_stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(c->cap_stream, &graph);
+    g_launch_count = launches_before;  // nothing ran during capture
+    if (rc != 0) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    FP_CUDA_OK(ce);
+    size_t n_nodes = 0;
+    cudaGraphGetNodes(graph, nullptr, &n_nodes);
+    const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    FP_CUDA_OK(ie);
+    g.epoch = g_epoch;
+    c->graph_nodes[key] = (int)n_nodes;
+  }
+  FP_CUDA_OK(cudaGraphLaunch(g.exec, st));
+  g_launch_count += (unsigned long long)c->graph_nodes[key];
+  return 0;
+}
+
 }  // namespace fp
 
 using namespace fp;
@@ -298,6 +365,8 @@ int fp_create(fp_ctx** out) {
   FP_REQUIRE(prop.major == 10, "libfpose targets sm_100a (B200); device %d is sm_%d%d", dev, prop.major, prop.minor);
   fp_ctx* c = new fp_ctx();
   c->device = dev;
+  const char* ng = getenv("FPOSE_NO_GRAPH");
+  c->use_graphs = !(ng && ng[0] == '1');
   *out = c;
   return 0;
 }
@@ -313,6 +382,12 @@ int fp_destroy(fp_ctx* c) {
                     &c->scores, &c->best};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
+  for (auto& kv : c->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
+  DevBuf* more[] = {&c->lt_buf, &c->lr_buf, &c->feat_buf, &c->pose_stage};
+  for (DevBuf* b : more)
+    if (b->p) cudaFree(b->p);
   delete c;
   return 0;
 }
@@ -321,6 +396,7 @@ int fp_set_config(fp_ctx* c, float crop_ratio, float rot_normalizer) {
   FP_REQUIRE(c, "null ctx");
   c->crop_ratio = crop_ratio;
   c->rot_normalizer = rot_normalizer;
+  ++g_epoch;
   return 0;
 }
 
@@ -328,6 +404,7 @@ int fp_load_network(fp_ctx* c, int which, const fp_tensor_t* tensors, int n) {
   FP_REQUIRE(c && tensors, "fp_load_network: null argument");
   FP_REQUIRE(which == 0 || which == 1, "fp_load_network: which must be 0 (refiner) or 1 (scorer)");
   Net& net = c->net[which];
+  ++g_epoch;
   for (auto& kv : net.t) cudaFree(kv.second.p);
   net.t.clear();
   net.loaded = false;
@@ -421,6 +498,7 @@ int fp_set_mesh(fp_ctx* c, int V, int F, const float* pos, const float* nrm, con
   c->F = F;
   c->diameter = diameter;
   c->has_mesh = true;
+  ++g_epoch;
   return 0;
 }
 
@@ -445,6 +523,9 @@ int fp_set_frame(fp_ctx* c, const unsigned char* rgb, const float* depth, const 
     rgb_dev = reinterpret_cast<const unsigned char*>(c->rgb_raw.p);
     depth_dev = reinterpret_cast<const float*>(c->depth_raw.p);
   }
+  bool same = (c->H == H && c->W == W);
+  for (int i = 0; i < 9; ++i) same = same && (c->K[i] == K[i]);
+  if (!same) ++g_epoch;  // intrinsics / frame size are by-value kernel parameters
   for (int i = 0; i < 9; ++i) c->K[i] = K[i];
   c->H = H;
   c->W = W;
@@ -528,22 +609,34 @@ int fp_refine(fp_ctx* c, const float* poses_in, int N, int iterations, float* po
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (N == 0) return 0;
   FP_TRY(ensure_capacity(c, N));
-  float* cur = reinterpret_cast<float*>(c->poses_a.p);
-  float* nxt = reinterpret_cast<float*>(c->poses_b.p);
-  FP_CUDA_OK(cudaMemcpyAsync(cur, poses_in, (size_t)N * 64, cudaMemcpyDeviceToDevice, st));
-  const float* ho = reinterpret_cast<const float*>(c->head_out.p);
-  for (int it = 0; it < iterations; ++it) {
-    FP_TRY(make_crops(c, cur, N, 0, nullptr, nullptr, st));
-    FP_TRY(run_encoder(c, c->net[0], reinterpret_cast<const __half*>(c->crops.p), N, st));
-    FP_TRY(run_refine_heads(c, c->net[0], N, st));
-    const bool last = it == iterations - 1;
-    FP_TRY(pose_update_launch(cur, ho, ho + (size_t)N * 3, nxt, last ? last_trans : nullptr, last ? last_rot : nullptr, N,
-                              c->diameter / 2.0f, c->rot_normalizer, st));
-    float* t = cur;
-    cur = nxt;
-    nxt = t;
+  float* pa = reinterpret_cast<float*>(c->poses_a.p);
+  float* pb = reinterpret_cast<float*>(c->poses_b.p);
+  FP_CUDA_OK(cudaMemcpyAsync(pa, poses_in, (size_t)N * 64, cudaMemcpyDeviceToDevice, st));
+  auto body = [&](cudaStream_t s2) -> int {
+    float* cur = pa;
+    float* nxt = pb;
+    const float* ho = reinterpret_cast<const float*>(c->head_out.p);
+    for (int it = 0; it < iterations; ++it) {
+      FP_TRY(make_crops(c, cur, N, 0, nullptr, nullptr, s2));
+      FP_TRY(run_encoder(c, c->net[0], reinterpret_cast<const __half*>(c->crops.p), N, s2));
+      FP_TRY(run_refine_heads(c, c->net[0], N, s2));
+      const bool last = it == iterations - 1;
+      FP_TRY(pose_update_launch(cur, ho, ho + (size_t)N * 3, nxt, last ? reinterpret_cast<float*>(c->lt_buf.p) : nullptr,
+                                last ? reinterpret_cast<float*>(c->lr_buf.p) : nullptr, N, c->diameter / 2.0f,
+                                c->rot_normalizer, s2));
+      float* t = cur;
+      cur = nxt;
+      nxt = t;
+    }
+    return 0;
+  };
+  FP_TRY(run_graphed(c, 0, N, iterations, st, body));
+  const float* fin = (iterations % 2 == 0) ? pa : pb;
+  FP_CUDA_OK(cudaMemcpyAsync(poses_out, fin, (size_t)N * 64, cudaMemcpyDeviceToDevice, st));
+  if (iterations > 0) {
+    if (last_trans) FP_CUDA_OK(cudaMemcpyAsync(last_trans, c->lt_buf.p, (size_t)N * 12, cudaMemcpyDeviceToDevice, st));
+    if (last_rot) FP_CUDA_OK(cudaMemcpyAsync(last_rot, c->lr_buf.p, (size_t)N * 36, cudaMemcpyDeviceToDevice, st));
   }
-  FP_CUDA_OK(cudaMemcpyAsync(poses_out, cur, (size_t)N * 64, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
@@ -553,9 +646,17 @@ int fp_score_features(fp_ctx* c, const float* poses, int N, float* feats_out, vo
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (N == 0) return 0;
   FP_TRY(ensure_capacity(c, N));
-  FP_TRY(make_crops(c, poses, N, 1, nullptr, nullptr, st));
-  FP_TRY(run_encoder(c, c->net[1], reinterpret_cast<const __half*>(c->crops.p), N, st));
-  FP_TRY(run_score_feats(c, c->net[1], N, feats_out, st));
+  float* ps = reinterpret_cast<float*>(c->pose_stage.p);
+  float* fb = reinterpret_cast<float*>(c->feat_buf.p);
+  FP_CUDA_OK(cudaMemcpyAsync(ps, poses, (size_t)N * 64, cudaMemcpyDeviceToDevice, st));
+  auto body = [&](cudaStream_t s2) -> int {
+    FP_TRY(make_crops(c, ps, N, 1, nullptr, nullptr, s2));
+    FP_TRY(run_encoder(c, c->net[1], reinterpret_cast<const __half*>(c->crops.p), N, s2));
+    FP_TRY(run_score_feats(c, c->net[1], N, fb, s2));
+    return 0;
+  };
+  FP_TRY(run_graphed(c, 1, N, 0, st, body));
+  FP_CUDA_OK(cudaMemcpyAsync(feats_out, fb, (size_t)N * 2048, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 

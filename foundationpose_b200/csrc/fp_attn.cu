@@ -229,7 +229,15 @@ __device__ __forceinline__ float warp_sum(float x) {
   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
   return x;
 }
-__device__ __forceinline__ void ln_row16(float (&v)[16], const float* gamma, const float* beta, int lane, float eps) {
+// gamma/beta slices of this lane (16 channels), loaded once per warp with vector loads
+struct LnAffine {
+  float g[16], b[16];
+};
+__device__ __forceinline__ void ln_load_affine(LnAffine& a, const float* gamma, const float* beta, int lane) {
+  load_row16(gamma, lane, a.g);
+  load_row16(beta, lane, a.b);
+}
+__device__ __forceinline__ void ln_row16(float (&v)[16], const LnAffine& a, float eps) {
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < 16; ++i) s += v[i];
@@ -242,28 +250,34 @@ __device__ __forceinline__ void ln_row16(float (&v)[16], const float* gamma, con
   }
   const float rstd = rsqrtf(warp_sum(q) * (1.f / 512.f) + eps);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = (v[i] - mean) * rstd * __ldg(gamma + lane * 16 + i) + __ldg(beta + lane * 16 + i);
+  for (int i = 0; i < 16; ++i) v[i] = (v[i] - mean) * rstd * a.g[i] + a.b[i];
 }
 
-__global__ void layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, int rows, float eps) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// persistent: each warp walks rows with a grid stride, keeping gamma/beta in registers
+__global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        int rows, float eps) {
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  float v[16];
-  load_row16(x + (size_t)row * 512, lane, v);
-  ln_row16(v, gamma, beta, lane, eps);
-  uint32_t o[8];
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  LnAffine af;
+  ln_load_affine(af, gamma, beta, lane);
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps_total) {
+    float v[16];
+    load_row16(x + (size_t)row * 512, lane, v);
+    ln_row16(v, af, eps);
+    uint32_t o[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = pack_half2(v[2 * i], v[2 * i + 1]);
-  uint4* dst = reinterpret_cast<uint4*>(y + (size_t)row * 512 + lane * 16);
-  dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-  dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    for (int i = 0; i < 8; ++i) o[i] = pack_half2(v[2 * i], v[2 * i + 1]);
+    uint4* dst = reinterpret_cast<uint4*>(y + (size_t)row * 512 + lane * 16);
+    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
 }
 
 int layernorm_launch(const __half* x, __half* y, const float* gamma, const float* beta, int rows, cudaStream_t stream) {
   if (rows == 0) return 0;
-  layernorm_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, y, gamma, beta, rows, 1e-5f);
+  const int blocks = min((rows + 7) / 8, 148 * 8);
+  layernorm_kernel<<<blocks, 256, 0, stream>>>(x, y, gamma, beta, rows, 1e-5f);
   ++g_launch_count;
   FP_CUDA_OK(cudaGetLastError());
   return 0;
@@ -280,10 +294,12 @@ __global__ void __launch_bounds__(256) head_final_kernel(const __half* __restric
   float a[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) a[i] = 0.f;
+  LnAffine af;
+  ln_load_affine(af, gamma, beta, lane);
   for (int t = warp; t < T; t += 8) {
     float v[16];
     load_row16(x + ((size_t)b * T + t) * 512, lane, v);
-    ln_row16(v, gamma, beta, lane, eps);
+    ln_row16(v, af, eps);
 #pragma unroll
     for (int i = 0; i < 16; ++i) a[i] += v[i];
   }

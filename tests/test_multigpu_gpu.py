@@ -1,0 +1,64 @@
+"""2-GPU: the sharded register (one process per GPU, NCCL all-gather of per-hypothesis features) returns
+bit-identical poses, scores and best index to the single-GPU run.  Skipped on boxes with < 2 GPUs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from foundationpose_b200 import hypotheses, synth
+    from foundationpose_b200.engine import Engine
+    from foundationpose_b200.estimater import make_mesh_tensors
+    from foundationpose_b200.parallel import ShardedRegister
+    from foundationpose_b200.weights import random_state_dict
+
+    mesh, gt, K, rgb, depth, mask = synth.default_scene(3, 0)
+    e = Engine()
+    e.load_network("refine", random_state_dict("refine", 0))
+    e.load_network("score", random_state_dict("score", 0))
+    mt = make_mesh_tensors(mesh)
+    e.set_mesh(mt["pos"], mt["normals"], mt["faces"], synth.mesh_diameter(mesh.vertices), uv=mt["uv"], tex=mt["tex"])
+    e.set_frame(rgb, depth, K, filter_depth=True)
+    d, _ = e.get_depth()
+    poses = hypotheses.make_rotation_grid()
+    poses[:, :3, 3] = hypotheses.guess_translation(d.cpu().numpy(), mask, K)
+    poses = torch.from_numpy(poses)
+    sh = ShardedRegister(e)
+    p, s, b = sh.run(poses, 2)
+    out = dict(rank=rank, poses=p.cpu().numpy(), scores=s.cpu().numpy(), best=int(b.item()))
+    if rank == 0:
+        # single-GPU reference on the same device
+        p1, _, _ = e.refine(poses, 2)
+        s1, b1 = e.score(p1)
+        out.update(poses1=p1.cpu().numpy(), scores1=s1.cpu().numpy(), best1=int(b1.item()))
+    q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_register_equals_single_gpu():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, 29611, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=600) for _ in procs], key=lambda d: d["rank"])
+    for p in procs:
+        p.join(timeout=120)
+    r0, r1 = res
+    assert np.array_equal(r0["poses"], r1["poses"]) and np.array_equal(r0["scores"], r1["scores"]) and r0["best"] == r1["best"]
+    assert np.array_equal(r0["poses"], r0["poses1"]), "sharded refinement differs from single-GPU"
+    assert np.array_equal(r0["scores"], r0["scores1"]) and r0["best"] == r0["best1"]
