@@ -55,6 +55,11 @@ struct Net {
 constexpr int S = 160;
 constexpr int T = 400;
 constexpr size_t kCropImg = (size_t)(S + 6) * (S + 8) * 8;  // fp16 elements per padded crop image
+// The encoder's first stage runs on the A (rendered) and B (observed) crops as one batch.  The 40x40
+// layers tile two images per 128-row MMA tile, and the layer that fuses torch.cat((a, b), 1) stores A and
+// B tiles to different channel halves, so the A/B boundary must fall on a tile boundary: B starts at
+// N rounded up to 2 (one never-read pad image when N is odd).
+static inline int b_img0_of(int N) { return (N + 1) & ~1; }
 
 }  // namespace fp
 
@@ -97,11 +102,12 @@ static int ensure_capacity(fp_ctx* c, int N) {
   const size_t n = (size_t)N;
   int rc = 0;
   // the crop buffer is zeroed once: the 3-pixel border is never written afterwards
-  rc |= dev_alloc(c->crops, 2 * n * kCropImg * 2, true);
-  rc |= dev_alloc(c->act0, 2 * n * 80 * 80 * 64 * 2);
-  rc |= dev_alloc(c->a1, 2 * n * 1600 * 128 * 2);
-  rc |= dev_alloc(c->a2, 2 * n * 1600 * 128 * 2);
-  rc |= dev_alloc(c->a3, 2 * n * 1600 * 128 * 2);
+  const size_t m = 2 * n + 1;  // A + pad + B images
+  rc |= dev_alloc(c->crops, m * kCropImg * 2, true);
+  rc |= dev_alloc(c->act0, m * 80 * 80 * 64 * 2);
+  rc |= dev_alloc(c->a1, m * 1600 * 128 * 2);
+  rc |= dev_alloc(c->a2, m * 1600 * 128 * 2);
+  rc |= dev_alloc(c->a3, m * 1600 * 128 * 2);
   rc |= dev_alloc(c->ab0, n * 1600 * 256 * 2);
   rc |= dev_alloc(c->ab1, n * 1600 * 256 * 2);
   rc |= dev_alloc(c->ab2, n * 1600 * 256 * 2);
@@ -175,14 +181,15 @@ static int run_encoder(fp_ctx* c, const Net& net, const __half* crops, int N, cu
   char wn[32], bn[32];
   auto W = [&](int i) { snprintf(wn, sizeof wn, "enc.%d.w", i); return net.h(wn); };
   auto B = [&](int i) { snprintf(bn, sizeof bn, "enc.%d.b", i); return net.f(bn); };
-  const int M = 2 * N;
+  const int Np = b_img0_of(N);
+  const int M = Np + N;
   FP_TRY(gemm_layer_launch(mk(LK_CONV7_S2, M, S, S, 8, 64, crops, W(0), B(0), c->act0.p, 1), st));
   FP_TRY(gemm_layer_launch(mk(LK_CONV3_S2, M, 80, 80, 64, 128, c->act0.p, W(1), B(1), c->a1.p, 1), st));
   FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, M, 40, 40, 128, 128, c->a1.p, W(2), B(2), c->a2.p, 1), st));
   FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, M, 40, 40, 128, 128, c->a2.p, W(3), B(3), c->a3.p, 1, c->a1.p), st));
   FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, M, 40, 40, 128, 128, c->a3.p, W(4), B(4), c->a2.p, 1), st));
   // last encodeA layer writes straight into the 256-channel concat buffer (refine_network.py:85)
-  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, M, 40, 40, 128, 128, c->a2.p, W(5), B(5), c->ab0.p, 1, c->a3.p, 256, N), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, M, 40, 40, 128, 128, c->a2.p, W(5), B(5), c->ab0.p, 1, c->a3.p, 256, Np), st));
   FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, N, 40, 40, 256, 256, c->ab0.p, W(6), B(6), c->ab1.p, 1), st));
   FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, N, 40, 40, 256, 256, c->ab1.p, W(7), B(7), c->ab2.p, 1, c->ab0.p), st));
   FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, N, 40, 40, 256, 256, c->ab2.p, W(8), B(8), c->ab1.p, 1), st));
@@ -268,6 +275,26 @@ static int run_score_feats(fp_ctx* c, const Net& net, int N, float* feats, cudaS
   return 0;
 }
 
+// external crop layout of the test hooks: [2N] images, A then B, contiguous
+static int crops_import(fp_ctx* c, const void* ext, int N, cudaStream_t st) {
+  const size_t img = kCropImg * 2;
+  __half* dst = reinterpret_cast<__half*>(c->crops.p);
+  const char* src = reinterpret_cast<const char*>(ext);
+  FP_CUDA_OK(cudaMemcpyAsync(dst, src, (size_t)N * img, cudaMemcpyDeviceToDevice, st));
+  FP_CUDA_OK(cudaMemcpyAsync(dst + (size_t)b_img0_of(N) * kCropImg, src + (size_t)N * img, (size_t)N * img,
+                             cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+static int crops_export(fp_ctx* c, void* ext, int N, cudaStream_t st) {
+  const size_t img = kCropImg * 2;
+  const __half* src = reinterpret_cast<const __half*>(c->crops.p);
+  char* dst = reinterpret_cast<char*>(ext);
+  FP_CUDA_OK(cudaMemcpyAsync(dst, src, (size_t)N * img, cudaMemcpyDeviceToDevice, st));
+  FP_CUDA_OK(cudaMemcpyAsync(dst + (size_t)N * img, src + (size_t)b_img0_of(N) * kCropImg, (size_t)N * img,
+                             cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
 static int make_crops(fp_ctx* c, const float* poses, int N, int mode, float* dbg, float* win, cudaStream_t st) {
   FP_REQUIRE(c->has_mesh, "no mesh: call fp_set_mesh first");
   FP_REQUIRE(c->has_frame, "no frame: call fp_set_frame first");
@@ -297,6 +324,7 @@ static int make_crops(fp_ctx* c, const float* poses, int N, int mode, float* dbg
   p.depth = c->depth_cur;
   p.mode = mode;
   p.crops = reinterpret_cast<__half*>(c->crops.p);
+  p.b_img0 = b_img0_of(N);
   p.dbg = dbg;
   p.win_out = win;
   return crop_launch(p, st);
@@ -561,8 +589,7 @@ int fp_make_crops(fp_ctx* c, const float* poses, int N, int mode, void* crops_ou
   if (N == 0) return 0;
   FP_TRY(ensure_capacity(c, N));
   FP_TRY(make_crops(c, poses, N, mode, dbg_out, win_out, st));
-  if (crops_out)
-    FP_CUDA_OK(cudaMemcpyAsync(crops_out, c->crops.p, 2 * (size_t)N * kCropImg * 2, cudaMemcpyDeviceToDevice, st));
+  if (crops_out) FP_TRY(crops_export(c, crops_out, N, st));
   return 0;
 }
 
@@ -572,7 +599,8 @@ int fp_op_refine_net(fp_ctx* c, const void* crops, int N, float* trans_out, floa
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (N == 0) return 0;
   FP_TRY(ensure_capacity(c, N));
-  FP_TRY(run_encoder(c, c->net[0], reinterpret_cast<const __half*>(crops), N, st));
+  FP_TRY(crops_import(c, crops, N, st));
+  FP_TRY(run_encoder(c, c->net[0], reinterpret_cast<const __half*>(c->crops.p), N, st));
   FP_TRY(run_refine_heads(c, c->net[0], N, st));
   const float* ho = reinterpret_cast<const float*>(c->head_out.p);
   FP_CUDA_OK(cudaMemcpyAsync(trans_out, ho, (size_t)N * 12, cudaMemcpyDeviceToDevice, st));
@@ -586,7 +614,8 @@ int fp_op_score_feats(fp_ctx* c, const void* crops, int N, float* feats_out, voi
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (N == 0) return 0;
   FP_TRY(ensure_capacity(c, N));
-  FP_TRY(run_encoder(c, c->net[1], reinterpret_cast<const __half*>(crops), N, st));
+  FP_TRY(crops_import(c, crops, N, st));
+  FP_TRY(run_encoder(c, c->net[1], reinterpret_cast<const __half*>(c->crops.p), N, st));
   FP_TRY(run_score_feats(c, c->net[1], N, feats_out, st));
   return 0;
 }
@@ -597,7 +626,8 @@ int fp_op_tokens(fp_ctx* c, int which, const void* crops, int N, void* tokens_ou
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (N == 0) return 0;
   FP_TRY(ensure_capacity(c, N));
-  FP_TRY(run_encoder(c, c->net[which], reinterpret_cast<const __half*>(crops), N, st));
+  FP_TRY(crops_import(c, crops, N, st));
+  FP_TRY(run_encoder(c, c->net[which], reinterpret_cast<const __half*>(c->crops.p), N, st));
   FP_CUDA_OK(cudaMemcpyAsync(tokens_out, c->tok.p, (size_t)N * T * 512 * 2, cudaMemcpyDeviceToDevice, st));
   return 0;
 }

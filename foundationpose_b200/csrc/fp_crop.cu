@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kCropThreads, 1) crop_kernel(const CropParams 
   const float tau = p.mode == 0 ? 0.001f : 0.1f;
   const size_t img_stride = (size_t)(S + 6) * (S + 8) * 8;
   __half* outA = p.crops + (size_t)n * img_stride;
-  __half* outB = p.crops + (size_t)(p.N + n) * img_stride;
+  __half* outB = p.crops + (size_t)(p.b_img0 + n) * img_stride;
 
   for (int pix = tid; pix < S * S; pix += kCropThreads) {
     const int r = pix / S, j = pix - r * S;

@@ -28,7 +28,8 @@ struct CropParams {
   const float* depth;    // [H][W]      (mode 1)
   int mode;              // 0 = refiner crops, 1 = scorer crops
   // outputs
-  __half* crops;   // [2N][166][168][8] fp16: images 0..N-1 = rendered (A), N..2N-1 = observed (B)
+  __half* crops;   // [b_img0 + N][166][168][8] fp16: images 0..N-1 = rendered (A), b_img0..b_img0+N-1 = observed (B)
+  int b_img0;      // first B image (N rounded up to the conv tile's image count, see fp_api.cu)
   float* dbg;      // optional [N][2][160][160][6] fp32 copy of the normalised crops
   float* win_out;  // optional [N][4] = (left, top, sx, sy)
 };

@@ -100,10 +100,8 @@ struct GemmParams {
   short tap_off[9][5];
   int Ho, Wo, n_img, Cout;
   const float* bias;
-  const __half* res;
-  int res_ld;
-  __half* out;
-  int out_ld;
+  int has_res;
+  int odim_h, odim_n;  // which coordinate of the output / residual maps receives the tile's row / image
   int out_split;
   const float* post_add;
   int relu;
@@ -114,6 +112,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kThreads = 192;
+constexpr int kSlabBytes = kBlockM * 64 * 2;  // 16 KB: one output slab (128 pixels x 64 channels, 128B-swizzled)
 
 template <int BN>
 struct TileCfg {
@@ -121,23 +120,27 @@ struct TileCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : 6;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = 2 * kSlabBytes;  // epilogue: two 128-row x 64-channel fp16 slabs
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-    gemm_tile_kernel(const __grid_constant__ CUtensorMap map_a,
-                     const __grid_constant__ CUtensorMap map_b, const __grid_constant__ GemmParams p) {
+    gemm_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                     const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
+                     const __grid_constant__ GemmParams p) {
   using Cfg = TileCfg<BN>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  uint8_t* staging = smem + S * Cfg::kStageBytes;  // [2][kSlabBytes], 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
   uint64_t* full = bars;                 // [S]
   uint64_t* empty = bars + S;            // [S]
   uint64_t* tmem_full = bars + 2 * S;    // [2]
   uint64_t* tmem_empty = bars + 2 * S + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  uint64_t* res_full = bars + 2 * S + 4;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -152,7 +155,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 128);
+      mbar_init(&res_full[a], 1);
     }
+    tma_prefetch_desc(&map_out);
+    if (p.has_res) tma_prefetch_desc(&map_res);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -232,12 +238,19 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // TMEM -> registers -> (+bias, +residual, ReLU, +pos.emb.) -> fp16 -> 128B-swizzled smem slab ->
+    // one TMA tensor store per 128-pixel x 64-channel slab.  The residual slab arrives the same way
+    // (TMA load into the slab buffer), so every global access of the epilogue is a bulk, fully
+    // coalesced transfer; out-of-range rows are clipped (store) / zero-filled (load) by the TMA unit.
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp may read
     const int row = quarter * 32 + lane;
     const int jj = row & (p.bw - 1);
     const int ii = (row >> p.lg_bw) & (p.bh - 1);
-    const int nn = row >> (p.lg_bw + p.lg_bh);
+    const bool leader = (warp == 2 && lane == 0);
+    const uint32_t row_off = (uint32_t)row * 128u;
+    const uint32_t sw = (uint32_t)(row & 7);
     int it = 0;
+    uint32_t slab_ctr = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const int acc_phase = (it >> 1) & 1;
@@ -246,63 +259,86 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int tw = m_tile % p.tiles_w;
       const int th = (m_tile / p.tiles_w) % p.tiles_h;
       const int tn = m_tile / (p.tiles_w * p.tiles_h);
-      const int n = tn * p.bn + nn, i = th * p.bh + ii, j = tw * p.bw + jj;
-      const bool valid = (n < p.n_img) && (i < p.Ho) && (j < p.Wo);
-      int n_o = n, coff = 0;
+      const int i = th * p.bh + ii, j = tw * p.bw + jj;
+      const int n0 = tn * p.bn;
+      int n_o0 = n0, coff = 0;
       if (p.out_split > 0) {
-        n_o = n % p.out_split;
-        coff = (n / p.out_split) * p.Cout;
+        n_o0 = n0 % p.out_split;
+        coff = (n0 / p.out_split) * p.Cout;
       }
-      const size_t pix = (size_t)(n * p.Ho + i) * p.Wo + j;
-      const size_t pix_o = (size_t)(n_o * p.Ho + i) * p.Wo + j;
-      __half* outp = p.out + pix_o * p.out_ld + coff + n_tile * BN;
-      const __half* resp = p.res ? p.res + pix * p.res_ld + n_tile * BN : nullptr;
       const float* pap = p.post_add ? p.post_add + (size_t)(i * p.Wo + j) * p.Cout + n_tile * BN : nullptr;
       const float* bp = p.bias + n_tile * BN;
+      // output / residual box coordinates (dim 0 = channel is added per slab)
+      int oc[5] = {0, 0, 0, 0, 0}, rc[5] = {0, 0, 0, 0, 0};
+      oc[1] = rc[1] = tw * p.bw;
+      if (p.odim_h >= 0) oc[p.odim_h] = rc[p.odim_h] = th * p.bh;
+      if (p.odim_n >= 0) {
+        oc[p.odim_n] = n_o0;
+        rc[p.odim_n] = n0;
+      }
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c, v);
+      for (int c = 0; c < BN; c += 64, ++slab_ctr) {
+        const uint32_t buf = slab_ctr & 1u;
+        uint8_t* slab = staging + buf * kSlabBytes;
+        // the TMA store that last used this buffer (two slabs ago) must have finished reading it
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (p.has_res) {
+          if (leader) {
+            mbar_expect_tx(&res_full[buf], kSlabBytes);
+            tma_load_5d(&map_res, &res_full[buf], slab, n_tile * BN + c, rc[1], rc[2], rc[3], rc[4]);
+          }
+        }
+        uint32_t v0[32], v1[32];
+        tmem_ld32(taddr + c, v0);
+        tmem_ld32(taddr + c + 32, v1);
         tmem_ld_wait();
-        if (valid) {
-          uint4 rv[4];
-          if (resp) {
+        if (c + 64 >= BN) {
+          // accumulator fully read: hand the TMEM stage back to the MMA warp before the stores
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[acc]);
+        }
+        if (p.has_res) mbar_wait(&res_full[buf], (slab_ctr >> 1) & 1u);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) rv[q] = __ldg(reinterpret_cast<const uint4*>(resp + c) + q);
+        for (int q = 0; q < 8; ++q) {  // 8 chunks of 8 channels (16 B)
+          uint4* cell = reinterpret_cast<uint4*>(slab + row_off + (((uint32_t)q ^ sw) << 4));
+          float a[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            a[k] = __uint_as_float(q < 4 ? v0[(q & 3) * 8 + k] : v1[(q & 3) * 8 + k]) + __ldg(bp + c + q * 8 + k);
+          if (p.has_res) {
+            const uint4 r = *cell;
+            const __half2* rh = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 rf = __half22float2(rh[k]);
+              a[2 * k] += rf.x;
+              a[2 * k + 1] += rf.y;
+            }
           }
-          uint32_t o[16];
+          if (p.relu) {
 #pragma unroll
-          for (int k = 0; k < 32; k += 2) {
-            float a0 = __uint_as_float(v[k]) + __ldg(bp + c + k);
-            float a1 = __uint_as_float(v[k + 1]) + __ldg(bp + c + k + 1);
-            if (resp) {
-              const __half2 r2 = reinterpret_cast<const __half2*>(rv)[k >> 1];
-              const float2 rf = __half22float2(r2);
-              a0 += rf.x;
-              a1 += rf.y;
-            }
-            if (p.relu) {
-              a0 = fmaxf(a0, 0.f);
-              a1 = fmaxf(a1, 0.f);
-            }
-            if (pap) {
-              a0 += __ldg(pap + c + k);
-              a1 += __ldg(pap + c + k + 1);
-            }
-            o[k >> 1] = pack_half2(a0, a1);
+            for (int k = 0; k < 8; ++k) a[k] = fmaxf(a[k], 0.f);
           }
+          if (pap) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            reinterpret_cast<uint4*>(outp + c)[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+            for (int k = 0; k < 8; ++k) a[k] += __ldg(pap + c + q * 8 + k);
+          }
+          *cell = make_uint4(pack_half2(a[0], a[1]), pack_half2(a[2], a[3]), pack_half2(a[4], a[5]), pack_half2(a[6], a[7]));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (leader) {
+          tma_store_5d(&map_out, slab, coff + n_tile * BN + c, oc[1], oc[2], oc[3], oc[4]);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
-      tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
     }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // smem must outlive the stores
   }
 
   tc_fence_before();
@@ -369,7 +405,8 @@ static int ilog2(int v) {
 static int g_num_sms = 0;
 
 template <int BN>
-static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
+static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mr,
+                     const GemmParams& p, cudaStream_t stream) {
   using Cfg = TileCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -384,7 +421,7 @@ static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const GemmPar
   }
   int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   prof_mark_begin(0, p.alg_flops, stream);
-  gemm_tile_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ma, mb, p);
+  gemm_tile_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ma, mb, mo, mr, p);
   prof_mark_end(stream);
   ++g_launch_count;
   FP_CUDA_OK(cudaGetLastError());
@@ -497,10 +534,7 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
   p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles_n;
   p.Ho = Ho; p.Wo = Wo; p.n_img = L.n_img; p.Cout = L.Cout;
   p.bias = L.bias;
-  p.res = reinterpret_cast<const __half*>(L.res);
-  p.res_ld = L.res_ld;
-  p.out = reinterpret_cast<__half*>(L.out);
-  p.out_ld = L.out_ld;
+  p.has_res = L.res != nullptr;
   p.out_split = L.out_split;
   p.post_add = L.post_add;
   p.relu = L.relu;
@@ -509,6 +543,9 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
     p.alg_flops = 2.0 * (double)L.n_img * Ho * Wo * L.Cout * k_real;
   }
   FP_REQUIRE(L.out_ld % 8 == 0 && (!L.res || L.res_ld % 8 == 0), "out_ld / res_ld must be multiples of 8");
+  FP_REQUIRE(L.out_split == 0 || L.out_split % p.bn == 0,
+             "out_split=%d must be a multiple of the tile's image count %d (pad the A/B batch boundary)", L.out_split,
+             p.bn);
   if (p.total_tiles == 0) return 0;
 
   int rc = encode_map(&ma, L.in, 5, dims, str, box);
@@ -518,11 +555,48 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
   uint32_t wb[2] = {64, (uint32_t)BN};
   rc = encode_map(&mb, L.w, 2, wd, ws, wb);
   if (rc) return rc;
+  // output / residual maps: NHWC (conv) or [M][ld] (linear), one box = 128 pixels x 64 channels
+  CUtensorMap mo, mr;
+  {
+    uint64_t od[5], os[4];
+    uint32_t ob[5];
+    const bool lin = (L.kind == LK_LINEAR);
+    const int n_out = L.out_split > 0 ? (L.n_img - L.out_split) : L.n_img;
+    FP_REQUIRE(n_out > 0, "out_split=%d leaves no output images (n_img=%d)", L.out_split, L.n_img);
+    auto fill = [&](int ld, int nimg) {
+      od[0] = (uint64_t)ld;
+      od[1] = (uint64_t)Wo;
+      od[2] = lin ? 1 : (uint64_t)Ho;
+      od[3] = lin ? 1 : (uint64_t)nimg;
+      od[4] = 1;
+      os[0] = (uint64_t)ld * E;
+      os[1] = os[0] * Wo;
+      os[2] = lin ? os[1] : os[1] * Ho;
+      os[3] = lin ? os[1] : os[2] * nimg;
+      ob[0] = 64;
+      ob[1] = (uint32_t)p.bw;
+      ob[2] = lin ? 1 : (uint32_t)p.bh;
+      ob[3] = lin ? 1 : (uint32_t)p.bn;
+      ob[4] = 1;
+    };
+    p.odim_h = lin ? -1 : 2;
+    p.odim_n = lin ? -1 : 3;
+    fill(L.out_ld, n_out);
+    rc = encode_map(&mo, L.out, 5, od, os, ob);
+    if (rc) return rc;
+    if (L.res) {
+      fill(L.res_ld, L.n_img);
+      rc = encode_map(&mr, L.res, 5, od, os, ob);
+      if (rc) return rc;
+    } else {
+      mr = mo;
+    }
+  }
 
   switch (BN) {
-    case 256: return launch_bn<256>(ma, mb, p, stream);
-    case 128: return launch_bn<128>(ma, mb, p, stream);
-    default: return launch_bn<64>(ma, mb, p, stream);
+    case 256: return launch_bn<256>(ma, mb, mo, mr, p, stream);
+    case 128: return launch_bn<128>(ma, mb, mo, mr, p, stream);
+    default: return launch_bn<64>(ma, mb, mo, mr, p, stream);
   }
 }
 
