@@ -93,6 +93,7 @@ struct fp_ctx {
   cudaStream_t cap_stream = nullptr;
   bool use_graphs = true;
   fp::DevBuf lt_buf, lr_buf, feat_buf, pose_stage;
+  fp::DevBuf vtx_a, vtx_b, win_buf;  // crop producer workspaces: [cap_n][V] x 16 B each, [cap_n][8]
 };
 
 namespace fp {
@@ -298,7 +299,14 @@ static int crops_export(fp_ctx* c, void* ext, int N, cudaStream_t st) {
 static int make_crops(fp_ctx* c, const float* poses, int N, int mode, float* dbg, float* win, cudaStream_t st) {
   FP_REQUIRE(c->has_mesh, "no mesh: call fp_set_mesh first");
   FP_REQUIRE(c->has_frame, "no frame: call fp_set_frame first");
+  FP_TRY(dev_alloc(c->vtx_a, (size_t)c->cap_n * c->V * 16));
+  FP_TRY(dev_alloc(c->vtx_b, (size_t)c->cap_n * c->V * 16));
+  FP_TRY(dev_alloc(c->win_buf, (size_t)c->cap_n * 8 * 4));
   CropParams p;
+  p.vtx_a = reinterpret_cast<VtxA*>(c->vtx_a.p);
+  p.vtx_b = reinterpret_cast<VtxB*>(c->vtx_b.p);
+  p.win_buf = reinterpret_cast<float*>(c->win_buf.p);
+  p.V = c->V;
   p.poses = poses;
   p.N = N;
   p.fx = c->K[0];
@@ -413,7 +421,7 @@ int fp_destroy(fp_ctx* c) {
   for (auto& kv : c->graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
-  DevBuf* more[] = {&c->lt_buf, &c->lr_buf, &c->feat_buf, &c->pose_stage};
+  DevBuf* more[] = {&c->lt_buf, &c->lr_buf, &c->feat_buf, &c->pose_stage, &c->vtx_a, &c->vtx_b, &c->win_buf};
   for (DevBuf* b : more)
     if (b->p) cudaFree(b->p);
   delete c;

@@ -161,48 +161,208 @@ __device__ __forceinline__ void normalise_xyz(float x, float y, float z, const f
   if (inv || fabsf(oz) >= 2.f) oz = 0.f;
 }
 
+// ------------------------------------------------------------------------------------------------
+// pass 0: one thread per (hypothesis, vertex): camera transform, projection into the crop raster,
+// 1/256-px snap, per-vertex diffuse term.  16 + 16 bytes per vertex, written once, read ~6x (L2).
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) VtxA {  // what the z-buffer pass needs
+  int xi, yi;
+  float iz, Z;
+};
+struct __align__(16) VtxB {  // what shading additionally needs
+  float X, Y, dif, pad;
+};
+
+__global__ void __launch_bounds__(256) vertex_kernel(const CropParams p) {
+  __shared__ float sP[16];
+  __shared__ Window sW;
+  const int n = blockIdx.y;
+  if (threadIdx.x < 16) sP[threadIdx.x] = p.poses[(size_t)n * 16 + threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Window w;
+    crop_window(sP, p.fx, p.fy, p.cx, p.cy, p.r3, w);
+    sW = w;
+    if (blockIdx.x == 0) {
+      float* wb = p.win_buf + (size_t)n * 8;
+      wb[0] = w.left; wb[1] = w.top; wb[2] = w.sx; wb[3] = w.sy;
+      wb[4] = w.umin; wb[5] = w.vmin; wb[6] = w.rsx; wb[7] = w.rsy;
+      if (p.win_out) {
+        p.win_out[n * 4 + 0] = w.left;
+        p.win_out[n * 4 + 1] = w.top;
+        p.win_out[n * 4 + 2] = w.sx;
+        p.win_out[n * 4 + 3] = w.sy;
+      }
+    }
+  }
+  __syncthreads();
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= p.V) return;
+  VtxScreen o;
+  xform_vertex(sP, p.vpos + 3 * v, sW, p.fx, p.fy, p.cx, p.cy, o);
+  // diffuse = clip(normalize(R n) . (0,0,-1), 0, 1)   (Utils.py:203-207)
+  const float nx = __ldg(p.vnrm + 3 * v), ny = __ldg(p.vnrm + 3 * v + 1), nz = __ldg(p.vnrm + 3 * v + 2);
+  const float cxn = sP[0] * nx + sP[1] * ny + sP[2] * nz;
+  const float cyn = sP[4] * nx + sP[5] * ny + sP[6] * nz;
+  const float czn = sP[8] * nx + sP[9] * ny + sP[10] * nz;
+  const float len = fmaxf(sqrtf(cxn * cxn + cyn * cyn + czn * czn), 1e-12f);
+  VtxA a;
+  a.xi = o.xi; a.yi = o.yi; a.iz = o.iz; a.Z = o.Z;
+  VtxB b;
+  b.X = o.X; b.Y = o.Y; b.dif = fminf(fmaxf(-czn / len, 0.f), 1.f); b.pad = 0.f;
+  p.vtx_a[(size_t)n * p.V + v] = a;
+  p.vtx_b[(size_t)n * p.V + v] = b;
+}
+
+// 32-bit edge functions relative to vertex 0 when the triangle is small enough (all deltas < 2^15, i.e.
+// < 128 px: products < 2^30); the integers are the same as the 64-bit ones, so coverage is unchanged.
+struct TriSetup32 {
+  int area2;
+  int x0, y0;               // vertex 0 (absolute, 1/256 px)
+  int ax, ay, bx, by;       // oriented vertices 1 and 2 relative to vertex 0
+  int swapped;
+};
+
+__device__ __forceinline__ bool tri_small(int x0, int y0, int x1, int y1, int x2, int y2) {
+  const int m = max(max(abs(x1 - x0), abs(y1 - y0)), max(abs(x2 - x0), abs(y2 - y0)));
+  return m < 16384;
+}
+__device__ __forceinline__ bool tri_setup32(int x0, int y0, int x1, int y1, int x2, int y2, TriSetup32& t) {
+  t.x0 = x0; t.y0 = y0;
+  t.ax = x1 - x0; t.ay = y1 - y0; t.bx = x2 - x0; t.by = y2 - y0;
+  t.swapped = 0;
+  int area2 = t.ax * t.by - t.ay * t.bx;
+  if (area2 == 0) return false;
+  if (area2 < 0) {
+    int tx = t.ax, ty = t.ay;
+    t.ax = t.bx; t.ay = t.by; t.bx = tx; t.by = ty;
+    t.swapped = 1;
+    area2 = -area2;
+  }
+  t.area2 = area2;
+  return true;
+}
+__device__ __forceinline__ bool edge_ok32(int e, int dx, int dy) {
+  return e > 0 || (e == 0 && (dy > 0 || (dy == 0 && dx > 0)));
+}
+// pixel centre (px, py) absolute; must lie inside the triangle's bounding box (deltas < 2^15)
+__device__ __forceinline__ bool tri_cover32(const TriSetup32& t, int px, int py, float& b0, float& b1, float& b2) {
+  const int qx = px - t.x0, qy = py - t.y0;
+  // e0: edge v1->v2 (weight of v0); e1: edge v2->v0 (weight of v1); e2 = area2 - e0 - e1
+  const int e0 = (t.bx - t.ax) * (qy - t.ay) - (t.by - t.ay) * (qx - t.ax);
+  const int e1 = (-t.bx) * (qy - t.by) - (-t.by) * (qx - t.bx);
+  const int e2 = t.area2 - e0 - e1;
+  if (!edge_ok32(e0, t.bx - t.ax, t.by - t.ay) || !edge_ok32(e1, -t.bx, -t.by) || !edge_ok32(e2, t.ax, t.ay)) return false;
+  const float fa = __int2float_rn(t.area2);
+  b0 = __fdiv_rn(__int2float_rn(e0), fa);
+  const float w1 = __fdiv_rn(__int2float_rn(e1), fa);
+  const float w2 = __fdiv_rn(__int2float_rn(e2), fa);
+  b1 = t.swapped ? w2 : w1;
+  b2 = t.swapped ? w1 : w2;
+  return true;
+}
+
+// rare path: triangles spanning >= 128 px use the 64-bit edge functions (same integers, same coverage)
+__device__ __noinline__ void raster_big_tri(const VtxA a, const VtxA b, const VtxA c, int f, int j0, int j1, int r0,
+                                            int r1, unsigned long long* zbuf) {
+  VtxScreen sa, sb, sc;
+  sa.xi = a.xi; sa.yi = a.yi; sb.xi = b.xi; sb.yi = b.yi; sc.xi = c.xi; sc.yi = c.yi;
+  TriSetup t;
+  if (!tri_setup(sa, sb, sc, t)) return;
+  for (int r = r0; r <= r1; ++r)
+    for (int j = j0; j <= j1; ++j) {
+      float b0, b1, b2;
+      if (!tri_cover(t, j * 256 + 128, r * 256 + 128, b0, b1, b2)) continue;
+      const float iz = inv_depth(b0, b1, b2, a.iz, b.iz, c.iz);
+      const unsigned long long key =
+          ((unsigned long long)__float_as_uint(iz) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)f);
+      atomicMax(&zbuf[r * S + j], key);
+    }
+}
+__device__ __noinline__ void bary_big_tri(const VtxA a, const VtxA b, const VtxA c, int px, int py, float* bw) {
+  VtxScreen sa, sb, sc;
+  sa.xi = a.xi; sa.yi = a.yi; sb.xi = b.xi; sb.yi = b.yi; sc.xi = c.xi; sc.yi = c.yi;
+  TriSetup t;
+  tri_setup(sa, sb, sc, t);
+  float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+  tri_cover(t, px, py, b0, b1, b2);
+  bw[0] = b0; bw[1] = b1; bw[2] = b2;
+}
+
+constexpr int kTabBytes = 8 * S * 4;  // per-axis resampling tables
+
 __global__ void __launch_bounds__(kCropThreads, 1) crop_kernel(const CropParams p) {
-  extern __shared__ unsigned long long zbuf[];  // [S*S]
+  extern __shared__ unsigned long long zbuf[];  // [S*S] then the tables
+  float* colf = reinterpret_cast<float*>(zbuf + S * S);  // source x of crop column j (kornia chain)
+  float* rowf = colf + S;
+  int* coln = reinterpret_cast<int*>(rowf + S);           // nearest source column (or -1)
+  int* rown = coln + S;
+  int* colz = rown + S;                                   // scorer: source column of the depth round trip (or -1)
+  int* rowz = colz + S;
   __shared__ float sP[16];
   __shared__ Window sW;
   const int n = blockIdx.x;
   const int tid = threadIdx.x;
 
   if (tid < 16) sP[tid] = p.poses[(size_t)n * 16 + tid];
-  __syncthreads();
-  if (tid == 0) {
+  if (tid == 32) {
+    const float* wb = p.win_buf + (size_t)n * 8;
     Window w;
-    crop_window(sP, p.fx, p.fy, p.cx, p.cy, p.r3, w);
+    w.left = wb[0]; w.top = wb[1]; w.sx = wb[2]; w.sy = wb[3];
+    w.umin = wb[4]; w.vmin = wb[5]; w.rsx = wb[6]; w.rsy = wb[7];
     sW = w;
-    if (p.win_out) {
-      p.win_out[n * 4 + 0] = w.left;
-      p.win_out[n * 4 + 1] = w.top;
-      p.win_out[n * 4 + 2] = w.sx;
-      p.win_out[n * 4 + 3] = w.sy;
-    }
   }
   for (int i = tid; i < S * S; i += kCropThreads) zbuf[i] = 0ull;
   __syncthreads();
   const Window w = sW;
+  // per-axis tables of the observed-crop resampling (every quantity is separable in x and y)
+  if (tid < 2 * S) {
+    const bool is_row = tid >= S;
+    const int d = is_row ? tid - S : tid;
+    const float sc = is_row ? w.sy : w.sx, org = is_row ? w.top : w.left;
+    const int size = is_row ? p.H : p.W;
+    const float xs = __fadd_rn(__fdiv_rn((float)d, sc), org);
+    const float ix = kornia_src_coord(xs, size);
+    int un = (int)rintf(ix);
+    if (un < 0 || un >= size) un = -1;
+    int uz = -1;
+    if (un >= 0) {
+      // scorer: depth crop -> full-res (nearest) -> back-project -> crop (nearest), h5_dataset.py:158-161
+      const float xc = __fadd_rn(__fmul_rn(sc, (float)un), __fmul_rn(-org, sc));
+      const int jc = (int)rintf(kornia_src_coord(xc, S));
+      if (jc >= 0 && jc < S) {
+        const float xs2 = __fadd_rn(__fdiv_rn((float)jc, sc), org);
+        const int u2 = (int)rintf(kornia_src_coord(xs2, size));
+        if (u2 >= 0 && u2 < size) uz = u2;
+      }
+    }
+    (is_row ? rowf : colf)[d] = ix;
+    (is_row ? rown : coln)[d] = un;
+    (is_row ? rowz : colz)[d] = uz;
+  }
+  const VtxA* va = p.vtx_a + (size_t)n * p.V;
+  const VtxB* vb = p.vtx_b + (size_t)n * p.V;
 
   // ---------------------------------------------------------------- pass 1: z-buffer
   for (int f = tid; f < p.F; f += kCropThreads) {
     const int i0 = __ldg(p.faces + 3 * f), i1 = __ldg(p.faces + 3 * f + 1), i2 = __ldg(p.faces + 3 * f + 2);
-    VtxScreen a, b, c;
-    xform_vertex(sP, p.vpos + 3 * i0, w, p.fx, p.fy, p.cx, p.cy, a);
-    xform_vertex(sP, p.vpos + 3 * i1, w, p.fx, p.fy, p.cx, p.cy, b);
-    xform_vertex(sP, p.vpos + 3 * i2, w, p.fx, p.fy, p.cx, p.cy, c);
+    const VtxA a = va[i0], b = va[i1], c = va[i2];
     if (!(a.Z > p.znear && b.Z > p.znear && c.Z > p.znear)) continue;  // no near-plane clipping
-    TriSetup t;
-    if (!tri_setup(a, b, c, t)) continue;
     const int minx = min(a.xi, min(b.xi, c.xi)), maxx = max(a.xi, max(b.xi, c.xi));
     const int miny = min(a.yi, min(b.yi, c.yi)), maxy = max(a.yi, max(b.yi, c.yi));
     const int j0 = max((minx + 127) >> 8, 0), j1 = min((maxx - 128) >> 8, S - 1);
     const int r0 = max((miny + 127) >> 8, 0), r1 = min((maxy - 128) >> 8, S - 1);
+    if (j0 > j1 || r0 > r1) continue;
+    if (!tri_small(a.xi, a.yi, b.xi, b.yi, c.xi, c.yi)) {
+      raster_big_tri(a, b, c, f, j0, j1, r0, r1, zbuf);
+      continue;
+    }
+    TriSetup32 t32;
+    if (!tri_setup32(a.xi, a.yi, b.xi, b.yi, c.xi, c.yi, t32)) continue;
     for (int r = r0; r <= r1; ++r)
       for (int j = j0; j <= j1; ++j) {
         float b0, b1, b2;
-        if (!tri_cover(t, j * 256 + 128, r * 256 + 128, b0, b1, b2)) continue;
+        if (!tri_cover32(t32, j * 256 + 128, r * 256 + 128, b0, b1, b2)) continue;
         const float iz = inv_depth(b0, b1, b2, a.iz, b.iz, c.iz);
         const unsigned long long key =
             ((unsigned long long)__float_as_uint(iz) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)f);
@@ -227,34 +387,26 @@ __global__ void __launch_bounds__(kCropThreads, 1) crop_kernel(const CropParams 
     if (key != 0ull) {
       const int f = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
       const int i0 = __ldg(p.faces + 3 * f), i1 = __ldg(p.faces + 3 * f + 1), i2 = __ldg(p.faces + 3 * f + 2);
-      VtxScreen a, b, c;
-      xform_vertex(sP, p.vpos + 3 * i0, w, p.fx, p.fy, p.cx, p.cy, a);
-      xform_vertex(sP, p.vpos + 3 * i1, w, p.fx, p.fy, p.cx, p.cy, b);
-      xform_vertex(sP, p.vpos + 3 * i2, w, p.fx, p.fy, p.cx, p.cy, c);
-      TriSetup t;
-      tri_setup(a, b, c, t);
+      const VtxA a = va[i0], b = va[i1], c = va[i2];
+      const VtxB a2 = vb[i0], b2v = vb[i1], c2 = vb[i2];
       float b0, b1, b2;
-      tri_cover(t, j * 256 + 128, r * 256 + 128, b0, b1, b2);
+      if (tri_small(a.xi, a.yi, b.xi, b.yi, c.xi, c.yi)) {
+        TriSetup32 t32;
+        tri_setup32(a.xi, a.yi, b.xi, b.yi, c.xi, c.yi, t32);
+        tri_cover32(t32, j * 256 + 128, r * 256 + 128, b0, b1, b2);
+      } else {
+        float bw[3];
+        bary_big_tri(a, b, c, j * 256 + 128, r * 256 + 128, bw);
+        b0 = bw[0]; b1 = bw[1]; b2 = bw[2];
+      }
       const float iz = inv_depth(b0, b1, b2, a.iz, b.iz, c.iz);
       // perspective-correct weights (nvdiffrast: barycentrics computed in clip space)
       const float z = 1.f / iz;
       const float w0 = b0 * a.iz * z, w1 = b1 * b.iz * z, w2 = b2 * c.iz * z;
-      const float X = w0 * a.X + w1 * b.X + w2 * c.X;
-      const float Y = w0 * a.Y + w1 * b.Y + w2 * c.Y;
+      const float X = w0 * a2.X + w1 * b2v.X + w2 * c2.X;
+      const float Y = w0 * a2.Y + w1 * b2v.Y + w2 * c2.Y;
       const float Z = w0 * a.Z + w1 * b.Z + w2 * c.Z;
-      // diffuse = interpolate(clip(normalize(R n) . (0,0,-1), 0, 1))   (Utils.py:203-207)
-      float dif[3];
-      const int vi[3] = {i0, i1, i2};
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const float nx = __ldg(p.vnrm + 3 * vi[k]), ny = __ldg(p.vnrm + 3 * vi[k] + 1), nz = __ldg(p.vnrm + 3 * vi[k] + 2);
-        const float cxn = sP[0] * nx + sP[1] * ny + sP[2] * nz;
-        const float cyn = sP[4] * nx + sP[5] * ny + sP[6] * nz;
-        const float czn = sP[8] * nx + sP[9] * ny + sP[10] * nz;
-        const float len = fmaxf(sqrtf(cxn * cxn + cyn * cyn + czn * czn), 1e-12f);
-        dif[k] = fminf(fmaxf(-czn / len, 0.f), 1.f);
-      }
-      const float diffuse = w0 * dif[0] + w1 * dif[1] + w2 * dif[2];
+      const float diffuse = w0 * a2.dif + w1 * b2v.dif + w2 * c2.dif;
       float cr, cg, cb;
       if (p.tex) {
         const float tu = w0 * __ldg(p.vuv + 2 * i0) + w1 * __ldg(p.vuv + 2 * i1) + w2 * __ldg(p.vuv + 2 * i2);
@@ -288,9 +440,7 @@ __global__ void __launch_bounds__(kCropThreads, 1) crop_kernel(const CropParams 
     // ---- B: observed crop
     float br = 0.f, bg = 0.f, bb = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
     {
-      const float xs = __fadd_rn(__fdiv_rn((float)j, w.sx), w.left);
-      const float ys = __fadd_rn(__fdiv_rn((float)r, w.sy), w.top);
-      const float ix = kornia_src_coord(xs, p.W), iy = kornia_src_coord(ys, p.H);
+      const float ix = colf[j], iy = rowf[r];
       // bilinear rgb, zeros padding
       const float fx0 = floorf(ix), fy0 = floorf(iy);
       const int x0 = (int)fx0, y0 = (int)fy0;
@@ -312,9 +462,9 @@ __global__ void __launch_bounds__(kCropThreads, 1) crop_kernel(const CropParams 
       bg *= (1.f / 255.f);
       bb *= (1.f / 255.f);
       // nearest geometry
-      const int un = (int)rintf(ix), vn = (int)rintf(iy);
+      const int un = coln[j], vn = rown[r];
       float X = 0.f, Y = 0.f, Z = 0.f;
-      if (un >= 0 && un < p.W && vn >= 0 && vn < p.H) {
+      if (un >= 0 && vn >= 0) {
         if (p.mode == 0) {
           // refiner: xyz_map (depth2xyzmap, Utils.py:399-438) sampled nearest
           const float* q = p.xyz_map + ((size_t)vn * p.W + un) * 3;
@@ -322,17 +472,9 @@ __global__ void __launch_bounds__(kCropThreads, 1) crop_kernel(const CropParams 
           Y = __ldg(q + 1);
           Z = __ldg(q + 2);
         } else {
-          // scorer: depth crop -> full-res (nearest) -> back-project -> crop (nearest), h5_dataset.py:158-161
-          const float xc = __fadd_rn(__fmul_rn(w.sx, (float)un), __fmul_rn(-w.left, w.sx));
-          const float yc = __fadd_rn(__fmul_rn(w.sy, (float)vn), __fmul_rn(-w.top, w.sy));
-          const int jc = (int)rintf(kornia_src_coord(xc, S)), rc = (int)rintf(kornia_src_coord(yc, S));
+          const int u2 = colz[j], v2 = rowz[r];
           float zz = 0.f;
-          if (jc >= 0 && jc < S && rc >= 0 && rc < S) {
-            const float xs2 = __fadd_rn(__fdiv_rn((float)jc, w.sx), w.left);
-            const float ys2 = __fadd_rn(__fdiv_rn((float)rc, w.sy), w.top);
-            const int u2 = (int)rintf(kornia_src_coord(xs2, p.W)), v2 = (int)rintf(kornia_src_coord(ys2, p.H));
-            if (u2 >= 0 && u2 < p.W && v2 >= 0 && v2 < p.H) zz = __ldg(p.depth + (size_t)v2 * p.W + u2);
-          }
+          if (u2 >= 0 && v2 >= 0) zz = __ldg(p.depth + (size_t)v2 * p.W + u2);
           if (zz >= 0.001f) {  // depth2xyzmap_batch(zfar=inf): invalid z<0.001 -> 0
             X = ((float)un - p.cx) * zz / p.fx;
             Y = ((float)vn - p.cy) * zz / p.fy;
@@ -357,15 +499,16 @@ __global__ void __launch_bounds__(kCropThreads, 1) crop_kernel(const CropParams 
 int crop_launch(const CropParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    FP_CUDA_OK(cudaFuncSetAttribute(crop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kZbufBytes));
+    FP_CUDA_OK(cudaFuncSetAttribute(crop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kZbufBytes + kTabBytes));
     attr_set = true;
   }
   if (p.N == 0) return 0;
   // algorithmic bytes: the two 6-channel fp16 crops each hypothesis produces
   prof_mark_begin(1, (double)p.N * 2.0 * 6.0 * S * S * 2.0, stream);
-  crop_kernel<<<p.N, kCropThreads, kZbufBytes, stream>>>(p);
+  vertex_kernel<<<dim3((p.V + 255) / 256, p.N), 256, 0, stream>>>(p);
+  crop_kernel<<<p.N, kCropThreads, kZbufBytes + kTabBytes, stream>>>(p);
   prof_mark_end(stream);
-  ++g_launch_count;
+  g_launch_count += 2;
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -19,7 +19,7 @@ struct CropParams {
   const float* vuv;    // [V][2] (v already flipped, Utils.py:117) or null
   const float* vcol;   // [V][3] in 0..1 or null
   const int* faces;    // [F][3]
-  int F;
+  int V, F;
   const uchar4* tex;   // [Ht][Wt] RGBA8 or null
   int Ht, Wt;
   // frame (device)
@@ -30,6 +30,10 @@ struct CropParams {
   // outputs
   __half* crops;   // [b_img0 + N][166][168][8] fp16: images 0..N-1 = rendered (A), b_img0..b_img0+N-1 = observed (B)
   int b_img0;      // first B image (N rounded up to the conv tile's image count, see fp_api.cu)
+  // workspaces (device): per-hypothesis pre-transformed vertices and crop windows
+  struct VtxA* vtx_a;  // [N][V] 16 B
+  struct VtxB* vtx_b;  // [N][V] 16 B
+  float* win_buf;      // [N][8]
   float* dbg;      // optional [N][2][160][160][6] fp32 copy of the normalised crops
   float* win_out;  // optional [N][4] = (left, top, sx, sy)
 };
