@@ -18,6 +18,7 @@
 #include "fp_attn.cuh"
 
 #include <mma.h>
+#include <stdlib.h>
 
 #include "fp_common.cuh"
 #include "fp_gemm.cuh"
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32, 1) attn_core_kernel(const Att
   }
 }
 
-int attn_core_launch(const AttnParams& p, cudaStream_t stream) {
+int attn_legacy_launch(const AttnParams& p, cudaStream_t stream) {
   FP_REQUIRE(p.T == kT && p.n_heads == 4, "attention core is specialised for T=400, 4 heads of 128 (got T=%d)", p.T);
   static bool attr_set = false;
   if (!attr_set) {
@@ -194,6 +195,15 @@ int attn_core_launch(const AttnParams& p, cudaStream_t stream) {
   ++g_launch_count;
   FP_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+int attn_core_launch(const AttnParams& p, cudaStream_t stream) {
+  static int use_tc = -1;
+  if (use_tc < 0) {
+    const char* e = getenv("FPOSE_ATTN");
+    use_tc = (e && e[0] == 'l') ? 0 : 1;
+  }
+  return use_tc ? attn_tc_launch(p, stream) : attn_legacy_launch(p, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -396,6 +396,11 @@ static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64
   return 0;
 }
 
+int encode_map_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  return encode_map(map, base, rank, dims, strides_bytes, box);
+}
+
 static int ilog2(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;

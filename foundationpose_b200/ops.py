@@ -43,3 +43,17 @@ def gemm_layer(kind, x, w_packed, bias, *, n_img, Hin, Win, Cin, Cout, out=None,
                        res_ld, _ptr(out), out_ld, out_split, _ptr(post_add), 1 if relu else 0)
     _lib.check(lib.fp_op_gemm_layer(C.byref(L), _stream()), "fp_op_gemm_layer")
     return out
+
+
+lib.fp_op_attention.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+lib.fp_op_attention.restype = C.c_int
+
+
+def attention(qkv, impl=1):
+    """qkv fp16 [B*400, 1536] -> fp16 [B*400, 512]; impl 1 = tcgen05, 0 = mma.sync."""
+    _require_cuda(qkv)
+    assert qkv.dtype == torch.float16 and qkv.shape[1] == 1536 and qkv.shape[0] % 400 == 0
+    B = qkv.shape[0] // 400
+    out = torch.empty(qkv.shape[0], 512, dtype=torch.float16, device=qkv.device)
+    _lib.check(lib.fp_op_attention(_ptr(qkv), _ptr(out), B, impl, _stream()), "fp_op_attention")
+    return out

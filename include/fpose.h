@@ -61,13 +61,19 @@ typedef struct fp_gemm_layer {
   int res_ld;
   void* out;          /* fp16 NHWC output                                                         */
   int out_ld;         /* elements between consecutive output pixels                               */
-  int out_split;      /* >0: image n goes to image n % out_split at channel (n / out_split)*Cout  */
+  int out_split;      /* >0: image n goes to image n % out_split at channel (n / out_split)*Cout;
+                         must be a multiple of the tile's image count (2 for >= 8x8 outputs, else 8)  */
   const float* post_add; /* optional fp32 [Ho*Wo][Cout], added after the activation               */
   int relu;
 } fp_gemm_layer_t;
 
 /* Runs one layer: out = act(in (*) w + bias [+ res]) [+ post_add]. */
 int fp_op_gemm_layer(const fp_gemm_layer_t* layer, void* stream);
+
+/* softmax(Q K^T / sqrt(128)) V of nn.MultiheadAttention (refine_network.py:56-70, score_network.py:53):
+ * qkv fp16 [B*400][1536] (q | k | v, 4 heads of 128 each), out fp16 [B*400][512].
+ * impl 1 = tcgen05 kernel (product path), 0 = the mma.sync kernel kept for A/B checks. */
+int fp_op_attention(const void* qkv, void* out, int B, int impl, void* stream);
 
 
 /* ------------------------------------------------------------------------------------------ */

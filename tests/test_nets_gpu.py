@@ -114,3 +114,19 @@ def test_score_tail_252(engine):
     ref = nets.score_tail(sd_s, feats, 252).reshape(-1)
     np.testing.assert_allclose(scores.cpu().numpy() - 100.0, ref.numpy(), atol=3e-3, rtol=0)
     assert int(best.item()) == int(ref.argmax())
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_attention_core(impl):
+    """softmax(QK^T/sqrt(128))V for 400 tokens x 4 heads vs torch fp32 on the same fp16 q, k, v."""
+    from foundationpose_b200 import ops
+
+    g = torch.Generator().manual_seed(21 + impl)
+    B = 3
+    qkv = (torch.randn(B * 400, 1536, generator=g) * 1.5).half().cuda()
+    out = ops.attention(qkv, impl=impl).float()
+    q, k, v = qkv.float().reshape(B, 400, 3, 4, 128).permute(2, 0, 3, 1, 4)
+    att = torch.softmax(q @ k.transpose(-1, -2) / 128 ** 0.5, dim=-1)
+    ref = (att @ v).permute(0, 2, 1, 3).reshape(B * 400, 512)
+    err = (out - ref).abs().max().item()
+    assert err < 4e-3, f"attention impl {impl}: max err {err}"
