@@ -23,6 +23,7 @@
 #include "fp_gemm.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -114,22 +115,25 @@ constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kThreads = 192;
 constexpr int kSlabBytes = kBlockM * 64 * 2;  // 16 KB: one output slab (128 pixels x 64 channels, 128B-swizzled)
 
-template <int BN>
+// CG = CTAs per MMA (tcgen05 cta_group): with CG = 2 the CTA pair of a cluster issues one M = 256 MMA; each CTA
+// stages its own 128 pixel rows of A and only HALF of the weight tile (BN/2 rows), which halves the B-operand
+// shared-memory traffic per SM — the bound of the N <= 128 layers.
+template <int BN, int CG>
 struct TileCfg {
-  static constexpr int kBBytes = BN * kBlockK * 2;
+  static constexpr int kBBytes = (BN / CG) * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
   static constexpr int kStagingBytes = 2 * kSlabBytes;  // epilogue: two 128-row x 64-channel fp16 slabs
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
                      const __grid_constant__ GemmParams p) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, CG>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -144,6 +148,11 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cta_rank = (CG == 2) ? (int)cluster_ctarank() : 0;
+  // virtual tiles: (pair of M tiles, N tile) for CG = 2; this CTA owns M tile  vt_m * CG + cta_rank
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int total_vt = ((m_tiles + CG - 1) / CG) * p.n_tiles_n;
+  const int vt0 = blockIdx.x / CG, vt_step = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -154,29 +163,47 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 128);
+      mbar_init(&tmem_empty[a], 128 * CG);
       mbar_init(&res_full[a], 1);
     }
     tma_prefetch_desc(&map_out);
     if (p.has_res) tma_prefetch_desc(&map_res);
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (CG == 2) cluster_sync_all();  // peer barriers initialised before any remote arrive / multicast commit
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+    else tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  // decode this CTA's tile of virtual tile vt; an odd leftover M tile is parked out of range (TMA zero-fills
+  // its loads and clips its stores)
+  auto decode = [&](int vt, int& n_tile, int& tw, int& th, int& tn) {
+    n_tile = vt % p.n_tiles_n;
+    const int m_tile = (vt / p.n_tiles_n) * CG + cta_rank;
+    if (m_tile < m_tiles) {
+      tw = m_tile % p.tiles_w;
+      th = (m_tile / p.tiles_w) % p.tiles_h;
+      tn = m_tile / (p.tiles_w * p.tiles_h);
+    } else {
+      tw = p.tiles_w;
+      th = 0;
+      tn = 0;
+    }
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles_n;
-        const int m_tile = tile / p.n_tiles_n;
-        const int tw = m_tile % p.tiles_w;
-        const int th = (m_tile / p.tiles_w) % p.tiles_h;
-        const int tn = m_tile / (p.tiles_w * p.tiles_h);
+      for (int vt = vt0; vt < total_vt; vt += vt_step) {
+        int n_tile, tw, th, tn;
+        decode(vt, n_tile, tw, th, tn);
         int base[5] = {0, 0, 0, 0, 0};
         base[p.dim_w] += tw * p.bw;
         if (p.dim_h >= 0) base[p.dim_h] += th * p.bh;
@@ -186,11 +213,18 @@ __global__ void __launch_bounds__(kThreads, 1)
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + kABytes;
-          mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-          tma_load_5d(&map_a, &full[stage], sa, base[0] + p.tap_off[tap][0] + chunk * kBlockK,
-                      base[1] + p.tap_off[tap][1], base[2] + p.tap_off[tap][2],
-                      base[3] + p.tap_off[tap][3], base[4] + p.tap_off[tap][4]);
-          tma_load_2d(&map_b, &full[stage], sb, kb * kBlockK, n_tile * BN);
+          const int c0 = base[0] + p.tap_off[tap][0] + chunk * kBlockK, c1 = base[1] + p.tap_off[tap][1],
+                    c2 = base[2] + p.tap_off[tap][2], c3 = base[3] + p.tap_off[tap][3], c4 = base[4] + p.tap_off[tap][4];
+          if (CG == 2) {
+            // both CTAs' bytes land on the leader's barrier; the leader alone arms it (for both)
+            if (cta_rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+            tma_load_5d_2sm(&map_a, &full[stage], sa, c0, c1, c2, c3, c4);
+            tma_load_2d_2sm(&map_b, &full[stage], sb, kb * kBlockK, n_tile * BN + cta_rank * (BN / 2));
+          } else {
+            mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+            tma_load_5d(&map_a, &full[stage], sa, c0, c1, c2, c3, c4);
+            tma_load_2d(&map_b, &full[stage], sb, kb * kBlockK, n_tile * BN);
+          }
           if (++chunk == p.chunks_per_tap) {
             chunk = 0;
             ++tap;
@@ -204,11 +238,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BN);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BN, 128u * CG);
       int stage = 0, phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (int vt = vt0; vt < total_vt; vt += vt_step, ++it) {
         const int acc = it & 1;
         const int acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -224,11 +258,18 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 fp16 = 32 B along K inside the 128 B swizzle atom: +2 in (addr >> 4) units
-            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                     (kb > 0 || k > 0) ? 1u : 0u);
+            if (CG == 2)
+              umma_f16_2sm(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else
+              umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
-          if (kb == p.num_kb - 1) umma_commit(&tmem_full[acc]);
+          // frees the smem slot (in both CTAs) when these MMAs retire
+          if (CG == 2) umma_commit_2sm(&empty[stage]);
+          else umma_commit(&empty[stage]);
+          if (kb == p.num_kb - 1) {
+            if (CG == 2) umma_commit_2sm(&tmem_full[acc]);
+            else umma_commit(&tmem_full[acc]);
+          }
           if (++stage == S) {
             stage = 0;
             phase ^= 1;
@@ -251,15 +292,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t sw = (uint32_t)(row & 7);
     int it = 0;
     uint32_t slab_ctr = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int vt = vt0; vt < total_vt; vt += vt_step, ++it) {
       const int acc = it & 1;
       const int acc_phase = (it >> 1) & 1;
-      const int n_tile = tile % p.n_tiles_n;
-      const int m_tile = tile / p.n_tiles_n;
-      const int tw = m_tile % p.tiles_w;
-      const int th = (m_tile / p.tiles_w) % p.tiles_h;
-      const int tn = m_tile / (p.tiles_w * p.tiles_h);
-      const int i = th * p.bh + ii, j = tw * p.bw + jj;
+      int n_tile, tw, th, tn;
+      decode(vt, n_tile, tw, th, tn);
+      const int i = th * p.bh + ii, j = min(tw * p.bw + jj, p.Wo - 1);  // j only indexes the pos.-emb. table
       const int n0 = tn * p.bn;
       int n_o0 = n0, coff = 0;
       if (p.out_split > 0) {
@@ -300,7 +338,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (c + 64 >= BN) {
           // accumulator fully read: hand the TMEM stage back to the MMA warp before the stores
           tc_fence_before();
-          mbar_arrive(&tmem_empty[acc]);
+          if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0);
+          else mbar_arrive(&tmem_empty[acc]);
         }
         if (p.has_res) mbar_wait(&res_full[buf], (slab_ctr >> 1) & 1u);
 #pragma unroll
@@ -342,10 +381,12 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -409,13 +450,15 @@ static int ilog2(int v) {
 
 static int g_num_sms = 0;
 
-template <int BN>
+static int g_cta_group = -1;  // FPOSE_CTA_GROUP=1 falls back to single-CTA MMAs (A/B checks)
+
+template <int BN, int CG>
 static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mr,
                      const GemmParams& p, cudaStream_t stream) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    FP_CUDA_OK(cudaFuncSetAttribute(gemm_tile_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FP_CUDA_OK(cudaFuncSetAttribute(gemm_tile_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -424,9 +467,25 @@ static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtenso
     FP_CUDA_OK(cudaGetDevice(&dev));
     FP_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int total_vt = ((m_tiles + CG - 1) / CG) * p.n_tiles_n;
+  const int slots = g_num_sms / CG;
+  const int grid = CG * (total_vt < slots ? total_vt : slots);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   prof_mark_begin(0, p.alg_flops, stream);
-  gemm_tile_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ma, mb, mo, mr, p);
+  FP_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tile_kernel<BN, CG>, ma, mb, mo, mr, p));
   prof_mark_end(stream);
   ++g_launch_count;
   FP_CUDA_OK(cudaGetLastError());
@@ -557,7 +616,12 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
   if (rc) return rc;
   uint64_t wd[2] = {(uint64_t)ktot, (uint64_t)L.Cout};
   uint64_t ws[1] = {(uint64_t)ktot * E};
-  uint32_t wb[2] = {64, (uint32_t)BN};
+  if (g_cta_group < 0) {
+    const char* e = getenv("FPOSE_CTA_GROUP");
+    g_cta_group = (e && e[0] == '1') ? 1 : 2;
+  }
+  const int CG = g_cta_group;
+  uint32_t wb[2] = {64, (uint32_t)(BN / CG)};
   rc = encode_map(&mb, L.w, 2, wd, ws, wb);
   if (rc) return rc;
   // output / residual maps: NHWC (conv) or [M][ld] (linear), one box = 128 pixels x 64 channels
@@ -599,9 +663,9 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
   }
 
   switch (BN) {
-    case 256: return launch_bn<256>(ma, mb, mo, mr, p, stream);
-    case 128: return launch_bn<128>(ma, mb, mo, mr, p, stream);
-    default: return launch_bn<64>(ma, mb, mo, mr, p, stream);
+    case 256: return CG == 2 ? launch_bn<256, 2>(ma, mb, mo, mr, p, stream) : launch_bn<256, 1>(ma, mb, mo, mr, p, stream);
+    case 128: return CG == 2 ? launch_bn<128, 2>(ma, mb, mo, mr, p, stream) : launch_bn<128, 1>(ma, mb, mo, mr, p, stream);
+    default: return CG == 2 ? launch_bn<64, 2>(ma, mb, mo, mr, p, stream) : launch_bn<64, 1>(ma, mb, mo, mr, p, stream);
   }
 }
 
