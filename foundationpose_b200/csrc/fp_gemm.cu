@@ -620,7 +620,10 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
     const char* e = getenv("FPOSE_CTA_GROUP");
     g_cta_group = (e && e[0] == '1') ? 1 : 2;
   }
-  const int CG = g_cta_group;
+  // Measured on B200 (profiles/r01_gemm_probe_cta_pair.log): the CTA-pair MMA (cta_group::2, each CTA stages half
+  // of the weight tile) is 8-10 % faster on the 256-wide, deep-K convolutions (up to 1.52 PFLOP/s) and slower on
+  // the narrow / shallow-K layers, whose bound is the shared-memory port, not the TMA fill.
+  const int CG = (g_cta_group == 2 && BN == 256 && p.num_kb >= 16) ? 2 : 1;
   uint32_t wb[2] = {64, (uint32_t)(BN / CG)};
   rc = encode_map(&mb, L.w, 2, wd, ws, wb);
   if (rc) return rc;

@@ -1,0 +1,63 @@
+"""BASELINE.json configs[2]: track_one latency — 1 hypothesis, 2 refine iterations, a synthetic sequence.
+
+Reports ms/frame (p50 / p99 / mean) through the public API `FoundationPose.track_one()` with host numpy
+frames (H2D of the frame, depth filters, 2 x (crop + RefineNet + pose update), D2H of the pose inside the
+timed region).  The sequence cycles over a few analytically generated frames of the object moving
+<= 5 mm / 2 deg per frame."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from foundationpose_b200 import synth  # noqa: E402
+from foundationpose_b200.estimater import FoundationPose, PoseRefinePredictor, ScorePredictor  # noqa: E402
+from foundationpose_b200.weights import random_state_dict  # noqa: E402
+
+
+def main():
+    n_frames = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+    n_unique = 16
+    mesh = synth.make_mesh(5)
+    rng = np.random.default_rng(3)
+    pose = np.eye(4)
+    pose[:3, :3] = synth.random_rotation(0)
+    pose[:3, 3] = [0.0, 0.0, 0.6]
+    frames = []
+    for i in range(n_unique):
+        rgb, depth, mask = synth.make_scene(mesh.visual.image, pose, seed=1 + i)
+        frames.append((rgb, depth, mask, pose.copy()))
+        ang = np.deg2rad(2.0) * rng.uniform(-1, 1, 3)
+        c, s = np.cos(ang[2]), np.sin(ang[2])
+        Rz = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]])
+        pose = pose.copy()
+        pose[:3, :3] = Rz @ pose[:3, :3]
+        pose[:3, 3] += rng.uniform(-0.005, 0.005, 3)
+    K = synth.DEFAULT_K
+    refiner = PoseRefinePredictor(state_dict=random_state_dict("refine", 0))
+    scorer = ScorePredictor(engine=refiner.engine, state_dict=random_state_dict("score", 0))
+    est = FoundationPose(model_pts=mesh.vertices, model_normals=mesh.vertex_normals, mesh=mesh, scorer=scorer, refiner=refiner)
+    est.register(K=K, rgb=frames[0][0], depth=frames[0][1], ob_mask=frames[0][2], iteration=5)
+    for i in range(20):  # warm-up (graph capture on the 2nd call)
+        f = frames[i % n_unique]
+        est.track_one(rgb=f[0], depth=f[1], K=K, iteration=2)
+    torch.cuda.synchronize()
+    lat = []
+    for i in range(n_frames):
+        f = frames[i % n_unique]
+        t0 = time.perf_counter()
+        est.track_one(rgb=f[0], depth=f[1], K=K, iteration=2)  # returns a host numpy pose (synchronises)
+        lat.append((time.perf_counter() - t0) * 1e3)
+    lat = np.array(lat)
+    print(json.dumps({"metric": "track_one latency, 1 hyp x 2 refine iters, 640x480 RGB-D (host API, host buffers)", "frames": n_frames,
+                      "ms_p50": float(np.percentile(lat, 50)), "ms_p99": float(np.percentile(lat, 99)), "ms_mean": float(lat.mean()),
+                      "fps_p50": float(1e3 / np.percentile(lat, 50))}))
+
+
+if __name__ == "__main__":
+    main()
