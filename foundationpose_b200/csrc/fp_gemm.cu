@@ -391,6 +391,229 @@ __global__ void __launch_bounds__(kThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
+// "swap-AB" variant for the 128-output-channel convolutions.
+//
+// With D[128 pixels x 128 channels] tiles the MMA (128x128x16, 64 cycles) reads 8 KB of operands from shared
+// memory while TMA writes the next 32 KB stage: 128 + 128 B/cycle against a 128 B/cycle port — measured 45 %
+// tensor-pipe utilisation.  Here the roles are exchanged: the weight tile [128 channels][64 k] is the M side
+// and TWO pixel tiles (256 pixels) are the N side, so one 128x256x16 MMA (128 cycles) reads 12 KB and the stage
+// is 48 KB per 512 cycles — the same 96 + 96 B/cycle budget as the 256-channel layers.  The accumulator is then
+// [channel (TMEM lane)][pixel (TMEM column)]: the epilogue thread owns one channel (bias is a register) and
+// scatters fp16 values into the 128B-swizzled [pixel][channel] slabs that the TMA store (and the TMA residual
+// load) use; a warp's 32 lanes write 64 contiguous bytes, so the transposition is bank-conflict free.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSwapStages = 3;
+constexpr int kSwapStageBytes = kABytes + 2 * kABytes;  // W 16 KB + X 2 x 16 KB
+constexpr int kSwapStaging = 4 * kSlabBytes;            // 2 pixel tiles x 2 channel halves
+constexpr int kSwapSmem = kSwapStages * kSwapStageBytes + kSwapStaging + 1024 + 256;
+
+__global__ void __launch_bounds__(kThreads, 1)
+    gemm_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                     const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
+                     const __grid_constant__ GemmParams p) {
+  constexpr int S = kSwapStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + S * kSwapStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kSwapStaging);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + S;
+  uint64_t* tmem_full = bars + 2 * S;
+  uint64_t* tmem_empty = bars + 2 * S + 2;
+  uint64_t* res_full = bars + 2 * S + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int c_tiles = p.Cout / 128;
+  const int total_vt = ((m_tiles + 1) / 2) * c_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_w);
+    tma_prefetch_desc(&map_out);
+    if (p.has_res) tma_prefetch_desc(&map_res);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 128);
+    }
+    mbar_init(res_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode_m = [&](int m_tile, int& tw, int& th, int& tn) {
+    if (m_tile < m_tiles) {
+      tw = m_tile % p.tiles_w;
+      th = (m_tile / p.tiles_w) % p.tiles_h;
+      tn = m_tile / (p.tiles_w * p.tiles_h);
+    } else {
+      tw = p.tiles_w;  // parked out of range: zero-filled loads, clipped stores
+      th = 0;
+      tn = 0;
+    }
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int vt = blockIdx.x; vt < total_vt; vt += gridDim.x) {
+        const int c_tile = vt % c_tiles, pair = vt / c_tiles;
+        int base[2][5];
+        for (int t = 0; t < 2; ++t) {
+          int tw, th, tn;
+          decode_m(2 * pair + t, tw, th, tn);
+          for (int d = 0; d < 5; ++d) base[t][d] = 0;
+          base[t][p.dim_w] += tw * p.bw;
+          if (p.dim_h >= 0) base[t][p.dim_h] += th * p.bh;
+          if (p.dim_n >= 0) base[t][p.dim_n] += tn * p.bn;
+        }
+        int tap = 0, chunk = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sw_ = smem + stage * kSwapStageBytes;
+          mbar_expect_tx(&full[stage], kSwapStageBytes);
+          tma_load_2d(&map_w, &full[stage], sw_, kb * kBlockK, c_tile * 128);
+          for (int t = 0; t < 2; ++t)
+            tma_load_5d(&map_a, &full[stage], sw_ + kABytes + t * kABytes, base[t][0] + p.tap_off[tap][0] + chunk * kBlockK,
+                        base[t][1] + p.tap_off[tap][1], base[t][2] + p.tap_off[tap][2], base[t][3] + p.tap_off[tap][3],
+                        base[t][4] + p.tap_off[tap][4]);
+          if (++chunk == p.chunks_per_tap) {
+            chunk = 0;
+            ++tap;
+          }
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(256, 128);
+      int stage = 0, phase = 0, it = 0;
+      for (int vt = blockIdx.x; vt < total_vt; vt += gridDim.x, ++it) {
+        const int acc = it & 1, acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sw_ = smem_u32(smem + stage * kSwapStageBytes);
+          const uint64_t da = umma_desc_sw128(sw_);            // weights: M = 128 channels
+          const uint64_t db = umma_desc_sw128(sw_ + kABytes);  // activations: N = 256 pixels
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (kb == p.num_kb - 1) umma_commit(&tmem_full[acc]);
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int half = quarter >> 1;                      // which 64-channel slab this warp's channels live in
+    const int c_local = (quarter & 1) * 32 + lane;      // channel inside the slab
+    const bool leader = (warp == 2 && lane == 0);
+    const uint32_t c_chunk = (uint32_t)(c_local >> 3), c_byte = (uint32_t)(c_local & 7) * 2u;
+    int it = 0;
+    for (int vt = blockIdx.x; vt < total_vt; vt += gridDim.x, ++it) {
+      const int acc = it & 1, acc_phase = (it >> 1) & 1;
+      const int c_tile = vt % c_tiles, pair = vt / c_tiles;
+      const float bias = __ldg(p.bias + c_tile * 128 + quarter * 32 + lane);
+      int oc[2][5], rc[2][5], coff[2];
+      for (int t = 0; t < 2; ++t) {
+        int tw, th, tn;
+        decode_m(2 * pair + t, tw, th, tn);
+        const int n0 = tn * p.bn;
+        int n_o0 = n0;
+        coff[t] = 0;
+        if (p.out_split > 0) {
+          n_o0 = n0 % p.out_split;
+          coff[t] = (n0 / p.out_split) * p.Cout;
+        }
+        for (int d = 0; d < 5; ++d) oc[t][d] = rc[t][d] = 0;
+        oc[t][1] = rc[t][1] = tw * p.bw;
+        if (p.odim_h >= 0) oc[t][p.odim_h] = rc[t][p.odim_h] = th * p.bh;
+        if (p.odim_n >= 0) {
+          oc[t][p.odim_n] = n_o0;
+          rc[t][p.odim_n] = n0;
+        }
+      }
+      // the previous tile's stores must have finished reading the four slabs
+      if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (p.has_res) {
+        if (leader) {
+          mbar_expect_tx(res_full, kSwapStaging);
+          for (int t = 0; t < 2; ++t)
+            for (int hh = 0; hh < 2; ++hh)
+              tma_load_5d(&map_res, res_full, staging + (t * 2 + hh) * kSlabBytes, c_tile * 128 + hh * 64, rc[t][1], rc[t][2],
+                          rc[t][3], rc[t][4]);
+        }
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      if (p.has_res) mbar_wait(res_full, it & 1);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256;
+#pragma unroll 1
+      for (int c = 0; c < 256; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c, v);
+        tmem_ld_wait();
+        if (c == 224) {
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[acc]);
+        }
+        uint8_t* slab = staging + ((c >> 7) * 2 + half) * kSlabBytes;
+        const int p0 = c & 127;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const uint32_t px = (uint32_t)(p0 + i);
+          __half* cell = reinterpret_cast<__half*>(slab + px * 128u + ((c_chunk ^ (px & 7u)) << 4) + c_byte);
+          float a = __uint_as_float(v[i]) + bias;
+          if (p.has_res) a += __half2float(*cell);
+          if (p.relu) a = fmaxf(a, 0.f);
+          *cell = __float2half_rn(a);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (leader) {
+        for (int t = 0; t < 2; ++t)
+          for (int hh = 0; hh < 2; ++hh)
+            tma_store_5d(&map_out, staging + (t * 2 + hh) * kSlabBytes, coff[t] + c_tile * 128 + hh * 64, oc[t][1], oc[t][2],
+                         oc[t][3], oc[t][4]);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -486,6 +709,31 @@ static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtenso
   cfg.numAttrs = 1;
   prof_mark_begin(0, p.alg_flops, stream);
   FP_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tile_kernel<BN, CG>, ma, mb, mo, mr, p));
+  prof_mark_end(stream);
+  ++g_launch_count;
+  FP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int g_swap_ab = -1;  // FPOSE_SWAP_AB=0 disables the swapped 128-channel kernel (A/B checks)
+
+static int launch_swap(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mo, const CUtensorMap& mr,
+                       const GemmParams& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    FP_CUDA_OK(cudaFuncSetAttribute(gemm_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSwapSmem));
+    attr_set = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    FP_CUDA_OK(cudaGetDevice(&dev));
+    FP_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int total_vt = ((m_tiles + 1) / 2) * (p.Cout / 128);
+  const int grid = total_vt < g_num_sms ? total_vt : g_num_sms;
+  prof_mark_begin(0, p.alg_flops, stream);
+  gemm_swap_kernel<<<grid, kThreads, kSwapSmem, stream>>>(ma, mw, mo, mr, p);
   prof_mark_end(stream);
   ++g_launch_count;
   FP_CUDA_OK(cudaGetLastError());
@@ -623,6 +871,12 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
   // Measured on B200 (profiles/r01_gemm_probe_cta_pair.log): the CTA-pair MMA (cta_group::2, each CTA stages half
   // of the weight tile) is 8-10 % faster on the 256-wide, deep-K convolutions (up to 1.52 PFLOP/s) and slower on
   // the narrow / shallow-K layers, whose bound is the shared-memory port, not the TMA fill.
+  if (g_swap_ab < 0) {
+    const char* e = getenv("FPOSE_SWAP_AB");
+    g_swap_ab = (e && e[0] == '0') ? 0 : 1;
+  }
+  const bool swap_ab = g_swap_ab && BN == 128 && L.Cout == 128 && !L.post_add &&
+                       (L.kind == LK_CONV3_S1 || L.kind == LK_CONV3_S2);
   const int CG = (g_cta_group == 2 && BN == 256 && p.num_kb >= 16) ? 2 : 1;
   uint32_t wb[2] = {64, (uint32_t)(BN / CG)};
   rc = encode_map(&mb, L.w, 2, wd, ws, wb);
@@ -665,6 +919,7 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
     }
   }
 
+  if (swap_ab) return launch_swap(ma, mb, mo, mr, p, stream);
   switch (BN) {
     case 256: return CG == 2 ? launch_bn<256, 2>(ma, mb, mo, mr, p, stream) : launch_bn<256, 1>(ma, mb, mo, mr, p, stream);
     case 128: return CG == 2 ? launch_bn<128, 2>(ma, mb, mo, mr, p, stream) : launch_bn<128, 1>(ma, mb, mo, mr, p, stream);
