@@ -112,28 +112,33 @@ struct GemmParams {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;       // swap kernel: producer, MMA, 4 epilogue warps
+constexpr int kTileThreads = 320;   // tile kernel: producer, MMA, 8 epilogue warps (two per TMEM lane quarter)
 constexpr int kSlabBytes = kBlockM * 64 * 2;  // 16 KB: one output slab (128 pixels x 64 channels, 128B-swizzled)
 
 // CG = CTAs per MMA (tcgen05 cta_group): with CG = 2 the CTA pair of a cluster issues one M = 256 MMA; each CTA
 // stages its own 128 pixel rows of A and only HALF of the weight tile (BN/2 rows), which halves the B-operand
 // shared-memory traffic per SM — the bound of the N <= 128 layers.
-template <int BN, int CG>
+// SLABS = epilogue staging slabs (16 KB each).  2: slabs are recycled one by one.  4 (residual layers with
+// BN = 256): one slab per 64-channel slice of the tile, so the whole tile's residual is prefetched by TMA
+// while the tile's MMAs are still running.
+template <int BN, int CG, int SLABS>
 struct TileCfg {
   static constexpr int kBBytes = (BN / CG) * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
+  static constexpr int kStagingBytes = SLABS * kSlabBytes;
+  static constexpr int kRing = 196608 + 2 * kSlabBytes - kStagingBytes;
+  static constexpr int kStages = (kRing / kStageBytes) > 8 ? 8 : (kRing / kStageBytes);
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-  static constexpr int kStagingBytes = 2 * kSlabBytes;  // epilogue: two 128-row x 64-channel fp16 slabs
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int CG>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, int CG, int SLABS>
+__global__ void __launch_bounds__(kTileThreads, 1)
     gemm_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
                      const __grid_constant__ GemmParams p) {
-  using Cfg = TileCfg<BN, CG>;
+  using Cfg = TileCfg<BN, CG, SLABS>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -143,8 +148,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* empty = bars + S;            // [S]
   uint64_t* tmem_full = bars + 2 * S;    // [2]
   uint64_t* tmem_empty = bars + 2 * S + 2;  // [2]
-  uint64_t* res_full = bars + 2 * S + 4;    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 6);
+  uint64_t* res_full = bars + 2 * S + 4;    // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -163,9 +168,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 128 * CG);
-      mbar_init(&res_full[a], 1);
+      mbar_init(&tmem_empty[a], 256 * CG);
     }
+    for (int a = 0; a < 4; ++a) mbar_init(&res_full[a], 1);
     tma_prefetch_desc(&map_out);
     if (p.has_res) tma_prefetch_desc(&map_res);
     mbar_fence_init();
@@ -283,7 +288,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     // one TMA tensor store per 128-pixel x 64-channel slab.  The residual slab arrives the same way
     // (TMA load into the slab buffer), so every global access of the epilogue is a bulk, fully
     // coalesced transfer; out-of-range rows are clipped (store) / zero-filled (load) by the TMA unit.
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp may read
+    const int quarter = warp & 3;       // TMEM lanes [32*quarter, +32) are the ones this warp may read
+    const int grp = (warp - 2) >> 2;    // which 32-column half of every 64-channel slab this warp handles
     const int row = quarter * 32 + lane;
     const int jj = row & (p.bw - 1);
     const int ii = (row >> p.lg_bw) & (p.bh - 1);
@@ -315,25 +321,38 @@ __global__ void __launch_bounds__(kThreads, 1)
         rc[p.odim_n] = n0;
       }
 
+      if (SLABS == 4) {
+        // one slab per 64-channel slice: fetch the whole tile's residual now, while its MMAs still run
+        if (leader) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // last tile's stores have left the slabs
+          if (p.has_res) {
+            for (int sidx = 0; sidx < BN / 64; ++sidx) {
+              mbar_expect_tx(&res_full[sidx], kSlabBytes);
+              tma_load_5d(&map_res, &res_full[sidx], staging + sidx * kSlabBytes, n_tile * BN + sidx * 64, rc[1], rc[2], rc[3],
+                          rc[4]);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + grp * 32;
 #pragma unroll 1
       for (int c = 0; c < BN; c += 64, ++slab_ctr) {
-        const uint32_t buf = slab_ctr & 1u;
+        const uint32_t buf = (SLABS == 4) ? (uint32_t)(c >> 6) : (slab_ctr & 1u);
         uint8_t* slab = staging + buf * kSlabBytes;
-        // the TMA store that last used this buffer (two slabs ago) must have finished reading it
-        if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (p.has_res) {
-          if (leader) {
+        if (SLABS == 2) {
+          // the TMA store that last used this buffer (two slabs ago) must have finished reading it
+          if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (p.has_res && leader) {
             mbar_expect_tx(&res_full[buf], kSlabBytes);
             tma_load_5d(&map_res, &res_full[buf], slab, n_tile * BN + c, rc[1], rc[2], rc[3], rc[4]);
           }
         }
-        uint32_t v0[32], v1[32];
-        tmem_ld32(taddr + c, v0);
-        tmem_ld32(taddr + c + 32, v1);
+        uint32_t v[32];
+        tmem_ld32(taddr + c, v);
         tmem_ld_wait();
         if (c + 64 >= BN) {
           // accumulator fully read: hand the TMEM stage back to the MMA warp before the stores
@@ -341,14 +360,19 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0);
           else mbar_arrive(&tmem_empty[acc]);
         }
-        if (p.has_res) mbar_wait(&res_full[buf], (slab_ctr >> 1) & 1u);
+        if (p.has_res) mbar_wait(&res_full[buf], (SLABS == 4) ? (uint32_t)(it & 1) : ((slab_ctr >> 1) & 1u));
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {  // 8 chunks of 8 channels (16 B)
+        for (int q4 = 0; q4 < 4; ++q4) {  // this warp's 4 chunks of 8 channels (16 B)
+          const int q = grp * 4 + q4;
           uint4* cell = reinterpret_cast<uint4*>(slab + row_off + (((uint32_t)q ^ sw) << 4));
           float a[8];
+          {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp + c + q * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bp + c + q * 8) + 1);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            a[k] = __uint_as_float(q < 4 ? v0[(q & 3) * 8 + k] : v1[(q & 3) * 8 + k]) + __ldg(bp + c + q * 8 + k);
+            for (int k = 0; k < 8; ++k) a[k] = __uint_as_float(v[q4 * 8 + k]) + bb[k];
+          }
           if (p.has_res) {
             const uint4 r = *cell;
             const __half2* rh = reinterpret_cast<const __half2*>(&r);
@@ -364,13 +388,15 @@ __global__ void __launch_bounds__(kThreads, 1)
             for (int k = 0; k < 8; ++k) a[k] = fmaxf(a[k], 0.f);
           }
           if (pap) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) a[k] += __ldg(pap + c + q * 8 + k);
+            const float4 p0 = __ldg(reinterpret_cast<const float4*>(pap + c + q * 8));
+            const float4 p1 = __ldg(reinterpret_cast<const float4*>(pap + c + q * 8) + 1);
+            a[0] += p0.x; a[1] += p0.y; a[2] += p0.z; a[3] += p0.w;
+            a[4] += p1.x; a[5] += p1.y; a[6] += p1.z; a[7] += p1.w;
           }
           *cell = make_uint4(pack_half2(a[0], a[1]), pack_half2(a[2], a[3]), pack_half2(a[4], a[5]), pack_half2(a[6], a[7]));
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (leader) {
           tma_store_5d(&map_out, slab, coff + n_tile * BN + c, oc[1], oc[2], oc[3], oc[4]);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -402,9 +428,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 // scatters fp16 values into the 128B-swizzled [pixel][channel] slabs that the TMA store (and the TMA residual
 // load) use; a warp's 32 lanes write 64 contiguous bytes, so the transposition is bank-conflict free.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSwapStages = 3;
+constexpr int kSwapStages = 4;  // 4 x 48 KB in flight: ~2k MMA cycles of lookahead (3 stages measured 60 % tensor-active)
 constexpr int kSwapStageBytes = kABytes + 2 * kABytes;  // W 16 KB + X 2 x 16 KB
-constexpr int kSwapStaging = 4 * kSlabBytes;            // 2 pixel tiles x 2 channel halves
+constexpr int kSwapStaging = 2 * kSlabBytes;            // one pixel tile x 2 channel halves at a time
 constexpr int kSwapSmem = kSwapStages * kSwapStageBytes + kSwapStaging + 1024 + 256;
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -555,51 +581,51 @@ __global__ void __launch_bounds__(kThreads, 1)
           rc[t][p.odim_n] = n0;
         }
       }
-      // the previous tile's stores must have finished reading the four slabs
-      if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (p.has_res) {
-        if (leader) {
-          mbar_expect_tx(res_full, kSwapStaging);
-          for (int t = 0; t < 2; ++t)
-            for (int hh = 0; hh < 2; ++hh)
-              tma_load_5d(&map_res, res_full, staging + (t * 2 + hh) * kSlabBytes, c_tile * 128 + hh * 64, rc[t][1], rc[t][2],
-                          rc[t][3], rc[t][4]);
-        }
-      }
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      if (p.has_res) mbar_wait(res_full, it & 1);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256;
 #pragma unroll 1
-      for (int c = 0; c < 256; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c, v);
-        tmem_ld_wait();
-        if (c == 224) {
-          tc_fence_before();
-          mbar_arrive(&tmem_empty[acc]);
-        }
-        uint8_t* slab = staging + ((c >> 7) * 2 + half) * kSlabBytes;
-        const int p0 = c & 127;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const uint32_t px = (uint32_t)(p0 + i);
-          __half* cell = reinterpret_cast<__half*>(slab + px * 128u + ((c_chunk ^ (px & 7u)) << 4) + c_byte);
-          float a = __uint_as_float(v[i]) + bias;
-          if (p.has_res) a += __half2float(*cell);
-          if (p.relu) a = fmaxf(a, 0.f);
-          *cell = __float2half_rn(a);
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (leader) {
-        for (int t = 0; t < 2; ++t)
+      for (int t = 0; t < 2; ++t) {
+        // the previous stores must have finished reading the two slabs
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (p.has_res && leader) {
+          mbar_expect_tx(res_full, kSwapStaging);
           for (int hh = 0; hh < 2; ++hh)
-            tma_store_5d(&map_out, staging + (t * 2 + hh) * kSlabBytes, coff[t] + c_tile * 128 + hh * 64, oc[t][1], oc[t][2],
-                         oc[t][3], oc[t][4]);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            tma_load_5d(&map_res, res_full, staging + hh * kSlabBytes, c_tile * 128 + hh * 64, rc[t][1], rc[t][2], rc[t][3],
+                        rc[t][4]);
+        }
+        if (t == 0) {
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tc_fence_after();
+        }
+        if (p.has_res) mbar_wait(res_full, (uint32_t)(2 * it + t) & 1u);
+        uint8_t* slab = staging + half * kSlabBytes;
+#pragma unroll 1
+        for (int c = 0; c < 128; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + t * 128 + c, v);
+          tmem_ld_wait();
+          if (t == 1 && c == 96) {
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const uint32_t px = (uint32_t)(c + i);
+            __half* cell = reinterpret_cast<__half*>(slab + px * 128u + ((c_chunk ^ (px & 7u)) << 4) + c_byte);
+            float a = __uint_as_float(v[i]) + bias;
+            if (p.has_res) a += __half2float(*cell);
+            if (p.relu) a = fmaxf(a, 0.f);
+            *cell = __float2half_rn(a);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (leader) {
+          for (int hh = 0; hh < 2; ++hh)
+            tma_store_5d(&map_out, staging + hh * kSlabBytes, coff[t] + c_tile * 128 + hh * 64, oc[t][1], oc[t][2], oc[t][3],
+                         oc[t][4]);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
       }
     }
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -675,13 +701,13 @@ static int g_num_sms = 0;
 
 static int g_cta_group = -1;  // FPOSE_CTA_GROUP=1 falls back to single-CTA MMAs (A/B checks)
 
-template <int BN, int CG>
+template <int BN, int CG, int SLABS>
 static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mr,
                      const GemmParams& p, cudaStream_t stream) {
-  using Cfg = TileCfg<BN, CG>;
+  using Cfg = TileCfg<BN, CG, SLABS>;
   static bool attr_set = false;
   if (!attr_set) {
-    FP_CUDA_OK(cudaFuncSetAttribute(gemm_tile_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FP_CUDA_OK(cudaFuncSetAttribute(gemm_tile_kernel<BN, CG, SLABS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -697,7 +723,7 @@ static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtenso
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(kTileThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -708,7 +734,7 @@ static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtenso
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   prof_mark_begin(0, p.alg_flops, stream);
-  FP_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tile_kernel<BN, CG>, ma, mb, mo, mr, p));
+  FP_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tile_kernel<BN, CG, SLABS>, ma, mb, mo, mr, p));
   prof_mark_end(stream);
   ++g_launch_count;
   FP_CUDA_OK(cudaGetLastError());
@@ -920,11 +946,13 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
   }
 
   if (swap_ab) return launch_swap(ma, mb, mo, mr, p, stream);
-  switch (BN) {
-    case 256: return CG == 2 ? launch_bn<256, 2>(ma, mb, mo, mr, p, stream) : launch_bn<256, 1>(ma, mb, mo, mr, p, stream);
-    case 128: return CG == 2 ? launch_bn<128, 2>(ma, mb, mo, mr, p, stream) : launch_bn<128, 1>(ma, mb, mo, mr, p, stream);
-    default: return CG == 2 ? launch_bn<64, 2>(ma, mb, mo, mr, p, stream) : launch_bn<64, 1>(ma, mb, mo, mr, p, stream);
+  if (BN == 256) {
+    // residual layers: 4 staging slabs so the tile's residual is prefetched (one ring stage fewer)
+    if (L.res) return CG == 2 ? launch_bn<256, 2, 4>(ma, mb, mo, mr, p, stream) : launch_bn<256, 1, 4>(ma, mb, mo, mr, p, stream);
+    return CG == 2 ? launch_bn<256, 2, 2>(ma, mb, mo, mr, p, stream) : launch_bn<256, 1, 2>(ma, mb, mo, mr, p, stream);
   }
+  if (BN == 128) return launch_bn<128, 1, 2>(ma, mb, mo, mr, p, stream);
+  return launch_bn<64, 1, 2>(ma, mb, mo, mr, p, stream);
 }
 
 }  // namespace fp
