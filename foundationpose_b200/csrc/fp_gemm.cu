@@ -428,12 +428,12 @@ __global__ void __launch_bounds__(kTileThreads, 1)
 // scatters fp16 values into the 128B-swizzled [pixel][channel] slabs that the TMA store (and the TMA residual
 // load) use; a warp's 32 lanes write 64 contiguous bytes, so the transposition is bank-conflict free.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSwapStages = 4;  // 4 x 48 KB in flight: ~2k MMA cycles of lookahead (3 stages measured 60 % tensor-active)
+constexpr int kSwapStages = 3;
 constexpr int kSwapStageBytes = kABytes + 2 * kABytes;  // W 16 KB + X 2 x 16 KB
-constexpr int kSwapStaging = 2 * kSlabBytes;            // one pixel tile x 2 channel halves at a time
+constexpr int kSwapStaging = 4 * kSlabBytes;            // 2 pixel tiles (one per epilogue warpgroup) x 2 channel halves
 constexpr int kSwapSmem = kSwapStages * kSwapStageBytes + kSwapStaging + 1024 + 256;
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kTileThreads, 1)
     gemm_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                      const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
                      const __grid_constant__ GemmParams p) {
@@ -446,8 +446,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* empty = bars + S;
   uint64_t* tmem_full = bars + 2 * S;
   uint64_t* tmem_empty = bars + 2 * S + 2;
-  uint64_t* res_full = bars + 2 * S + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 5);
+  uint64_t* res_full = bars + 2 * S + 4;  // [2]: one per epilogue warpgroup
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -466,9 +466,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 128);
+      mbar_init(&tmem_empty[a], 256);
+      mbar_init(&res_full[a], 1);
     }
-    mbar_init(res_full, 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -552,80 +552,78 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else {
+    // two independent epilogue warpgroups: group t (warps 2+4t .. 5+4t) owns pixel tile t of every virtual
+    // tile (TMEM columns [128 t, 128 t + 128)), its own two staging slabs, named barrier, residual barrier and
+    // TMA bulk groups
     const int quarter = warp & 3;
+    const int t = (warp - 2) >> 2;
     const int half = quarter >> 1;                      // which 64-channel slab this warp's channels live in
     const int c_local = (quarter & 1) * 32 + lane;      // channel inside the slab
-    const bool leader = (warp == 2 && lane == 0);
+    const bool leader = (((warp - 2) & 3) == 0 && lane == 0);
     const uint32_t c_chunk = (uint32_t)(c_local >> 3), c_byte = (uint32_t)(c_local & 7) * 2u;
+    uint8_t* my_staging = staging + t * 2 * kSlabBytes;
+    uint8_t* slab = my_staging + half * kSlabBytes;
     int it = 0;
     for (int vt = blockIdx.x; vt < total_vt; vt += gridDim.x, ++it) {
       const int acc = it & 1, acc_phase = (it >> 1) & 1;
       const int c_tile = vt % c_tiles, pair = vt / c_tiles;
       const float bias = __ldg(p.bias + c_tile * 128 + quarter * 32 + lane);
-      int oc[2][5], rc[2][5], coff[2];
-      for (int t = 0; t < 2; ++t) {
+      int oc[5] = {0, 0, 0, 0, 0}, rc[5] = {0, 0, 0, 0, 0}, coff = 0;
+      {
         int tw, th, tn;
         decode_m(2 * pair + t, tw, th, tn);
         const int n0 = tn * p.bn;
         int n_o0 = n0;
-        coff[t] = 0;
         if (p.out_split > 0) {
           n_o0 = n0 % p.out_split;
-          coff[t] = (n0 / p.out_split) * p.Cout;
+          coff = (n0 / p.out_split) * p.Cout;
         }
-        for (int d = 0; d < 5; ++d) oc[t][d] = rc[t][d] = 0;
-        oc[t][1] = rc[t][1] = tw * p.bw;
-        if (p.odim_h >= 0) oc[t][p.odim_h] = rc[t][p.odim_h] = th * p.bh;
+        oc[1] = rc[1] = tw * p.bw;
+        if (p.odim_h >= 0) oc[p.odim_h] = rc[p.odim_h] = th * p.bh;
         if (p.odim_n >= 0) {
-          oc[t][p.odim_n] = n_o0;
-          rc[t][p.odim_n] = n0;
+          oc[p.odim_n] = n_o0;
+          rc[p.odim_n] = n0;
         }
       }
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256;
+      // this group's previous stores must have finished reading its two slabs
+      if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (t == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (p.has_res && leader) {
+        mbar_expect_tx(&res_full[t], 2 * kSlabBytes);
+        for (int hh = 0; hh < 2; ++hh)
+          tma_load_5d(&map_res, &res_full[t], my_staging + hh * kSlabBytes, c_tile * 128 + hh * 64, rc[1], rc[2], rc[3], rc[4]);
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      if (p.has_res) mbar_wait(&res_full[t], it & 1);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256 + t * 128;
 #pragma unroll 1
-      for (int t = 0; t < 2; ++t) {
-        // the previous stores must have finished reading the two slabs
-        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (p.has_res && leader) {
-          mbar_expect_tx(res_full, kSwapStaging);
-          for (int hh = 0; hh < 2; ++hh)
-            tma_load_5d(&map_res, res_full, staging + hh * kSlabBytes, c_tile * 128 + hh * 64, rc[t][1], rc[t][2], rc[t][3],
-                        rc[t][4]);
+      for (int c = 0; c < 128; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c, v);
+        tmem_ld_wait();
+        if (c == 96) {
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[acc]);
         }
-        if (t == 0) {
-          mbar_wait(&tmem_full[acc], acc_phase);
-          tc_fence_after();
-        }
-        if (p.has_res) mbar_wait(res_full, (uint32_t)(2 * it + t) & 1u);
-        uint8_t* slab = staging + half * kSlabBytes;
-#pragma unroll 1
-        for (int c = 0; c < 128; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(taddr + t * 128 + c, v);
-          tmem_ld_wait();
-          if (t == 1 && c == 96) {
-            tc_fence_before();
-            mbar_arrive(&tmem_empty[acc]);
-          }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const uint32_t px = (uint32_t)(c + i);
-            __half* cell = reinterpret_cast<__half*>(slab + px * 128u + ((c_chunk ^ (px & 7u)) << 4) + c_byte);
-            float a = __uint_as_float(v[i]) + bias;
-            if (p.has_res) a += __half2float(*cell);
-            if (p.relu) a = fmaxf(a, 0.f);
-            *cell = __float2half_rn(a);
-          }
+        for (int i = 0; i < 32; ++i) {
+          const uint32_t px = (uint32_t)(c + i);
+          __half* cell = reinterpret_cast<__half*>(slab + px * 128u + ((c_chunk ^ (px & 7u)) << 4) + c_byte);
+          float a = __uint_as_float(v[i]) + bias;
+          if (p.has_res) a += __half2float(*cell);
+          if (p.relu) a = fmaxf(a, 0.f);
+          *cell = __float2half_rn(a);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (leader) {
-          for (int hh = 0; hh < 2; ++hh)
-            tma_store_5d(&map_out, staging + hh * kSlabBytes, coff[t] + c_tile * 128 + hh * 64, oc[t][1], oc[t][2], oc[t][3],
-                         oc[t][4]);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (t == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (leader) {
+        for (int hh = 0; hh < 2; ++hh)
+          tma_store_5d(&map_out, my_staging + hh * kSlabBytes, coff + c_tile * 128 + hh * 64, oc[1], oc[2], oc[3], oc[4]);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -759,7 +757,7 @@ static int launch_swap(const CUtensorMap& ma, const CUtensorMap& mw, const CUten
   const int total_vt = ((m_tiles + 1) / 2) * (p.Cout / 128);
   const int grid = total_vt < g_num_sms ? total_vt : g_num_sms;
   prof_mark_begin(0, p.alg_flops, stream);
-  gemm_swap_kernel<<<grid, kThreads, kSwapSmem, stream>>>(ma, mw, mo, mr, p);
+  gemm_swap_kernel<<<grid, kTileThreads, kSwapSmem, stream>>>(ma, mw, mo, mr, p);
   prof_mark_end(stream);
   ++g_launch_count;
   FP_CUDA_OK(cudaGetLastError());

@@ -96,8 +96,13 @@ def run_case(case):
                   ("conv3 256 @40 (252)", _lib.LAYER_CONV3_S1, 252, 40, 256, 256, 2304),
                   ("conv3s2 256->512 @40 (252)", _lib.LAYER_CONV3_S2, 252, 40, 256, 512, 2304),
                   ("conv3 512 @20 (252)", _lib.LAYER_CONV3_S1, 252, 20, 512, 512, 4608),
-                  ("linear 512->1536 (100800 rows)", _lib.LAYER_LINEAR, 1, 100800, 512, 1536, 512)]
+                  ("linear 512->1536 (100800 rows)", _lib.LAYER_LINEAR, 1, 100800, 512, 1536, 512),
+                  ("conv3 128 @40 (504) +res", _lib.LAYER_CONV3_S1, 504, 40, 128, 128, 1152),
+                  ("conv3 256 @40 (252) +res", _lib.LAYER_CONV3_S1, 252, 40, 256, 256, 2304),
+                  ("conv3 512 @20 (252) +res", _lib.LAYER_CONV3_S1, 252, 20, 512, 512, 4608),
+                  ("linear 512->512 (100800) +res", _lib.LAYER_LINEAR, 1, 100800, 512, 512, 512)]
         for name, kind, n, H, Ci, Co, Kreal in shapes:
+            use_res = name.endswith("+res")
             if kind == _lib.LAYER_LINEAR:
                 x = torch.randn(H, Ci, device=dev).half()
                 w = torch.randn(Co, Ci, device=dev).half()
@@ -116,6 +121,8 @@ def run_case(case):
             b = torch.zeros(Co, device=dev)
             Ho = 1 if kind == _lib.LAYER_LINEAR else (H if kind == _lib.LAYER_CONV3_S1 else H // 2)
             out = torch.empty(M * Co, device=dev, dtype=torch.float16)
+            if use_res:
+                kw.update(res=torch.randn(M * Co, device=dev).half(), res_ld=Co)
             for _ in range(3):
                 ops.gemm_layer(kind, x, w, b, out=out, out_ld=Co, relu=True, **kw)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
