@@ -203,6 +203,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # keep stdout for the ONE JSON line: NCCL's version / debug banner goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from foundationpose_b200 import _lib, hypotheses, synth

@@ -94,6 +94,7 @@ struct fp_ctx {
   bool use_graphs = true;
   fp::DevBuf lt_buf, lr_buf, feat_buf, pose_stage;
   fp::DevBuf vtx_a, vtx_b, win_buf;  // crop producer workspaces: [cap_n][V] x 16 B each, [cap_n][8]
+  fp::DevBuf mask_buf;
 };
 
 namespace fp {
@@ -421,7 +422,7 @@ int fp_destroy(fp_ctx* c) {
   for (auto& kv : c->graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
-  DevBuf* more[] = {&c->lt_buf, &c->lr_buf, &c->feat_buf, &c->pose_stage, &c->vtx_a, &c->vtx_b, &c->win_buf};
+  DevBuf* more[] = {&c->lt_buf, &c->lr_buf, &c->feat_buf, &c->pose_stage, &c->vtx_a, &c->vtx_b, &c->win_buf, &c->mask_buf};
   for (DevBuf* b : more)
     if (b->p) cudaFree(b->p);
   delete c;
@@ -588,6 +589,22 @@ int fp_get_depth(fp_ctx* c, float* depth_out_dev, float* xyz_out_dev, void* stre
   if (depth_out_dev) FP_CUDA_OK(cudaMemcpyAsync(depth_out_dev, c->depth_cur, npix * 4, cudaMemcpyDeviceToDevice, st));
   if (xyz_out_dev) FP_CUDA_OK(cudaMemcpyAsync(xyz_out_dev, c->xyz.p, npix * 12, cudaMemcpyDeviceToDevice, st));
   return 0;
+}
+
+int fp_start_poses(fp_ctx* c, const unsigned char* mask, int mask_on_device, const float* rot_grid, int N, float* poses_out,
+                   float* info_out, void* stream) {
+  FP_REQUIRE(c && mask && rot_grid && poses_out && info_out && N >= 0, "fp_start_poses: bad argument");
+  FP_REQUIRE(c->has_frame, "fp_start_poses: no frame (call fp_set_frame first)");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t npix = (size_t)c->H * c->W;
+  const unsigned char* mdev = mask;
+  if (!mask_on_device) {
+    FP_TRY(dev_alloc(c->mask_buf, npix));
+    FP_CUDA_OK(cudaMemcpyAsync(c->mask_buf.p, mask, npix, cudaMemcpyHostToDevice, st));
+    mdev = reinterpret_cast<const unsigned char*>(c->mask_buf.p);
+  }
+  return start_poses_launch(c->depth_cur, mdev, c->H, c->W, c->K[0], c->K[4], c->K[2], c->K[5], rot_grid, N, poses_out,
+                            info_out, st);
 }
 
 int fp_make_crops(fp_ctx* c, const float* poses, int N, int mode, void* crops_out, float* dbg_out, float* win_out,

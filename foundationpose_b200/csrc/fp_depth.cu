@@ -91,3 +91,112 @@ int bilateral_depth_launch(const float* depth, float* out, int H, int W, int rad
 }
 
 }  // namespace fp
+
+// ------------------------------------------------------------------------------------------------
+// start poses on the device: guess_translation (estimater.py:137-156) + rot_grid with that translation
+// (estimater.py:127-134, :203-209).  One CTA; the median of the masked valid depths is an exact radix
+// select over the float bit patterns (depths are positive, so the patterns are ordered), np.median's
+// mean of the two middle elements for an even count included.
+// ------------------------------------------------------------------------------------------------
+namespace fp {
+
+__device__ unsigned int radix_select(const float* __restrict__ depth, const unsigned char* __restrict__ mask, int npix,
+                                     unsigned int k, unsigned int* hist /*smem[256]*/, unsigned int* sh /*smem[2]*/) {
+  // returns the bit pattern of the k-th smallest (0-based) valid masked depth
+  unsigned int prefix = 0, prefix_mask = 0;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < npix; i += blockDim.x) {
+      const float d = depth[i];
+      if (mask[i] && d >= 0.001f) {
+        const unsigned int b = __float_as_uint(d);
+        if ((b & prefix_mask) == prefix) atomicAdd(&hist[(b >> shift) & 255u], 1u);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int acc = 0, bin = 0;
+      for (; bin < 256; ++bin) {
+        if (acc + hist[bin] > k) break;
+        acc += hist[bin];
+      }
+      sh[0] = bin;
+      sh[1] = k - acc;
+    }
+    __syncthreads();
+    prefix |= sh[0] << shift;
+    prefix_mask |= 255u << shift;
+    k = sh[1];
+    __syncthreads();
+  }
+  return prefix;
+}
+
+__global__ void __launch_bounds__(1024) start_poses_kernel(const float* __restrict__ depth,
+                                                           const unsigned char* __restrict__ mask, int H, int W, float fx,
+                                                           float fy, float cx, float cy, const float* __restrict__ rot_grid,
+                                                           int N, float* __restrict__ poses_out, float* __restrict__ info) {
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int sh[2];
+  __shared__ int bb[4];  // umin, umax, vmin, vmax
+  __shared__ unsigned int cnt[2];
+  __shared__ float tvec[3];
+  const int npix = H * W;
+  if (threadIdx.x == 0) {
+    bb[0] = W; bb[1] = -1; bb[2] = H; bb[3] = -1;
+    cnt[0] = 0; cnt[1] = 0;
+  }
+  __syncthreads();
+  int umin = W, umax = -1, vmin = H, vmax = -1;
+  unsigned int n_mask = 0, n_valid = 0;
+  for (int i = threadIdx.x; i < npix; i += blockDim.x) {
+    if (mask[i]) {
+      const int v = i / W, u = i - v * W;
+      umin = min(umin, u); umax = max(umax, u); vmin = min(vmin, v); vmax = max(vmax, v);
+      ++n_mask;
+      if (depth[i] >= 0.001f) ++n_valid;
+    }
+  }
+  atomicMin(&bb[0], umin); atomicMax(&bb[1], umax); atomicMin(&bb[2], vmin); atomicMax(&bb[3], vmax);
+  atomicAdd(&cnt[0], n_mask); atomicAdd(&cnt[1], n_valid);
+  __syncthreads();
+  const unsigned int nm = cnt[0], nv = cnt[1];
+  float zc = 0.f;
+  if (nm > 0 && nv > 0) {  // uniform branch
+    const unsigned int lo = radix_select(depth, mask, npix, (nv - 1) / 2, hist, sh);
+    const unsigned int hi = (nv & 1u) ? lo : radix_select(depth, mask, npix, nv / 2, hist, sh);
+    zc = (nv & 1u) ? __uint_as_float(lo) : (__uint_as_float(lo) + __uint_as_float(hi)) * 0.5f;
+  }
+  if (threadIdx.x == 0) {
+    double t[3] = {0.0, 0.0, 0.0};
+    if (nm > 0 && nv > 0) {
+      const double uc = (bb[0] + bb[1]) / 2.0, vc = (bb[2] + bb[3]) / 2.0;
+      // np.linalg.inv(K) @ [uc, vc, 1] * zc  for K = [[fx,0,cx],[0,fy,cy],[0,0,1]]
+      t[0] = (uc - (double)cx) / (double)fx * (double)zc;
+      t[1] = (vc - (double)cy) / (double)fy * (double)zc;
+      t[2] = (double)zc;
+    }
+    tvec[0] = (float)t[0]; tvec[1] = (float)t[1]; tvec[2] = (float)t[2];
+    info[0] = tvec[0]; info[1] = tvec[1]; info[2] = tvec[2]; info[3] = (float)nv;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N * 16; i += blockDim.x) {
+    const int e = i & 15;
+    float v = rot_grid[i];
+    if (e == 3) v = tvec[0];
+    else if (e == 7) v = tvec[1];
+    else if (e == 11) v = tvec[2];
+    poses_out[i] = v;
+  }
+}
+
+int start_poses_launch(const float* depth, const unsigned char* mask, int H, int W, float fx, float fy, float cx, float cy,
+                       const float* rot_grid, int N, float* poses_out, float* info, cudaStream_t stream) {
+  start_poses_kernel<<<1, 1024, 0, stream>>>(depth, mask, H, W, fx, fy, cx, cy, rot_grid, N, poses_out, info);
+  ++g_launch_count;
+  FP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace fp

@@ -29,6 +29,7 @@ def _proto():
     lib.fp_set_frame.argtypes = [vp, vp, vp, C.POINTER(f), i, i, i, f, vp]
     lib.fp_get_depth.argtypes = [vp, vp, vp, vp]
     lib.fp_make_crops.argtypes = [vp, vp, i, i, vp, vp, vp, vp]
+    lib.fp_start_poses.argtypes = [vp, vp, i, vp, i, vp, vp, vp]
     lib.fp_refine.argtypes = [vp, vp, i, i, vp, vp, vp, vp]
     lib.fp_score.argtypes = [vp, vp, i, vp, vp, vp]
     lib.fp_score_features.argtypes = [vp, vp, i, vp, vp]
@@ -40,7 +41,7 @@ def _proto():
     lib.fp_op_depth_filter.argtypes = [vp, vp, i, i, i, vp]
     lib.fp_op_pose_update.argtypes = [vp, vp, vp, vp, i, f, f, vp]
     for name in ("fp_create", "fp_destroy", "fp_set_config", "fp_load_network", "fp_set_mesh", "fp_set_frame",
-                 "fp_get_depth", "fp_make_crops", "fp_refine", "fp_score", "fp_score_features", "fp_score_tail",
+                 "fp_get_depth", "fp_make_crops", "fp_start_poses", "fp_refine", "fp_score", "fp_score_features", "fp_score_tail",
                  "fp_register", "fp_op_refine_net", "fp_op_score_feats", "fp_op_tokens", "fp_op_depth_filter",
                  "fp_op_pose_update"):
         getattr(lib, name).restype = C.c_int
@@ -209,6 +210,24 @@ class Engine:
         x = torch.empty(H, W, 3, dtype=torch.float32, device="cuda")
         _lib.check(lib.fp_get_depth(self._h, _p(d), _p(x), _stream()), "fp_get_depth")
         return d, x
+
+    def start_poses(self, mask, rot_grid):
+        """guess_translation + start poses on the device (no host synchronisation).
+        mask: bool/uint8 (H,W) numpy / CPU tensor / CUDA tensor; rot_grid: (N,4,4) CUDA float32.
+        Returns poses (N,4,4) and info (4,) = (tx, ty, tz, n_valid), both CUDA tensors."""
+        rot_grid = rot_grid.contiguous()
+        N = len(rot_grid)
+        if torch.is_tensor(mask) and mask.is_cuda:
+            m = mask.to(torch.uint8).contiguous()
+            on_dev = 1
+        else:
+            m = torch.as_tensor(np.ascontiguousarray(mask)).to(torch.uint8).contiguous() if not torch.is_tensor(mask) else mask.to(torch.uint8).contiguous()
+            on_dev = 0
+        self._mask_keep = m
+        poses = torch.empty(N, 4, 4, dtype=torch.float32, device="cuda")
+        info = torch.empty(4, dtype=torch.float32, device="cuda")
+        _lib.check(lib.fp_start_poses(self._h, _p(m), on_dev, _p(rot_grid), N, _p(poses), _p(info), _stream()), "fp_start_poses")
+        return poses, info
 
     # ---- hot path
     @staticmethod

@@ -197,29 +197,27 @@ class FoundationPose:
     def register(self, K, rgb, depth, ob_mask, ob_id=None, glctx=None, iteration=5):
         """Compute the object pose in the frame (estimater.py:159-240). Returns (4,4) numpy."""
         e = self.engine
-        # erode_depth + bilateral_filter_depth + depth2xyzmap on the device (estimater.py:173-174, :214)
+        # erode_depth + bilateral_filter_depth + depth2xyzmap on the device (estimater.py:173-174, :214), then the
+        # translation guess and the start poses, also on the device: nothing synchronises until the result is read
         e.set_frame(rgb, depth, K, filter_depth=True, zfar=float("inf"))
-        depth_f, _ = e.get_depth()
-        depth_f = depth_f.cpu().numpy()  # the translation guess (median) is host-side, as in the reference
-        valid = (depth_f >= 0.001) & (ob_mask > 0)
-        if valid.sum() < 4:
-            logging.info("valid too small, return")
-            pose = np.eye(4)
-            pose[:3, 3] = self.guess_translation(depth=depth_f, mask=ob_mask, K=K)
-            return pose
-        self.H, self.W = depth_f.shape[:2]
+        poses, info = e.start_poses(ob_mask, self.rot_grid)
+        self.H, self.W = depth.shape[:2]
         self.K = K
         self.ob_id = ob_id
         self.ob_mask = ob_mask
-        center = self.guess_translation(depth=depth_f, mask=ob_mask, K=K)
-        poses = self._rot_grid_host.clone()
-        poses[:, :3, 3] = torch.as_tensor(center.reshape(1, 3), dtype=torch.float32)
-        poses, _ = self.refiner.predict(mesh=self.mesh, mesh_tensors=self.mesh_tensors, rgb=rgb, depth=depth_f, K=K,
-                                        ob_in_cams=poses.cuda(non_blocking=True), normal_map=None, xyz_map=None, glctx=self.glctx,
+        poses, _ = self.refiner.predict(mesh=self.mesh, mesh_tensors=self.mesh_tensors, rgb=rgb, depth=depth, K=K,
+                                        ob_in_cams=poses, normal_map=None, xyz_map=None, glctx=self.glctx,
                                         mesh_diameter=self.diameter, iteration=iteration, _frame_ready=True)
-        scores, _ = self.scorer.predict(mesh=self.mesh, rgb=rgb, depth=depth_f, K=K, ob_in_cams=poses, normal_map=None,
+        scores, _ = self.scorer.predict(mesh=self.mesh, rgb=rgb, depth=depth, K=K, ob_in_cams=poses, normal_map=None,
                                         mesh_tensors=self.mesh_tensors, glctx=self.glctx, mesh_diameter=self.diameter,
                                         _frame_ready=True)
+        info = info.cpu().numpy()  # first host synchronisation
+        if info[3] < 4:
+            # estimater.py:183-189: too few valid pixels -> identity rotation, guessed translation
+            logging.info("valid too small, return")
+            pose = np.eye(4)
+            pose[:3, 3] = info[:3]
+            return pose
         ids = torch.as_tensor(scores).argsort(descending=True)
         scores = scores[ids]
         poses = poses[ids]

@@ -119,6 +119,14 @@ int fp_set_frame(fp_ctx* ctx, const unsigned char* rgb, const float* depth, cons
 /* Copies the filtered depth [H][W] and/or the xyz map [H][W][3] to device buffers (test hook). */
 int fp_get_depth(fp_ctx* ctx, float* depth_out_dev, float* xyz_out_dev, void* stream);
 
+/* FoundationPose.guess_translation (estimater.py:137-156: centre of the mask's bounding box, median of the
+ * masked valid depths of the CURRENT FILTERED frame) and generate_random_pose_hypo (estimater.py:127-134,
+ * :203-209) on the device: mask uint8/bool [H][W] (host, or device if mask_on_device), rot_grid [N][16]
+ * device -> poses_out [N][16] device (grid rotations, guessed translation) and info_out[4] device =
+ * {tx, ty, tz, number of valid masked pixels (the `valid.sum() < 4` test of estimater.py:183)}. */
+int fp_start_poses(fp_ctx* ctx, const unsigned char* mask, int mask_on_device, const float* rot_grid, int N,
+                   float* poses_out, float* info_out, void* stream);
+
 /* make_crop_data_batch (predict_pose_refine.py:25-89 for mode 0, predict_score.py:56-114 for mode 1):
  * poses [N][16] device.  Fills the context's crop buffer; optionally copies it to crops_out
  * (fp16 [2N][166][168][8]: images 0..N-1 rendered, N..2N-1 observed), an fp32 copy of the

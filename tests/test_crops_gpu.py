@@ -130,3 +130,34 @@ def test_pose_update(scene):
     out = op_pose_update(poses.cuda(), trans.cuda(), rot.cuda(), scene["d"], 0.3490658503988659)
     ref, _, _ = geometry.pose_update(poses, trans, rot, scene["d"], 0.3490658503988659)
     np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), atol=2e-6, rtol=0)
+
+
+def test_start_poses_match_host_guess_translation(scene):
+    """Device-side guess_translation (exact masked median via radix select) vs the host restatement of
+    estimater.py:137-156, odd and even valid counts, empty mask, no valid depth."""
+    from foundationpose_b200 import hypotheses, synth
+
+    e = scene["e"]
+    e.set_frame(scene["rgb"], scene["depth"], scene["K"], filter_depth=True)
+    depth_f = e.get_depth()[0].cpu().numpy()
+    grid = torch.from_numpy(hypotheses.make_rotation_grid()).cuda()
+    _, _, mask = synth.make_scene(scene["mesh"].visual.image, scene["poses"][0].astype(np.float64))
+    masks = [mask.copy(), mask.copy(), np.zeros_like(mask), mask.copy()]
+    vs, us = np.where(masks[1])
+    masks[1][vs[0], us[0]] = False  # flips the parity of the valid count
+    depths_zero = [False, False, False, True]
+    for m, dz in zip(masks, depths_zero):
+        if dz:
+            e.set_frame(scene["rgb"], np.zeros_like(scene["depth"]), scene["K"], filter_depth=True)
+            dref = np.zeros_like(depth_f)
+        else:
+            e.set_frame(scene["rgb"], scene["depth"], scene["K"], filter_depth=True)
+            dref = depth_f
+        poses, info = e.start_poses(m, grid)
+        ref_t = hypotheses.guess_translation(dref, m, scene["K"])
+        info = info.cpu().numpy()
+        np.testing.assert_allclose(info[:3], ref_t, atol=1e-6, rtol=0)
+        assert int(info[3]) == int((m & (dref >= 0.001)).sum())
+        p = poses.cpu().numpy()
+        np.testing.assert_array_equal(p[:, :3, :3], grid.cpu().numpy()[:, :3, :3])
+        np.testing.assert_allclose(p[:, :3, 3], np.tile(ref_t.astype(np.float32), (252, 1)), atol=1e-6, rtol=0)
