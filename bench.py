@@ -210,7 +210,7 @@ def main():
     from foundationpose_b200 import _lib, hypotheses, synth
     from foundationpose_b200.engine import Engine
     from foundationpose_b200.estimater import FoundationPose, PoseRefinePredictor, ScorePredictor
-    from foundationpose_b200.parallel import ShardedRegister, shard_bounds
+    from foundationpose_b200.parallel import ShardedRegister
     from foundationpose_b200.weights import random_state_dict
 
     peaks = load_peaks()
@@ -265,12 +265,10 @@ def main():
     def step_e2e():
         if world == 1:
             return est.register(K=K, rgb=rgb_h, depth=depth_h, ob_mask=mask, iteration=N_ITER)
-        # sharded register: every rank uploads the frame, refines its slice, one all-gather, same result everywhere
+        # sharded register: every rank uploads the frame and the mask, derives the start poses on the device,
+        # refines its slice; one all-gather; same result everywhere
         eng.set_frame(rgb_h, depth_h, K, filter_depth=True)
-        dd, _ = eng.get_depth()
-        c = hypotheses.guess_translation(dd.cpu().numpy(), mask, K)
-        p = est._rot_grid_host.clone()
-        p[:, :3, 3] = torch.as_tensor(c.reshape(1, 3), dtype=torch.float32)
+        p, info = eng.start_poses(mask, est.rot_grid)
         po, sc, b = sharded.run(p, N_ITER)
         return (po[int(b.item())] @ est.get_tf_to_centered_mesh()).cpu().numpy()
 
@@ -286,9 +284,9 @@ def main():
         t = torch.tensor([e2e_ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
-    lo, hi = shard_bounds(N_HYP, world, rank)
-    h2d = rgb_h.nbytes + depth_h.nbytes + (hi - lo) * 64
-    d2h = depth_h.nbytes + 64 + 4
+    # per step and rank: frame + mask up; (tx, ty, tz, n_valid) and the best pose down
+    h2d = rgb_h.nbytes + depth_h.nbytes + mask.nbytes
+    d2h = 16 + 64
 
     # ---------------------------------------------------------------- roofline of the dominant kernel (dedicated pass)
     _lib.prof_enable(True)
