@@ -122,40 +122,34 @@ constexpr int kSlabBytes = kBlockM * 64 * 2;  // 16 KB: one output slab (128 pix
 // SLABS = epilogue staging slabs (16 KB each).  2: slabs are recycled one by one.  4 (residual layers with
 // BN = 256): one slab per 64-channel slice of the tile, so the whole tile's residual is prefetched by TMA
 // while the tile's MMAs are still running.
-// WRES = k-blocks of the weight matrix kept resident in shared memory for the whole kernel (0 = weights stream
-// through the ring with the activations).  Used by the stem: its 64 x 448 weight matrix (56 KB) is the same for
-// all 25 200 tiles, and re-fetching it was a third of the layer's L2 -> smem traffic.
-template <int BN, int CG, int SLABS, int WRES>
+template <int BN, int CG, int SLABS>
 struct TileCfg {
   static constexpr int kBBytes = (BN / CG) * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + (WRES ? 0 : kBBytes);
+  static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = SLABS * kSlabBytes;
-  static constexpr int kWresBytes = WRES * kBBytes;
-  static constexpr int kRing = 196608 + 2 * kSlabBytes - kStagingBytes - kWresBytes;
+  static constexpr int kRing = 196608 + 2 * kSlabBytes - kStagingBytes;
   static constexpr int kStages = (kRing / kStageBytes) > 8 ? 8 : (kRing / kStageBytes);
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-  static constexpr int kSmemBytes = kStages * kStageBytes + kWresBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int CG, int SLABS, int WRES>
+template <int BN, int CG, int SLABS>
 __global__ void __launch_bounds__(kTileThreads, 1)
     gemm_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
                      const __grid_constant__ GemmParams p) {
-  using Cfg = TileCfg<BN, CG, SLABS, WRES>;
+  using Cfg = TileCfg<BN, CG, SLABS>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* wres = smem + S * Cfg::kStageBytes;     // [WRES][kBBytes] resident weight k-blocks
-  uint8_t* staging = wres + Cfg::kWresBytes;       // [SLABS][kSlabBytes], 1024-aligned
+  uint8_t* staging = smem + S * Cfg::kStageBytes;  // [2][kSlabBytes], 1024-aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
   uint64_t* full = bars;                 // [S]
   uint64_t* empty = bars + S;            // [S]
   uint64_t* tmem_full = bars + 2 * S;    // [2]
   uint64_t* tmem_empty = bars + 2 * S + 2;  // [2]
   uint64_t* res_full = bars + 2 * S + 4;    // [4]
-  uint64_t* w_full = bars + 2 * S + 8;      // resident weights landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 9);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -177,7 +171,6 @@ __global__ void __launch_bounds__(kTileThreads, 1)
       mbar_init(&tmem_empty[a], 256 * CG);
     }
     for (int a = 0; a < 4; ++a) mbar_init(&res_full[a], 1);
-    mbar_init(w_full, 1);
     tma_prefetch_desc(&map_out);
     if (p.has_res) tma_prefetch_desc(&map_res);
     mbar_fence_init();
@@ -213,10 +206,6 @@ __global__ void __launch_bounds__(kTileThreads, 1)
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0, phase = 0;
-      if (WRES) {
-        mbar_expect_tx(w_full, Cfg::kWresBytes);
-        for (int kb = 0; kb < WRES; ++kb) tma_load_2d(&map_b, w_full, wres + kb * Cfg::kBBytes, kb * kBlockK, 0);
-      }
       for (int vt = vt0; vt < total_vt; vt += vt_step) {
         int n_tile, tw, th, tn;
         decode(vt, n_tile, tw, th, tn);
@@ -239,7 +228,7 @@ __global__ void __launch_bounds__(kTileThreads, 1)
           } else {
             mbar_expect_tx(&full[stage], Cfg::kStageBytes);
             tma_load_5d(&map_a, &full[stage], sa, c0, c1, c2, c3, c4);
-            if (!WRES) tma_load_2d(&map_b, &full[stage], sb, kb * kBlockK, n_tile * BN);
+            tma_load_2d(&map_b, &full[stage], sb, kb * kBlockK, n_tile * BN);
           }
           if (++chunk == p.chunks_per_tap) {
             chunk = 0;
@@ -258,7 +247,6 @@ __global__ void __launch_bounds__(kTileThreads, 1)
       constexpr uint32_t idesc = umma_idesc_f16(BN, 128u * CG);
       int stage = 0, phase = 0;
       int it = 0;
-      if (WRES) mbar_wait(w_full, 0);
       for (int vt = vt0; vt < total_vt; vt += vt_step, ++it) {
         const int acc = it & 1;
         const int acc_phase = (it >> 1) & 1;
@@ -269,7 +257,7 @@ __global__ void __launch_bounds__(kTileThreads, 1)
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = WRES ? smem_u32(wres + kb * Cfg::kBBytes) : sa + kABytes;
+          const uint32_t sb = sa + kABytes;
           const uint64_t da = umma_desc_sw128(sa);
           const uint64_t db = umma_desc_sw128(sb);
 #pragma unroll
@@ -711,13 +699,13 @@ static int g_num_sms = 0;
 
 static int g_cta_group = -1;  // FPOSE_CTA_GROUP=1 falls back to single-CTA MMAs (A/B checks)
 
-template <int BN, int CG, int SLABS, int WRES = 0>
+template <int BN, int CG, int SLABS>
 static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mr,
                      const GemmParams& p, cudaStream_t stream) {
-  using Cfg = TileCfg<BN, CG, SLABS, WRES>;
+  using Cfg = TileCfg<BN, CG, SLABS>;
   static bool attr_set = false;
   if (!attr_set) {
-    FP_CUDA_OK(cudaFuncSetAttribute(gemm_tile_kernel<BN, CG, SLABS, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FP_CUDA_OK(cudaFuncSetAttribute(gemm_tile_kernel<BN, CG, SLABS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -744,7 +732,7 @@ static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtenso
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   prof_mark_begin(0, p.alg_flops, stream);
-  FP_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tile_kernel<BN, CG, SLABS, WRES>, ma, mb, mo, mr, p));
+  FP_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tile_kernel<BN, CG, SLABS>, ma, mb, mo, mr, p));
   prof_mark_end(stream);
   ++g_launch_count;
   FP_CUDA_OK(cudaGetLastError());
@@ -962,8 +950,6 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
     return CG == 2 ? launch_bn<256, 2, 2>(ma, mb, mo, mr, p, stream) : launch_bn<256, 1, 2>(ma, mb, mo, mr, p, stream);
   }
   if (BN == 128) return launch_bn<128, 1, 2>(ma, mb, mo, mr, p, stream);
-  // stem: 7 k-blocks of weights (56 KB) resident, only activations stream through the ring
-  if (L.kind == LK_CONV7_S2 && p.num_kb == 7 && p.n_tiles_n == 1) return launch_bn<64, 1, 2, 7>(ma, mb, mo, mr, p, stream);
   return launch_bn<64, 1, 2>(ma, mb, mo, mr, p, stream);
 }
 
