@@ -94,7 +94,7 @@ struct fp_ctx {
   bool use_graphs = true;
   fp::DevBuf lt_buf, lr_buf, feat_buf, pose_stage;
   fp::DevBuf vtx_a, vtx_b, win_buf;  // crop producer workspaces: [cap_n][V] x 16 B each, [cap_n][8]
-  fp::DevBuf mask_buf;
+  fp::DevBuf mask_buf, tab_buf, zbuf;
 };
 
 namespace fp {
@@ -303,10 +303,14 @@ static int make_crops(fp_ctx* c, const float* poses, int N, int mode, float* dbg
   FP_TRY(dev_alloc(c->vtx_a, (size_t)c->cap_n * c->V * 16));
   FP_TRY(dev_alloc(c->vtx_b, (size_t)c->cap_n * c->V * 16));
   FP_TRY(dev_alloc(c->win_buf, (size_t)c->cap_n * 8 * 4));
+  FP_TRY(dev_alloc(c->tab_buf, (size_t)c->cap_n * 6 * 160 * 4));
+  FP_TRY(dev_alloc(c->zbuf, (size_t)c->cap_n * 160 * 160 * 8));
   CropParams p;
   p.vtx_a = reinterpret_cast<VtxA*>(c->vtx_a.p);
   p.vtx_b = reinterpret_cast<VtxB*>(c->vtx_b.p);
   p.win_buf = reinterpret_cast<float*>(c->win_buf.p);
+  p.tab_buf = reinterpret_cast<float*>(c->tab_buf.p);
+  p.zbuf = reinterpret_cast<unsigned long long*>(c->zbuf.p);
   p.V = c->V;
   p.poses = poses;
   p.N = N;
@@ -422,7 +426,7 @@ int fp_destroy(fp_ctx* c) {
   for (auto& kv : c->graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
-  DevBuf* more[] = {&c->lt_buf, &c->lr_buf, &c->feat_buf, &c->pose_stage, &c->vtx_a, &c->vtx_b, &c->win_buf, &c->mask_buf};
+  DevBuf* more[] = {&c->lt_buf, &c->lr_buf, &c->feat_buf, &c->pose_stage, &c->vtx_a, &c->vtx_b, &c->win_buf, &c->mask_buf, &c->tab_buf, &c->zbuf};
   for (DevBuf* b : more)
     if (b->p) cudaFree(b->p);
   delete c;

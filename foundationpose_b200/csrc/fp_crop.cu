@@ -20,8 +20,6 @@
 namespace fp {
 
 constexpr int S = 160;               // crop size (cfg.input_resize)
-constexpr int kCropThreads = 1024;
-constexpr int kZbufBytes = S * S * 8;
 
 struct Window {
   float left, top, sx, sy;           // tf_to_crop = [[sx,0,-left*sx],[0,sy,-top*sy],[0,0,1]]
@@ -165,6 +163,8 @@ __device__ __forceinline__ void normalise_xyz(float x, float y, float z, const f
 // pass 0: one thread per (hypothesis, vertex): camera transform, projection into the crop raster,
 // 1/256-px snap, per-vertex diffuse term.  16 + 16 bytes per vertex, written once, read ~6x (L2).
 // ------------------------------------------------------------------------------------------------
+constexpr int kTabWords = 6 * S;  // per hypothesis: colf, rowf (float), coln, rown, colz, rowz (int)
+
 struct __align__(16) VtxA {  // what the z-buffer pass needs
   int xi, yi;
   float iz, Z;
@@ -196,6 +196,34 @@ __global__ void __launch_bounds__(256) vertex_kernel(const CropParams p) {
     }
   }
   __syncthreads();
+  if (blockIdx.x == 0) {
+    // per-axis tables of the observed-crop resampling (every quantity is separable in x and y): S columns, S rows
+    for (int tI = threadIdx.x; tI < 2 * S; tI += blockDim.x) {
+      const bool is_row = tI >= S;
+      const int d = is_row ? tI - S : tI;
+      const float sc = is_row ? sW.sy : sW.sx, org = is_row ? sW.top : sW.left;
+      const int size = is_row ? p.H : p.W;
+      const float xs = __fadd_rn(__fdiv_rn((float)d, sc), org);
+      const float ix = kornia_src_coord(xs, size);
+      int un = (int)rintf(ix);
+      if (un < 0 || un >= size) un = -1;
+      int uz = -1;
+      if (un >= 0) {
+        // scorer: depth crop -> full-res (nearest) -> back-project -> crop (nearest), h5_dataset.py:158-161
+        const float xc = __fadd_rn(__fmul_rn(sc, (float)un), __fmul_rn(-org, sc));
+        const int jc = (int)rintf(kornia_src_coord(xc, S));
+        if (jc >= 0 && jc < S) {
+          const float xs2 = __fadd_rn(__fdiv_rn((float)jc, sc), org);
+          const int u2 = (int)rintf(kornia_src_coord(xs2, size));
+          if (u2 >= 0 && u2 < size) uz = u2;
+        }
+      }
+      float* tb = p.tab_buf + (size_t)n * kTabWords;
+      tb[(is_row ? 1 : 0) * S + d] = ix;
+      reinterpret_cast<int*>(tb)[(2 + (is_row ? 1 : 0)) * S + d] = un;
+      reinterpret_cast<int*>(tb)[(4 + (is_row ? 1 : 0)) * S + d] = uz;
+    }
+  }
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= p.V) return;
   VtxScreen o;
@@ -289,101 +317,68 @@ __device__ __noinline__ void bary_big_tri(const VtxA a, const VtxA b, const VtxA
   bw[0] = b0; bw[1] = b1; bw[2] = b2;
 }
 
-constexpr int kTabBytes = 8 * S * 4;  // per-axis resampling tables
-
-__global__ void __launch_bounds__(kCropThreads, 1) crop_kernel(const CropParams p) {
-  extern __shared__ unsigned long long zbuf[];  // [S*S] then the tables
-  float* colf = reinterpret_cast<float*>(zbuf + S * S);  // source x of crop column j (kornia chain)
-  float* rowf = colf + S;
-  int* coln = reinterpret_cast<int*>(rowf + S);           // nearest source column (or -1)
-  int* rown = coln + S;
-  int* colz = rown + S;                                   // scorer: source column of the depth round trip (or -1)
-  int* rowz = colz + S;
-  __shared__ float sP[16];
-  __shared__ Window sW;
-  const int n = blockIdx.x;
-  const int tid = threadIdx.x;
-
-  if (tid < 16) sP[tid] = p.poses[(size_t)n * 16 + tid];
-  if (tid == 32) {
-    const float* wb = p.win_buf + (size_t)n * 8;
-    Window w;
-    w.left = wb[0]; w.top = wb[1]; w.sx = wb[2]; w.sy = wb[3];
-    w.umin = wb[4]; w.vmin = wb[5]; w.rsx = wb[6]; w.rsy = wb[7];
-    sW = w;
+// ------------------------------------------------------------------------------------------------
+// pass 1: one thread per (hypothesis, triangle): coverage + depth test into the per-hypothesis z-buffer
+// (64-bit keys in global memory = L2: 200 KB per hypothesis), so the work spreads over the whole GPU for
+// any batch size (one pose in track_one, ~32 per GPU when sharded, 252 in register).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) raster_kernel(const CropParams p) {
+  const int n = blockIdx.y;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= p.F) return;
+  const VtxA* va = p.vtx_a + (size_t)n * p.V;
+  unsigned long long* zbuf = p.zbuf + (size_t)n * S * S;
+  const int i0 = __ldg(p.faces + 3 * f), i1 = __ldg(p.faces + 3 * f + 1), i2 = __ldg(p.faces + 3 * f + 2);
+  const VtxA a = va[i0], b = va[i1], c = va[i2];
+  if (!(a.Z > p.znear && b.Z > p.znear && c.Z > p.znear)) return;  // no near-plane clipping
+  const int minx = min(a.xi, min(b.xi, c.xi)), maxx = max(a.xi, max(b.xi, c.xi));
+  const int miny = min(a.yi, min(b.yi, c.yi)), maxy = max(a.yi, max(b.yi, c.yi));
+  const int j0 = max((minx + 127) >> 8, 0), j1 = min((maxx - 128) >> 8, S - 1);
+  const int r0 = max((miny + 127) >> 8, 0), r1 = min((maxy - 128) >> 8, S - 1);
+  if (j0 > j1 || r0 > r1) return;
+  if (!tri_small(a.xi, a.yi, b.xi, b.yi, c.xi, c.yi)) {
+    raster_big_tri(a, b, c, f, j0, j1, r0, r1, zbuf);
+    return;
   }
-  for (int i = tid; i < S * S; i += kCropThreads) zbuf[i] = 0ull;
-  __syncthreads();
-  const Window w = sW;
-  // per-axis tables of the observed-crop resampling (every quantity is separable in x and y)
-  if (tid < 2 * S) {
-    const bool is_row = tid >= S;
-    const int d = is_row ? tid - S : tid;
-    const float sc = is_row ? w.sy : w.sx, org = is_row ? w.top : w.left;
-    const int size = is_row ? p.H : p.W;
-    const float xs = __fadd_rn(__fdiv_rn((float)d, sc), org);
-    const float ix = kornia_src_coord(xs, size);
-    int un = (int)rintf(ix);
-    if (un < 0 || un >= size) un = -1;
-    int uz = -1;
-    if (un >= 0) {
-      // scorer: depth crop -> full-res (nearest) -> back-project -> crop (nearest), h5_dataset.py:158-161
-      const float xc = __fadd_rn(__fmul_rn(sc, (float)un), __fmul_rn(-org, sc));
-      const int jc = (int)rintf(kornia_src_coord(xc, S));
-      if (jc >= 0 && jc < S) {
-        const float xs2 = __fadd_rn(__fdiv_rn((float)jc, sc), org);
-        const int u2 = (int)rintf(kornia_src_coord(xs2, size));
-        if (u2 >= 0 && u2 < size) uz = u2;
-      }
+  TriSetup32 t32;
+  if (!tri_setup32(a.xi, a.yi, b.xi, b.yi, c.xi, c.yi, t32)) return;
+  for (int r = r0; r <= r1; ++r)
+    for (int j = j0; j <= j1; ++j) {
+      float b0, b1, b2;
+      if (!tri_cover32(t32, j * 256 + 128, r * 256 + 128, b0, b1, b2)) continue;
+      const float iz = inv_depth(b0, b1, b2, a.iz, b.iz, c.iz);
+      const unsigned long long key =
+          ((unsigned long long)__float_as_uint(iz) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)f);
+      atomicMax(&zbuf[r * S + j], key);
     }
-    (is_row ? rowf : colf)[d] = ix;
-    (is_row ? rown : coln)[d] = un;
-    (is_row ? rowz : colz)[d] = uz;
-  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 2: one thread per (hypothesis, crop pixel): shade the winning triangle (A), resample the observed
+// frame (B), normalise both, write the two fp16 NHWC(8) pixels.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) shade_kernel(const CropParams p) {
+  __shared__ float sP[16];
+  const int n = blockIdx.y;
+  if (threadIdx.x < 16) sP[threadIdx.x] = p.poses[(size_t)n * 16 + threadIdx.x];
+  __syncthreads();
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= S * S) return;
+  const float* tb = p.tab_buf + (size_t)n * kTabWords;
+  const int* tbi = reinterpret_cast<const int*>(tb);
   const VtxA* va = p.vtx_a + (size_t)n * p.V;
   const VtxB* vb = p.vtx_b + (size_t)n * p.V;
-
-  // ---------------------------------------------------------------- pass 1: z-buffer
-  for (int f = tid; f < p.F; f += kCropThreads) {
-    const int i0 = __ldg(p.faces + 3 * f), i1 = __ldg(p.faces + 3 * f + 1), i2 = __ldg(p.faces + 3 * f + 2);
-    const VtxA a = va[i0], b = va[i1], c = va[i2];
-    if (!(a.Z > p.znear && b.Z > p.znear && c.Z > p.znear)) continue;  // no near-plane clipping
-    const int minx = min(a.xi, min(b.xi, c.xi)), maxx = max(a.xi, max(b.xi, c.xi));
-    const int miny = min(a.yi, min(b.yi, c.yi)), maxy = max(a.yi, max(b.yi, c.yi));
-    const int j0 = max((minx + 127) >> 8, 0), j1 = min((maxx - 128) >> 8, S - 1);
-    const int r0 = max((miny + 127) >> 8, 0), r1 = min((maxy - 128) >> 8, S - 1);
-    if (j0 > j1 || r0 > r1) continue;
-    if (!tri_small(a.xi, a.yi, b.xi, b.yi, c.xi, c.yi)) {
-      raster_big_tri(a, b, c, f, j0, j1, r0, r1, zbuf);
-      continue;
-    }
-    TriSetup32 t32;
-    if (!tri_setup32(a.xi, a.yi, b.xi, b.yi, c.xi, c.yi, t32)) continue;
-    for (int r = r0; r <= r1; ++r)
-      for (int j = j0; j <= j1; ++j) {
-        float b0, b1, b2;
-        if (!tri_cover32(t32, j * 256 + 128, r * 256 + 128, b0, b1, b2)) continue;
-        const float iz = inv_depth(b0, b1, b2, a.iz, b.iz, c.iz);
-        const unsigned long long key =
-            ((unsigned long long)__float_as_uint(iz) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)f);
-        atomicMax(&zbuf[r * S + j], key);
-      }
-  }
-  __syncthreads();
-
-  // ---------------------------------------------------------------- pass 2: shade + observed crop + normalise
   const float inv_radius = p.inv_radius;
   const float tvec[3] = {sP[3], sP[7], sP[11]};
   const float tau = p.mode == 0 ? 0.001f : 0.1f;
   const size_t img_stride = (size_t)(S + 6) * (S + 8) * 8;
   __half* outA = p.crops + (size_t)n * img_stride;
   __half* outB = p.crops + (size_t)(p.b_img0 + n) * img_stride;
-
-  for (int pix = tid; pix < S * S; pix += kCropThreads) {
+  {
     const int r = pix / S, j = pix - r * S;
     // ---- A: rendered crop
     float ar = 0.f, ag = 0.f, ab = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
-    const unsigned long long key = zbuf[pix];
+    const unsigned long long key = p.zbuf[(size_t)n * S * S + pix];
     if (key != 0ull) {
       const int f = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
       const int i0 = __ldg(p.faces + 3 * f), i1 = __ldg(p.faces + 3 * f + 1), i2 = __ldg(p.faces + 3 * f + 2);
@@ -440,7 +435,7 @@ __global__ void __launch_bounds__(kCropThreads, 1) crop_kernel(const CropParams 
     // ---- B: observed crop
     float br = 0.f, bg = 0.f, bb = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
     {
-      const float ix = colf[j], iy = rowf[r];
+      const float ix = __ldg(tb + j), iy = __ldg(tb + S + r);
       // bilinear rgb, zeros padding
       const float fx0 = floorf(ix), fy0 = floorf(iy);
       const int x0 = (int)fx0, y0 = (int)fy0;
@@ -462,7 +457,7 @@ __global__ void __launch_bounds__(kCropThreads, 1) crop_kernel(const CropParams 
       bg *= (1.f / 255.f);
       bb *= (1.f / 255.f);
       // nearest geometry
-      const int un = coln[j], vn = rown[r];
+      const int un = __ldg(tbi + 2 * S + j), vn = __ldg(tbi + 3 * S + r);
       float X = 0.f, Y = 0.f, Z = 0.f;
       if (un >= 0 && vn >= 0) {
         if (p.mode == 0) {
@@ -472,7 +467,7 @@ __global__ void __launch_bounds__(kCropThreads, 1) crop_kernel(const CropParams 
           Y = __ldg(q + 1);
           Z = __ldg(q + 2);
         } else {
-          const int u2 = colz[j], v2 = rowz[r];
+          const int u2 = __ldg(tbi + 4 * S + j), v2 = __ldg(tbi + 5 * S + r);
           float zz = 0.f;
           if (u2 >= 0 && v2 >= 0) zz = __ldg(p.depth + (size_t)v2 * p.W + u2);
           if (zz >= 0.001f) {  // depth2xyzmap_batch(zfar=inf): invalid z<0.001 -> 0
@@ -497,18 +492,15 @@ __global__ void __launch_bounds__(kCropThreads, 1) crop_kernel(const CropParams 
 }
 
 int crop_launch(const CropParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    FP_CUDA_OK(cudaFuncSetAttribute(crop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kZbufBytes + kTabBytes));
-    attr_set = true;
-  }
   if (p.N == 0) return 0;
   // algorithmic bytes: the two 6-channel fp16 crops each hypothesis produces
   prof_mark_begin(1, (double)p.N * 2.0 * 6.0 * S * S * 2.0, stream);
+  FP_CUDA_OK(cudaMemsetAsync(p.zbuf, 0, (size_t)p.N * S * S * sizeof(unsigned long long), stream));
   vertex_kernel<<<dim3((p.V + 255) / 256, p.N), 256, 0, stream>>>(p);
-  crop_kernel<<<p.N, kCropThreads, kZbufBytes + kTabBytes, stream>>>(p);
+  raster_kernel<<<dim3((p.F + 255) / 256, p.N), 256, 0, stream>>>(p);
+  shade_kernel<<<dim3((S * S + 255) / 256, p.N), 256, 0, stream>>>(p);
   prof_mark_end(stream);
-  g_launch_count += 2;
+  g_launch_count += 3;
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -34,6 +34,8 @@ struct CropParams {
   struct VtxA* vtx_a;  // [N][V] 16 B
   struct VtxB* vtx_b;  // [N][V] 16 B
   float* win_buf;      // [N][8]
+  float* tab_buf;      // [N][6][160] per-axis resampling tables
+  unsigned long long* zbuf;  // [N][160*160] depth/triangle keys
   float* dbg;      // optional [N][2][160][160][6] fp32 copy of the normalised crops
   float* win_out;  // optional [N][4] = (left, top, sx, sy)
 };

@@ -901,7 +901,12 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
   }
   const bool swap_ab = g_swap_ab && BN == 128 && L.Cout == 128 && !L.post_add &&
                        (L.kind == LK_CONV3_S1 || L.kind == LK_CONV3_S2);
-  const int CG = (g_cta_group == 2 && BN == 256 && p.num_kb >= 16) ? 2 : 1;
+  static int cg2_min_kb = -1;
+  if (cg2_min_kb < 0) {
+    const char* e = getenv("FPOSE_CG2_MIN_KB");
+    cg2_min_kb = e ? atoi(e) : 16;
+  }
+  const int CG = (g_cta_group == 2 && BN == 256 && p.num_kb >= cg2_min_kb) ? 2 : 1;
   uint32_t wb[2] = {64, (uint32_t)(BN / CG)};
   rc = encode_map(&mb, L.w, 2, wd, ws, wb);
   if (rc) return rc;
