@@ -100,14 +100,18 @@ int bilateral_depth_launch(const float* depth, float* out, int H, int W, int rad
 // ------------------------------------------------------------------------------------------------
 namespace fp {
 
-__device__ unsigned int radix_select(const float* __restrict__ depth, const unsigned char* __restrict__ mask, int npix,
-                                     unsigned int k, unsigned int* hist /*smem[256]*/, unsigned int* sh /*smem[2]*/) {
-  // returns the bit pattern of the k-th smallest (0-based) valid masked depth
+__device__ unsigned int radix_select(const float* __restrict__ depth, const unsigned char* __restrict__ mask, int W,
+                                     int u0, int v0, int bw, int bh, unsigned int k, unsigned int* hist /*smem[256]*/,
+                                     unsigned int* sh /*smem[2]*/) {
+  // returns the bit pattern of the k-th smallest (0-based) valid masked depth; only the mask's bounding box
+  // (u0, v0, bw x bh) is scanned
   unsigned int prefix = 0, prefix_mask = 0;
+  const int nbox = bw * bh;
   for (int shift = 24; shift >= 0; shift -= 8) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < npix; i += blockDim.x) {
+    for (int q = threadIdx.x; q < nbox; q += blockDim.x) {
+      const int i = (v0 + q / bw) * W + u0 + q % bw;
       const float d = depth[i];
       if (mask[i] && d >= 0.001f) {
         const unsigned int b = __float_as_uint(d);
@@ -164,8 +168,9 @@ __global__ void __launch_bounds__(1024) start_poses_kernel(const float* __restri
   const unsigned int nm = cnt[0], nv = cnt[1];
   float zc = 0.f;
   if (nm > 0 && nv > 0) {  // uniform branch
-    const unsigned int lo = radix_select(depth, mask, npix, (nv - 1) / 2, hist, sh);
-    const unsigned int hi = (nv & 1u) ? lo : radix_select(depth, mask, npix, nv / 2, hist, sh);
+    const int u0 = bb[0], v0 = bb[2], bw = bb[1] - bb[0] + 1, bh = bb[3] - bb[2] + 1;
+    const unsigned int lo = radix_select(depth, mask, W, u0, v0, bw, bh, (nv - 1) / 2, hist, sh);
+    const unsigned int hi = (nv & 1u) ? lo : radix_select(depth, mask, W, u0, v0, bw, bh, nv / 2, hist, sh);
     zc = (nv & 1u) ? __uint_as_float(lo) : (__uint_as_float(lo) + __uint_as_float(hi)) * 0.5f;
   }
   if (threadIdx.x == 0) {

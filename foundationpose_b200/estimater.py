@@ -211,22 +211,25 @@ class FoundationPose:
         scores, _ = self.scorer.predict(mesh=self.mesh, rgb=rgb, depth=depth, K=K, ob_in_cams=poses, normal_map=None,
                                         mesh_tensors=self.mesh_tensors, glctx=self.glctx, mesh_diameter=self.diameter,
                                         _frame_ready=True)
-        info = info.cpu().numpy()  # first host synchronisation
-        if info[3] < 4:
-            # estimater.py:183-189: too few valid pixels -> identity rotation, guessed translation
-            logging.info("valid too small, return")
-            pose = np.eye(4)
-            pose[:3, 3] = info[:3]
-            return pose
         ids = torch.as_tensor(scores).argsort(descending=True)
         scores = scores[ids]
         poses = poses[ids]
         best_pose = poses[0] @ self.get_tf_to_centered_mesh()
+        prev = (self.pose_last, getattr(self, "best_id", None), getattr(self, "poses", None), getattr(self, "scores", None))
         self.pose_last = poses[0]
         self.best_id = ids[0]
         self.poses = poses
         self.scores = scores
-        return best_pose.data.cpu().numpy()
+        # the only host synchronisation of register(): (tx, ty, tz, n_valid) and the best pose in one read-back
+        out = torch.cat([info, best_pose.reshape(-1)]).cpu().numpy()
+        if out[3] < 4:
+            # estimater.py:183-189: too few valid pixels -> identity rotation, guessed translation
+            logging.info("valid too small, return")
+            pose = np.eye(4)
+            pose[:3, 3] = out[:3]
+            self.pose_last, self.best_id, self.poses, self.scores = prev  # the reference returns before touching them
+            return pose
+        return out[4:].reshape(4, 4).copy()
 
     def track_one(self, rgb, depth, K, iteration, extra={}):
         if self.pose_last is None:
