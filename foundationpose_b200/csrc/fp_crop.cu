@@ -5,8 +5,8 @@
 //   3. resamples the observed frame into the same window  (predict_pose_refine.py:63,72 / predict_score.py:89-90,
 //      kornia warp_perspective -> F.grid_sample; h5_dataset.py:158-161 depth round trip for the scorer)
 //   4. normalises both crops                              (h5_dataset.py:79-127 refiner, :137-179 scorer)
-// and writes the two 6-channel crops as fp16 NHWC(8) images with the 3-pixel zero border the 7x7 stem
-// convolution reads (fp_gemm.cu, LK_CONV7_S2).  Nothing full-frame and nothing fp32 is materialised in HBM.
+// and writes the two 6-channel crops as fp16 8-channel images with the 3-pixel zero border and the even/odd
+// column split the 7x7 stem convolution reads (fp_stem.cu, LK_CONV7_S2).  Nothing full-frame and nothing fp32 is materialised in HBM.
 //
 // Raster: integer/fp32 load-store work (no tensor cores).  Vertices are snapped to 1/256 pixel and
 // coverage is decided by exact 64-bit integer edge functions with a top-left tie rule (watertight);
@@ -479,7 +479,10 @@ __global__ void __launch_bounds__(256) shade_kernel(const CropParams p) {
       }
       normalise_xyz(X, Y, Z, tvec, inv_radius, tau, bx, by, bz);
     }
-    const size_t off = ((size_t)(r + 3) * (S + 8) + (j + 3)) * 8;
+    // even / odd padded columns live in separate half-rows ("EO" layout, fp_stem.cu): pixel (row, col) ->
+    // [row][col & 1][col >> 1][8]
+    const int pc = j + 3;
+    const size_t off = (((size_t)(r + 3) * 2 + (pc & 1)) * ((S + 8) / 2) + (pc >> 1)) * 8;
     *reinterpret_cast<uint4*>(outA + off) = make_uint4(pack_half2(ar, ag), pack_half2(ab, ax), pack_half2(ay, az), 0u);
     *reinterpret_cast<uint4*>(outB + off) = make_uint4(pack_half2(br, bg), pack_half2(bb, bx), pack_half2(by, bz), 0u);
     if (p.dbg) {

@@ -28,7 +28,8 @@ struct CropParams {
   const float* depth;    // [H][W]      (mode 1)
   int mode;              // 0 = refiner crops, 1 = scorer crops
   // outputs
-  __half* crops;   // [b_img0 + N][166][168][8] fp16: images 0..N-1 = rendered (A), b_img0..b_img0+N-1 = observed (B)
+  __half* crops;   // [b_img0 + N][166][2][84][8] fp16 (rows x {even, odd columns} x column pairs x 8 channels, the
+                   // "EO" layout of fp_stem.cu): images 0..N-1 = rendered (A), b_img0..b_img0+N-1 = observed (B)
   int b_img0;      // first B image (N rounded up to the conv tile's image count, see fp_api.cu)
   // workspaces (device): per-hypothesis pre-transformed vertices and crop windows
   struct VtxA* vtx_a;  // [N][V] 16 B

@@ -17,9 +17,8 @@
 //     5-D TMA box over the NHWC activation tensor, displaced by the tap offset; out-of-bounds
 //     coordinates are zero-filled by the TMA unit, which implements the zero padding.  Stride-2
 //     convolutions use a (2C, W/2, 2, H/2, N) view of the same memory so that every tap is again a
-//     dense box; the 7x7/s2 stem reads a spatially pre-padded 8-channel image through an
-//     overlapping-stride view (64 contiguous fp16 = 8 pixels x 8 channels per output pixel and
-//     filter row).  No im2col buffer is ever materialised.
+//     dense box; the 7x7/s2 stem has its own kernel (fp_stem.cu).  No im2col buffer is ever
+//     materialised.
 #include "fp_gemm.cuh"
 
 #include <stdarg.h>
@@ -640,6 +639,8 @@ __global__ void __launch_bounds__(kTileThreads, 1)
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -659,7 +660,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box) {
+                      const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box, bool swizzle128 = true) {
   EncodeTiledFn fn = get_encode_fn();
   FP_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
   cuuint64_t gdim[5];
@@ -673,7 +674,7 @@ static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64
   }
   for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
-                  bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FP_REQUIRE(r == CUDA_SUCCESS,
              "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u]",
@@ -688,14 +689,24 @@ int encode_map_f16(CUtensorMap* map, const void* base, int rank, const uint64_t*
                    const uint32_t* box) {
   return encode_map(map, base, rank, dims, strides_bytes, box);
 }
+int encode_map_f16_linear(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box) {
+  return encode_map(map, base, rank, dims, strides_bytes, box, false);
+}
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  }
+  return g_num_sms;
+}
 
 static int ilog2(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;
   return l;
 }
-
-static int g_num_sms = 0;
 
 static int g_cta_group = -1;  // FPOSE_CTA_GROUP=1 falls back to single-CTA MMAs (A/B checks)
 
@@ -764,7 +775,10 @@ static int launch_swap(const CUtensorMap& ma, const CUtensorMap& mw, const CUten
   return 0;
 }
 
+int stem_conv_launch(const GemmLayer& L, cudaStream_t stream);  // fp_stem.cu
+
 int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
+  if (L.kind == LK_CONV7_S2) return stem_conv_launch(L, stream);
   GemmParams p;
   memset(&p, 0, sizeof(p));
   CUtensorMap ma, mb;
@@ -836,28 +850,10 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
       p.tiles_w = Wo / p.bw; p.tiles_h = Ho / p.bh; p.tiles_n = (L.n_img + p.bn - 1) / p.bn;
       break;
     }
-    case LK_CONV7_S2: {
-      FP_REQUIRE(L.Cin == 8, "CONV7_S2: input must be channel-padded to 8");
-      FP_REQUIRE(L.Hin % 16 == 0 && L.Win % 32 == 0, "CONV7_S2: unsupported size");
-      Ho = L.Hin / 2; Wo = L.Win / 2;
-      taps = 7;
-      p.chunks_per_tap = 1;
-      p.bw = 16; p.bh = 8; p.bn = 1;
-      p.dim_w = 1; p.dim_h = 2; p.dim_n = 4;
-      const uint64_t Hp = L.Hin + 6, Wp = L.Win + 8;
-      // per (output pixel, filter row r): 64 contiguous fp16 = input pixels 2j..2j+7 (8 ch each) of
-      // padded row 2i + r.  Overlapping strides: j advances 2 pixels (32 B), i advances 2 rows.
-      dims[0] = 64; dims[1] = Wo; dims[2] = Ho; dims[3] = 7; dims[4] = L.n_img;
-      str[0] = 2 * 8 * E; str[1] = 2 * Wp * 8 * E; str[2] = Wp * 8 * E; str[3] = Hp * Wp * 8 * E;
-      box[0] = 64; box[1] = 16; box[2] = 8; box[3] = 1; box[4] = 1;
-      for (int r = 0; r < 7; ++r) p.tap_off[r][3] = (short)r;
-      p.tiles_w = Wo / 16; p.tiles_h = Ho / 8; p.tiles_n = L.n_img;
-      break;
-    }
     default:
       FP_REQUIRE(false, "unknown layer kind %d", L.kind);
   }
-  ktot = (L.kind == LK_CONV7_S2) ? 7 * 64 : taps * L.Cin;
+  ktot = taps * L.Cin;
   p.num_kb = ktot / 64;
   p.lg_bw = ilog2(p.bw);
   p.lg_bh = ilog2(p.bh);
@@ -875,7 +871,7 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
   p.post_add = L.post_add;
   p.relu = L.relu;
   {
-    const double k_real = (L.kind == LK_CONV7_S2) ? 7.0 * 7.0 * 6.0 : (double)taps * L.Cin;
+    const double k_real = (double)taps * L.Cin;
     p.alg_flops = 2.0 * (double)L.n_img * Ho * Wo * L.Cout * k_real;
   }
   FP_REQUIRE(L.out_ld % 8 == 0 && (!L.res || L.res_ld % 8 == 0), "out_ld / res_ld must be multiples of 8");

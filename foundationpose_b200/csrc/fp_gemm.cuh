@@ -11,8 +11,8 @@ enum LayerKind : int {
   LK_LINEAR = 0,    // out[m, :] = in[m, :] @ W^T            (in: [M, K] fp16 row-major)
   LK_CONV3_S1 = 1,  // 3x3 stride 1 pad 1                      (in: NHWC fp16)
   LK_CONV3_S2 = 2,  // 3x3 stride 2 pad 1                      (in: NHWC fp16, H, W even)
-  LK_CONV7_S2 = 3,  // 7x7 stride 2 pad 3, Cin padded to 8     (in: [n][Hin+6][Win+8][8] fp16,
-                    //   3-pixel zero border already in memory: see DESIGN.md "crop layout")
+  LK_CONV7_S2 = 3,  // 7x7 stride 2 pad 3, Cin padded to 8     (in: [n][Hin+6][2][(Win+8)/2][8] fp16,
+                    //   3-pixel zero border already in memory, even/odd column split: fp_stem.cu)
 };
 
 // Geometry + pointers of one layer launch.  All pointers are device pointers.
@@ -23,7 +23,7 @@ struct GemmLayer {
   int Cin;          // input channels (LINEAR: K).  CONV7: 8 (6 real + 2 zero)
   int Cout;         // output channels; multiple of the N tile (64 / 128 / 256)
   const void* in;   // fp16 activations
-  const void* w;    // fp16 packed weights [Cout][Ktot], Ktot = taps * Cin (CONV7: 7 * 64)
+  const void* w;    // fp16 packed weights [Cout][Ktot], Ktot = taps * Cin (CONV7: [7][4][2][64][8], fp_stem.cu)
   const float* bias;      // [Cout] fp32 (BN folded)
   const void* res;        // optional residual, fp16, indexed like the output with ld = res_ld
   int res_ld;

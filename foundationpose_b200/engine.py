@@ -12,7 +12,7 @@ import torch
 from . import _lib, packing
 from ._lib import lib
 
-CROP_H, CROP_W, CROP_C = 166, 168, 8  # padded fp16 crop image consumed by the stem convolution
+CROP_SHAPE = (166, 2, 84, 8)  # padded fp16 crop image consumed by the stem convolution: rows x {even, odd cols} x pairs x ch
 
 
 class _FpTensor(C.Structure):
@@ -240,7 +240,7 @@ class Engine:
     def make_crops(self, poses, mode=0, want_crops=True, want_dbg=False):
         poses = self._poses(poses)
         N = len(poses)
-        crops = torch.empty(2 * N, CROP_H, CROP_W, CROP_C, dtype=torch.float16, device="cuda") if want_crops else None
+        crops = torch.empty(2 * N, *CROP_SHAPE, dtype=torch.float16, device="cuda") if want_crops else None
         dbg = torch.empty(N, 2, 160, 160, 6, dtype=torch.float32, device="cuda") if want_dbg else None
         win = torch.empty(N, 4, dtype=torch.float32, device="cuda")
         _lib.check(lib.fp_make_crops(self._h, _p(poses), N, mode, _p(crops), _p(dbg), _p(win), _stream()), "fp_make_crops")
@@ -309,7 +309,7 @@ class Engine:
 
 
 def crops_from_planar(A, B):
-    """(N,6,160,160) float A, B -> the fp16 padded NHWC(8) crop buffer layout [2N][166][168][8]."""
+    """(N,6,160,160) float A, B -> the fp16 padded crop buffer layout [2N][166][2][84][8] (packing.pad_image_c8)."""
     return packing.pad_image_c8(torch.cat([A, B], 0))
 
 

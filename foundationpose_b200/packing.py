@@ -27,11 +27,13 @@ def pack_conv3(w):
 
 
 def pack_conv7(w):
-    """(Co,Ci<=8,7,7) fp32 -> (Co, 7*64) fp16: per filter row r, 7 taps x 8 channels + 8 zeros."""
+    """(Co,Ci<=8,7,7) fp32 -> (7, 4, 2, Co, 8) fp16 = [filter row r][tap pair s][tap 2s + e][Co][8 ch]: one
+    un-swizzled K-major tcgen05 B tile (N = Co, K = 16) per (r, s); tap 7 and channels >= Ci are zero
+    (csrc/fp_stem.cu)."""
     co, ci = w.shape[:2]
-    out = torch.zeros(co, 7, 8, 8, dtype=torch.float32)  # (co, r, s(pad to 8), c(pad to 8))
-    out[:, :, :7, :ci] = w.permute(0, 2, 3, 1)
-    return out.reshape(co, 7 * 64).contiguous().half()
+    out = torch.zeros(7, 8, co, 8, dtype=torch.float32)  # (r, tap padded to 8, co, c padded to 8)
+    out[:, :7, :, :ci] = w.detach().float().permute(2, 3, 0, 1)
+    return out.reshape(7, 4, 2, co, 8).contiguous().half()
 
 
 def pack_linear(w):
@@ -40,8 +42,16 @@ def pack_linear(w):
 
 
 def pad_image_c8(x):
-    """(N,C<=8,H,W) float -> stem input layout [N][H+6][W+8][8] fp16, image at (3,3), zero border."""
+    """(N,C<=8,H,W) float -> stem input layout [N][H+6][2][(W+8)/2][8] fp16: the image sits at (3,3) of a
+    zero-bordered (H+6, W+8) canvas whose rows are stored as even columns then odd columns ("EO" layout,
+    csrc/fp_stem.cu)."""
     n, c, h, w = x.shape
-    out = torch.zeros(n, h + 6, w + 8, 8, dtype=torch.float16, device=x.device)
-    out[:, 3 : 3 + h, 3 : 3 + w, :c] = x.permute(0, 2, 3, 1).half()
-    return out
+    canvas = torch.zeros(n, h + 6, w + 8, 8, dtype=torch.float16, device=x.device)
+    canvas[:, 3 : 3 + h, 3 : 3 + w, :c] = x.permute(0, 2, 3, 1).half()
+    return canvas.reshape(n, h + 6, (w + 8) // 2, 2, 8).permute(0, 1, 3, 2, 4).contiguous()
+
+
+def unpad_image_c8(buf):
+    """Inverse view of pad_image_c8: [N][H+6][2][(W+8)/2][8] -> the padded NHWC canvas (N, H+6, W+8, 8)."""
+    n, hp, two, wh, c = buf.shape
+    return buf.permute(0, 1, 3, 2, 4).reshape(n, hp, 2 * wh, c)

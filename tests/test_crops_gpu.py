@@ -76,18 +76,22 @@ def test_crops_match_oracle(scene, mode):
 
 
 def test_fp16_crop_buffer_layout(scene):
-    """The fp16 NHWC(8) buffer the stem convolution reads: interior = crops, border = zeros."""
+    """The fp16 buffer the stem convolution reads: [2N][166 rows][even | odd columns][84 pairs][8]; interior =
+    crops, border = zeros."""
+    from foundationpose_b200 import packing
+
     e = scene["e"]
     e.set_frame(scene["rgb"], scene["depth"], scene["K"], filter_depth=False)
     crops, dbg, _ = e.make_crops(scene["poses"], mode=0, want_dbg=True)
     N = len(scene["poses"])
-    assert crops.shape == (2 * N, 166, 168, 8)
-    inner = crops[:, 3:163, 3:163, :6].float()
+    assert crops.shape == (2 * N, 166, 2, 84, 8)
+    canvas = packing.unpad_image_c8(crops)
+    inner = canvas[:, 3:163, 3:163, :6].float()
     ref = torch.cat([dbg[:, 0], dbg[:, 1]], 0)
     assert (inner - ref).abs().max().item() <= 2e-3
-    assert crops[:, :3].abs().max().item() == 0 and crops[:, 163:].abs().max().item() == 0
-    assert crops[:, :, :3].abs().max().item() == 0 and crops[:, :, 163:].abs().max().item() == 0
-    assert crops[..., 6:].abs().max().item() == 0
+    assert canvas[:, :3].abs().max().item() == 0 and canvas[:, 163:].abs().max().item() == 0
+    assert canvas[:, :, :3].abs().max().item() == 0 and canvas[:, :, 163:].abs().max().item() == 0
+    assert canvas[..., 6:].abs().max().item() == 0
 
 
 def test_depth_filters(scene):

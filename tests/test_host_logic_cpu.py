@@ -36,19 +36,24 @@ def test_pack_layouts():
     # K order (r, s, c)
     assert float(p[1, (1 * 3 + 2) * 3 + 1]) == float(w[1, 1, 1, 2])
     w7 = torch.randn(4, 6, 7, 7)
-    p7 = packing.pack_conv7(w7).float().reshape(4, 7, 8, 8)
-    assert torch.allclose(p7[:, :, :7, :6], w7.permute(0, 2, 3, 1).half().float())
-    assert p7[:, :, 7].abs().max() == 0 and p7[:, :, :, 6:].abs().max() == 0
+    p7 = packing.pack_conv7(w7).float()  # [r][s][e][co][c], tap = 2s + e
+    assert p7.shape == (7, 4, 2, 4, 8)
+    taps = p7.reshape(7, 8, 4, 8)
+    assert torch.allclose(taps[:, :7, :, :6], w7.permute(2, 3, 0, 1).half().float())
+    assert taps[:, 7].abs().max() == 0 and taps[..., 6:].abs().max() == 0
     x = torch.rand(2, 6, 160, 160)
     xp = packing.pad_image_c8(x)
-    assert xp.shape == (2, 166, 168, 8)
-    assert torch.equal(xp[:, 3:163, 3:163, :6], x.permute(0, 2, 3, 1).half())
-    assert xp[:, :3].abs().max() == 0 and xp[..., 6:].abs().max() == 0
+    assert xp.shape == (2, 166, 2, 84, 8)
+    canvas = packing.unpad_image_c8(xp)
+    assert torch.equal(canvas[:, 3:163, 3:163, :6], x.permute(0, 2, 3, 1).half())
+    assert canvas[:, :3].abs().max() == 0 and canvas[..., 6:].abs().max() == 0
+    # even columns first, then odd columns: padded column 3 (image column 0) is odd, pair 1
+    assert torch.equal(xp[:, 3, 1, 1, :6], x[:, :, 0, 0].half())
 
 
 def test_pack_network_names_and_shapes():
     r = pack_network(random_state_dict("refine", 0), "refine")
-    assert r["enc.0.w"].shape == (64, 448) and r["enc.14.w"].shape == (512, 4608) and r["heads.in_w"].shape == (3072, 512)
+    assert r["enc.0.w"].shape == (7, 4, 2, 64, 8) and r["enc.14.w"].shape == (512, 4608) and r["heads.in_w"].shape == (3072, 512)
     assert r["pe"].shape == (400, 512) and r["head1.fin_w"].shape == (3, 512)
     s = pack_network(random_state_dict("score", 0), "score")
     assert s["cross.in_w"].dtype == np.float32 and s["att.in_w"].dtype == np.float16 and s["lin.w"].shape == (512,)
