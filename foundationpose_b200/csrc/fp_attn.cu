@@ -271,6 +271,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
   const int warps_total = gridDim.x * (blockDim.x >> 5);
   LnAffine af;
   ln_load_affine(af, gamma, beta, lane);
+  pdl_trigger();
+  pdl_wait();
   for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps_total) {
     float v[16];
     load_row16(x + (size_t)row * 512, lane, v);
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
 int layernorm_launch(const __half* x, __half* y, const float* gamma, const float* beta, int rows, cudaStream_t stream) {
   if (rows == 0) return 0;
   const int blocks = min((rows + 7) / 8, 148 * 8);
-  layernorm_kernel<<<blocks, 256, 0, stream>>>(x, y, gamma, beta, rows, 1e-5f);
+  FP_CUDA_OK(launch_pdl(layernorm_kernel, dim3(blocks), dim3(256), 0, stream, 1, x, y, gamma, beta, rows, 1e-5f));
   ++g_launch_count;
   FP_CUDA_OK(cudaGetLastError());
   return 0;
@@ -306,6 +308,8 @@ __global__ void __launch_bounds__(256) head_final_kernel(const __half* __restric
   for (int i = 0; i < 16; ++i) a[i] = 0.f;
   LnAffine af;
   ln_load_affine(af, gamma, beta, lane);
+  pdl_trigger();
+  pdl_wait();
   for (int t = warp; t < T; t += 8) {
     float v[16];
     load_row16(x + ((size_t)b * T + t) * 512, lane, v);
@@ -335,7 +339,7 @@ int head_final_launch(const __half* x, const float* gamma, const float* beta, co
                       float* out, int B, int T, int out_dim, cudaStream_t stream) {
   FP_REQUIRE(out_dim <= 8, "head_final: out_dim %d > 8", out_dim);
   if (B == 0) return 0;
-  head_final_kernel<<<B, 256, 0, stream>>>(x, gamma, beta, w, bias, out, T, out_dim, 1e-5f);
+  FP_CUDA_OK(launch_pdl(head_final_kernel, dim3(B), dim3(256), 0, stream, 1, x, gamma, beta, w, bias, out, T, out_dim, 1e-5f));
   ++g_launch_count;
   FP_CUDA_OK(cudaGetLastError());
   return 0;
@@ -351,6 +355,8 @@ __global__ void __launch_bounds__(256) token_mean_proj_kernel(const __half* __re
   float a[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) a[i] = 0.f;
+  pdl_trigger();
+  pdl_wait();
   for (int t = warp; t < T; t += 8) {
     float v[16];
     load_row16(x + ((size_t)b * T + t) * 512, lane, v);
@@ -382,7 +388,7 @@ __global__ void __launch_bounds__(256) token_mean_proj_kernel(const __half* __re
 int token_mean_proj_launch(const __half* x, const __half* w, const float* bias, float* out, int B, int T,
                            cudaStream_t stream) {
   if (B == 0) return 0;
-  token_mean_proj_kernel<<<B, 256, 0, stream>>>(x, w, bias, out, T);
+  FP_CUDA_OK(launch_pdl(token_mean_proj_kernel, dim3(B), dim3(256), 0, stream, 1, x, w, bias, out, T));
   ++g_launch_count;
   FP_CUDA_OK(cudaGetLastError());
   return 0;
@@ -513,6 +519,8 @@ __global__ void pose_update_kernel(const float* __restrict__ pose_in, const floa
                                    const float* __restrict__ rot, float* __restrict__ pose_out,
                                    float* __restrict__ trans_delta_out, float* __restrict__ rot_delta_out, int N,
                                    float trans_scale, float rot_normalizer) {
+  pdl_trigger();
+  pdl_wait();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const float* A = pose_in + (size_t)n * 16;
@@ -573,8 +581,8 @@ int pose_update_launch(const float* pose_in, const float* trans, const float* ro
                        float* trans_delta_out, float* rot_delta_out, int N, float trans_scale, float rot_normalizer,
                        cudaStream_t stream) {
   if (N == 0) return 0;
-  pose_update_kernel<<<(N + 127) / 128, 128, 0, stream>>>(pose_in, trans, rot, pose_out, trans_delta_out, rot_delta_out,
-                                                          N, trans_scale, rot_normalizer);
+  FP_CUDA_OK(launch_pdl(pose_update_kernel, dim3((N + 127) / 128), dim3(128), 0, stream, 1, pose_in, trans, rot, pose_out,
+                        trans_delta_out, rot_delta_out, N, trans_scale, rot_normalizer));
   ++g_launch_count;
   FP_CUDA_OK(cudaGetLastError());
   return 0;

@@ -165,6 +165,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -375,7 +377,7 @@ int attn_tc_launch(const AttnParams& p, cudaStream_t stream) {
   tp.group_col_stride = p.group_col_stride;
   tp.scale_log2e = p.scale * 1.4426950408889634f;
   dim3 grid(p.B, p.n_heads, p.n_groups);
-  attn_tc_kernel<<<grid, kThreadsTc, kSmem, stream>>>(mk, mq, mv, mo, tp);
+  FP_CUDA_OK(launch_pdl(attn_tc_kernel, grid, dim3(kThreadsTc), kSmem, stream, 1, mk, mq, mv, mo, tp));
   ++g_launch_count;
   FP_CUDA_OK(cudaGetLastError());
   return 0;

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 namespace fp {
 
@@ -32,8 +33,50 @@ void set_last_error(const char* fmt, ...);
   } while (0)
 
 // ----------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL).  Every kernel of a network pass is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may be scheduled (on SMs the previous kernel has
+// already left) and run their prologue — barrier init, TMEM allocation, tensor-map prefetch, loads of constant
+// weights — while the previous kernel's last wave is still draining.  Contract inside a kernel: pdl_trigger()
+// early (lets the NEXT kernel be scheduled once every CTA of this one has started), and pdl_wait() before the
+// first access to global memory that an earlier kernel writes or reads (it returns when all earlier kernels of
+// the stream have completed and flushed).  FPOSE_PDL=0 falls back to plain stream order.
+// ----------------------------------------------------------------------------------------------
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              int cluster_x, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster_x;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// ----------------------------------------------------------------------------------------------
 // device PTX helpers
 // ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

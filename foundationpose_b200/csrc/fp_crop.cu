@@ -323,6 +323,8 @@ __device__ __noinline__ void bary_big_tri(const VtxA a, const VtxA b, const VtxA
 // any batch size (one pose in track_one, ~32 per GPU when sharded, 252 in register).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) raster_kernel(const CropParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int n = blockIdx.y;
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= p.F) return;
@@ -359,6 +361,8 @@ __global__ void __launch_bounds__(256) raster_kernel(const CropParams p) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) shade_kernel(const CropParams p) {
   __shared__ float sP[16];
+  pdl_trigger();
+  pdl_wait();
   const int n = blockIdx.y;
   if (threadIdx.x < 16) sP[threadIdx.x] = p.poses[(size_t)n * 16 + threadIdx.x];
   __syncthreads();
@@ -500,8 +504,8 @@ int crop_launch(const CropParams& p, cudaStream_t stream) {
   prof_mark_begin(1, (double)p.N * 2.0 * 6.0 * S * S * 2.0, stream);
   FP_CUDA_OK(cudaMemsetAsync(p.zbuf, 0, (size_t)p.N * S * S * sizeof(unsigned long long), stream));
   vertex_kernel<<<dim3((p.V + 255) / 256, p.N), 256, 0, stream>>>(p);
-  raster_kernel<<<dim3((p.F + 255) / 256, p.N), 256, 0, stream>>>(p);
-  shade_kernel<<<dim3((S * S + 255) / 256, p.N), 256, 0, stream>>>(p);
+  FP_CUDA_OK(launch_pdl(raster_kernel, dim3((p.F + 255) / 256, p.N), dim3(256), 0, stream, 1, p));
+  FP_CUDA_OK(launch_pdl(shade_kernel, dim3((S * S + 255) / 256, p.N), dim3(256), 0, stream, 1, p));
   prof_mark_end(stream);
   g_launch_count += 3;
   FP_CUDA_OK(cudaGetLastError());

@@ -91,6 +91,15 @@ void set_last_error(const char* fmt, ...) {
 }
 const char* get_last_error() { return t_last_error; }
 
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("FPOSE_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+
 struct GemmParams {
   int lg_bw, lg_bh;  // tile rows m -> (nn, ii, jj): jj = m & (bw-1), ii = (m >> lg_bw) & (bh-1)
   int bw, bh, bn;
@@ -184,6 +193,8 @@ __global__ void __launch_bounds__(kTileThreads, 1)
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();  // everything above overlapped the previous kernel's tail; activations are touched only from here on
 
   // decode this CTA's tile of virtual tile vt; an odd leftover M tile is parked out of range (TMA zero-fills
   // its loads and clips its stores)
@@ -475,6 +486,8 @@ __global__ void __launch_bounds__(kTileThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
 
   auto decode_m = [&](int m_tile, int& tw, int& th, int& tn) {
     if (m_tile < m_tiles) {
@@ -729,21 +742,9 @@ static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtenso
   const int total_vt = ((m_tiles + CG - 1) / CG) * p.n_tiles_n;
   const int slots = g_num_sms / CG;
   const int grid = CG * (total_vt < slots ? total_vt : slots);
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kTileThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
   prof_mark_begin(0, p.alg_flops, stream);
-  FP_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tile_kernel<BN, CG, SLABS>, ma, mb, mo, mr, p));
+  FP_CUDA_OK(launch_pdl(gemm_tile_kernel<BN, CG, SLABS>, dim3(grid), dim3(kTileThreads), Cfg::kSmemBytes, stream, CG, ma, mb, mo, mr,
+                        p));
   prof_mark_end(stream);
   ++g_launch_count;
   FP_CUDA_OK(cudaGetLastError());
@@ -768,7 +769,7 @@ static int launch_swap(const CUtensorMap& ma, const CUtensorMap& mw, const CUten
   const int total_vt = ((m_tiles + 1) / 2) * (p.Cout / 128);
   const int grid = total_vt < g_num_sms ? total_vt : g_num_sms;
   prof_mark_begin(0, p.alg_flops, stream);
-  gemm_swap_kernel<<<grid, kTileThreads, kSwapSmem, stream>>>(ma, mw, mo, mr, p);
+  FP_CUDA_OK(launch_pdl(gemm_swap_kernel, dim3(grid), dim3(kTileThreads), kSwapSmem, stream, 1, ma, mw, mo, mr, p));
   prof_mark_end(stream);
   ++g_launch_count;
   FP_CUDA_OK(cudaGetLastError());

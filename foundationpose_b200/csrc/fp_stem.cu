@@ -19,8 +19,8 @@
 // resident in shared memory for the life of the (persistent) CTA.
 //
 // Roles per CTA (320 threads, one CTA per SM): warp 0 = TMA producer (patch ring), warp 1 = MMA issuer,
-// warps 2..9 = epilogue (TMEM -> +bias, ReLU -> fp16 -> 128B-swizzled slab -> TMA tensor store), fp32
-// accumulators double-buffered in TMEM (2 x 64 columns).
+// warps 2..9 = two epilogue warpgroups, one per TMEM accumulator (TMEM -> +bias, ReLU -> fp16 -> 128B-swizzled
+// slab -> TMA tensor store), fp32 accumulators double-buffered in TMEM (2 x 64 columns).
 #include <stdlib.h>
 #include <string.h>
 
@@ -45,16 +45,17 @@ constexpr int kParStride = kPatchPairs * 16;             // 176 B: E -> O half-r
 constexpr int kRowStride = 2 * kParStride;               // 352 B: padded input row
 constexpr int kPatchBytes = kPatchRows * kRowStride;     // 13,024 B
 constexpr int kPatchSlot = 13 * 1024;                    // ring slot (1024-aligned)
-constexpr int kStagesStem = 8;
+constexpr int kStagesStem = 6;
 constexpr int kWTileBytes = 2 * 64 * 16;                 // one (r, s) weight tile: [E/O][64 ch][8 ci] fp16
 constexpr int kWBytes = 28 * kWTileBytes;                // 57,344 B
 constexpr int kSlab = 128 * 64 * 2;                      // 16 KB output slab
-constexpr int kStemSmem = kWBytes + kStagesStem * kPatchSlot + 2 * kSlab + 1024 + 256;
+constexpr int kStemSmem = kWBytes + kStagesStem * kPatchSlot + 4 * kSlab + 1024 + 256;
 
 struct StemParams {
   int tiles_w, tiles_h, n_img, total_tiles;
   const float* bias;
   int relu;
+  int align_test;
 };
 
 // un-swizzled K-major operand: 8 rows at 16 B, row groups `sbo` bytes apart, the two 8-element K chunks
@@ -83,8 +84,8 @@ __global__ void __launch_bounds__(kThreadsStem, 1)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* wsm = smem;
   uint8_t* ring = smem + kWBytes;
-  uint8_t* staging = ring + S * kPatchSlot;  // [2][kSlab], 1024-aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kSlab);
+  uint8_t* staging = ring + S * kPatchSlot;  // [2 groups][2][kSlab], 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 4 * kSlab);
   uint64_t* full = bars;                    // [S]
   uint64_t* empty = bars + S;               // [S]
   uint64_t* tmem_full = bars + 2 * S;       // [2]
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(kThreadsStem, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 256);
+      mbar_init(&tmem_empty[a], 128);
     }
     mbar_init(w_full, 1);
     mbar_fence_init();
@@ -115,20 +116,22 @@ __global__ void __launch_bounds__(kThreadsStem, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_per_img = p.tiles_w * p.tiles_h;
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       mbar_expect_tx(w_full, kWBytes);
-      bulk_load_1d(wsm, wpack, kWBytes, w_full);
+      bulk_load_1d(wsm, wpack, kWBytes, w_full);  // constant weights: fetched while the previous kernel drains
+      pdl_wait();
       int stage = 0, phase = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const int n = t / tiles_per_img, rem = t - n * tiles_per_img;
         const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_expect_tx(&full[stage], kPatchBytes);
-        // box (8 ch, 11 pairs, E/O, 37 rows, 1 image) at (0, 8 tw, 0, 32 th, n)
-        tma_load_5d(&map_in, &full[stage], ring + stage * kPatchSlot, 0, tw * kTileW, 0, th * 2 * kTileH, n);
+        // box (11 pairs x 8 ch, E/O, 37 rows, 1 image) at (64 tw, 0, 32 th, n)
+        tma_load_5d(&map_in, &full[stage], ring + stage * kPatchSlot, tw * kTileW * 8, 0, th * 2 * kTileH, n, 0);
         if (++stage == S) {
           stage = 0;
           phase ^= 1;
@@ -154,7 +157,8 @@ __global__ void __launch_bounds__(kThreadsStem, 1)
 #pragma unroll
           for (int s = 0; s < 4; ++s) {
             // A: rows j at 16 B from pair j + s of padded row 2i + r; row groups i two padded rows apart
-            const uint64_t da = umma_desc_linear(patch + r * kRowStride + s * 16, kParStride, 2 * kRowStride);
+            const uint64_t da = p.align_test ? umma_desc_linear(patch + r * 256, 128, 512)  // timing experiment only
+                                             : umma_desc_linear(patch + r * kRowStride + s * 16, kParStride, 2 * kRowStride);
             // B: [E/O][64 ch][8]: rows (channels) at 16 B, groups of 8 channels 128 B apart, K chunks 1 KB apart
             const uint64_t db = umma_desc_linear(w_addr + (r * 4 + s) * kWTileBytes, 1024, 128);
             umma_f16(d_tmem, da, db, idesc, (r | s) ? 1u : 0u);
@@ -170,45 +174,53 @@ __global__ void __launch_bounds__(kThreadsStem, 1)
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9)
+    // Two independent warpgroups: group g drains the tiles with (it & 1) == g, i.e. TMEM accumulator g, through its
+    // own pair of staging slabs and its own named barrier, so the per-tile chain (TMEM load -> smem -> TMA store)
+    // of one tile overlaps the next tile's.
     const int quarter = warp & 3;     // TMEM lanes [32*quarter, +32)
-    const int grp = (warp - 2) >> 2;  // 32-channel half of the 64-channel slab
+    const int grp = (warp - 2) >> 2;  // which accumulator / tile parity
     const int row = quarter * 32 + lane;
-    const bool leader = (warp == 2 && lane == 0);
+    const bool leader = (quarter == 2 && lane == 0);  // warps 2 and 6
     const uint32_t row_off = (uint32_t)row * 128u;
     const uint32_t sw = (uint32_t)(row & 7);
-    float bias[32];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) bias[k] = __ldg(p.bias + grp * 32 + k);
-    int it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-      const int acc = it & 1;
+    const float4* bias4 = reinterpret_cast<const float4*>(p.bias);
+    pdl_wait();  // the output buffer may still be read by an earlier kernel
+    int use = 0;
+    for (int t = blockIdx.x + grp * gridDim.x; t < p.total_tiles; t += 2 * gridDim.x, ++use) {
       const int n = t / tiles_per_img, rem = t - n * tiles_per_img;
       const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
-      uint8_t* slab = staging + (it & 1) * kSlab;
-      // the TMA store that last used this slab (two tiles ago) must have finished reading it
+      uint8_t* slab = staging + (grp * 2 + (use & 1)) * kSlab;
+      // the TMA store that last used this slab (two of this group's tiles ago) must have finished reading it
       if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      mbar_wait(&tmem_full[grp], use & 1);
       tc_fence_after();
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 64 + grp * 32, v);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
 #pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        const int q = grp * 4 + q4;
-        float a[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          a[k] = __uint_as_float(v[q4 * 8 + k]) + bias[q4 * 8 + k];
-          if (p.relu) a[k] = fmaxf(a[k], 0.f);
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + grp * 64 + h * 32, v);
+        tmem_ld_wait();
+        if (h == 1) {
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[grp]);
         }
-        *reinterpret_cast<uint4*>(slab + row_off + (((uint32_t)q ^ sw) << 4)) =
-            make_uint4(pack_half2(a[0], a[1]), pack_half2(a[2], a[3]), pack_half2(a[4], a[5]), pack_half2(a[6], a[7]));
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int q = h * 4 + q4;
+          const float4 b0 = __ldg(bias4 + q * 2), b1 = __ldg(bias4 + q * 2 + 1);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          float a[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            a[k] = __uint_as_float(v[q4 * 8 + k]) + bb[k];
+            if (p.relu) a[k] = fmaxf(a[k], 0.f);
+          }
+          *reinterpret_cast<uint4*>(slab + row_off + (((uint32_t)q ^ sw) << 4)) =
+              make_uint4(pack_half2(a[0], a[1]), pack_half2(a[2], a[3]), pack_half2(a[4], a[5]), pack_half2(a[6], a[7]));
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
       if (leader) {
         tma_store_5d(&map_out, slab, 0, tw * kTileW, th * kTileH, n, 0);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -240,9 +252,11 @@ int stem_conv_launch(const GemmLayer& L, cudaStream_t stream) {
   const uint64_t rows = L.Hin + 6, pairs = (L.Win + 8) / 2;
   CUtensorMap mi, mo;
   {
-    uint64_t d[5] = {8, pairs, 2, rows, (uint64_t)L.n_img};
-    uint64_t s[4] = {8 * E, pairs * 8 * E, 2 * pairs * 8 * E, rows * 2 * pairs * 8 * E};
-    uint32_t b[5] = {8, (uint32_t)kPatchPairs, 2, (uint32_t)kPatchRows, 1};
+    // (channel, pair) are contiguous in memory and are merged into one dimension, so that a box row is the
+    // 176 contiguous bytes of 11 pairs: the TMA unit's cost is per box row, not per byte
+    uint64_t d[5] = {8 * pairs, 2, rows, (uint64_t)L.n_img, 1};
+    uint64_t s[4] = {pairs * 8 * E, 2 * pairs * 8 * E, rows * 2 * pairs * 8 * E, rows * 2 * pairs * 8 * E * L.n_img};
+    uint32_t b[5] = {8 * (uint32_t)kPatchPairs, 2, (uint32_t)kPatchRows, 1, 1};
     int rc = encode_map_f16_linear(&mi, L.in, 5, d, s, b);
     if (rc) return rc;
   }
@@ -261,6 +275,7 @@ int stem_conv_launch(const GemmLayer& L, cudaStream_t stream) {
   p.total_tiles = p.tiles_w * p.tiles_h * L.n_img;
   p.bias = L.bias;
   p.relu = L.relu;
+  p.align_test = getenv("FPOSE_STEM_ALIGN_TEST") != nullptr;
   static bool attr_set = false;
   if (!attr_set) {
     FP_CUDA_OK(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem));
@@ -270,7 +285,8 @@ int stem_conv_launch(const GemmLayer& L, cudaStream_t stream) {
   FP_REQUIRE(sms > 0, "no CUDA device");
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   prof_mark_begin(0, 2.0 * (double)L.n_img * Ho * Wo * 64.0 * (7.0 * 7.0 * 6.0), stream);
-  stem_conv_kernel<<<grid, kThreadsStem, kStemSmem, stream>>>(mi, mo, reinterpret_cast<const __half*>(L.w), p);
+  FP_CUDA_OK(launch_pdl(stem_conv_kernel, dim3(grid), dim3(kThreadsStem), kStemSmem, stream, 1, mi, mo,
+                        reinterpret_cast<const __half*>(L.w), p));
   prof_mark_end(stream);
   ++g_launch_count;
   FP_CUDA_OK(cudaGetLastError());
