@@ -52,10 +52,11 @@ typedef struct fp_gemm_layer {
   int Hin, Win;       /* un-padded input size (LINEAR: Hin = 1, Win = number of rows M)           */
   int Cin;            /* input channels (LINEAR: K; CONV7_S2: 8 = 6 real + 2 zero)                */
   int Cout;           /* output channels, multiple of 64                                          */
-  const void* in;     /* fp16; NHWC.  CONV7_S2: [n][Hin+6][Win+8][8] with image at offset (3,3)
-                         and a zero border                                                        */
-  const void* w;      /* fp16 [Cout][taps*Cin] (tap-major, channel-minor); CONV7_S2: [Cout][7][64]
-                         = per filter row 7 taps x 8 ch + 8 zeros                                 */
+  const void* in;     /* fp16; NHWC.  CONV7_S2: [n][Hin+6][2][(Win+8)/2][8] = a zero-bordered
+                         (Hin+6) x (Win+8) canvas, image at (3,3), every row stored as its even
+                         columns then its odd columns (packing.pad_image_c8)                      */
+  const void* w;      /* fp16 [Cout][taps*Cin] (tap-major, channel-minor); CONV7_S2:
+                         [7 rows][4 tap pairs][2][64][8] (packing.pack_conv7)                     */
   const float* bias;  /* fp32 [Cout] (BatchNorm folded in)                                        */
   const void* res;    /* optional fp16 residual, same indexing as the output, leading dim res_ld  */
   int res_ld;
@@ -129,7 +130,7 @@ int fp_start_poses(fp_ctx* ctx, const unsigned char* mask, int mask_on_device, c
 
 /* make_crop_data_batch (predict_pose_refine.py:25-89 for mode 0, predict_score.py:56-114 for mode 1):
  * poses [N][16] device.  Fills the context's crop buffer; optionally copies it to crops_out
- * (fp16 [2N][166][168][8]: images 0..N-1 rendered, N..2N-1 observed), an fp32 copy of the
+ * (fp16 [2N][166][2][84][8]: images 0..N-1 rendered, N..2N-1 observed), an fp32 copy of the
  * normalised crops to dbg_out ([N][2][160][160][6]) and the crop windows to win_out
  * ([N][4] = left, top, sx, sy of tf_to_crop). */
 int fp_make_crops(fp_ctx* ctx, const float* poses, int N, int mode, void* crops_out, float* dbg_out, float* win_out,
@@ -156,7 +157,7 @@ int fp_score_tail(fp_ctx* ctx, const float* feats, int L, float* scores_out, int
 int fp_register(fp_ctx* ctx, const float* poses_host, int N, int iterations, float* poses_out_host,
                 float* scores_out_host, int* best_out_host, void* stream);
 
-/* parity-test hooks on pre-built crops (fp16 [2N][166][168][8], device) */
+/* parity-test hooks on pre-built crops (fp16 [2N][166][2][84][8], device) */
 int fp_op_refine_net(fp_ctx* ctx, const void* crops, int N, float* trans_out, float* rot_out, void* stream);
 int fp_op_score_feats(fp_ctx* ctx, const void* crops, int N, float* feats_out, void* stream);
 int fp_op_tokens(fp_ctx* ctx, int which, const void* crops, int N, void* tokens_out, void* stream);
