@@ -295,12 +295,17 @@ int layernorm_launch(const __half* x, __half* y, const float* gamma, const float
   return 0;
 }
 
-// norm2 -> token mean -> Linear(512, out_dim<=8).  One CTA (8 warps) per sequence.
-__global__ void __launch_bounds__(256) head_final_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
-                                                         const float* __restrict__ beta, const float* __restrict__ w,
-                                                         const float* __restrict__ bias, float* __restrict__ out, int T,
-                                                         int out_dim, float eps) {
-  __shared__ float acc[8][512];
+// norm2 -> token mean -> Linear(512, out_dim<=8).  One CTA (16 warps) per sequence; every warp walks its tokens two
+// at a time so that the second row's loads overlap the first row's reductions (the kernel is latency-bound: only
+// 252 CTAs exist).  The partial sums are combined in a fixed order: the result does not depend on N or the shard.
+constexpr int kHeadWarps = 16;
+__global__ void __launch_bounds__(kHeadWarps * 32) head_final_kernel(const __half* __restrict__ x,
+                                                                     const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta,
+                                                                     const float* __restrict__ w,
+                                                                     const float* __restrict__ bias, float* __restrict__ out,
+                                                                     int T, int out_dim, float eps) {
+  __shared__ float acc[kHeadWarps][512];
   __shared__ float meanv[512];
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float a[16];
@@ -310,9 +315,22 @@ __global__ void __launch_bounds__(256) head_final_kernel(const __half* __restric
   ln_load_affine(af, gamma, beta, lane);
   pdl_trigger();
   pdl_wait();
-  for (int t = warp; t < T; t += 8) {
+  const __half* xb = x + (size_t)b * T * 512;
+  int t = warp;
+  for (; t + kHeadWarps < T; t += 2 * kHeadWarps) {
+    float v0[16], v1[16];
+    load_row16(xb + (size_t)t * 512, lane, v0);
+    load_row16(xb + (size_t)(t + kHeadWarps) * 512, lane, v1);
+    ln_row16(v0, af, eps);
+    ln_row16(v1, af, eps);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] += v0[i];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] += v1[i];
+  }
+  if (t < T) {
     float v[16];
-    load_row16(x + ((size_t)b * T + t) * 512, lane, v);
+    load_row16(xb + (size_t)t * 512, lane, v);
     ln_row16(v, af, eps);
 #pragma unroll
     for (int i = 0; i < 16; ++i) a[i] += v[i];
@@ -320,10 +338,10 @@ __global__ void __launch_bounds__(256) head_final_kernel(const __half* __restric
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[warp][lane * 16 + i] = a[i];
   __syncthreads();
-  for (int c = threadIdx.x; c < 512; c += 256) {
+  for (int c = threadIdx.x; c < 512; c += kHeadWarps * 32) {
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s += acc[k][c];
+    for (int k = 0; k < kHeadWarps; ++k) s += acc[k][c];
     meanv[c] = s / (float)T;
   }
   __syncthreads();
@@ -339,7 +357,8 @@ int head_final_launch(const __half* x, const float* gamma, const float* beta, co
                       float* out, int B, int T, int out_dim, cudaStream_t stream) {
   FP_REQUIRE(out_dim <= 8, "head_final: out_dim %d > 8", out_dim);
   if (B == 0) return 0;
-  FP_CUDA_OK(launch_pdl(head_final_kernel, dim3(B), dim3(256), 0, stream, 1, x, gamma, beta, w, bias, out, T, out_dim, 1e-5f));
+  FP_CUDA_OK(launch_pdl(head_final_kernel, dim3(B), dim3(kHeadWarps * 32), 0, stream, 1, x, gamma, beta, w, bias, out, T, out_dim,
+                        1e-5f));
   ++g_launch_count;
   FP_CUDA_OK(cudaGetLastError());
   return 0;
@@ -397,22 +416,47 @@ int token_mean_proj_launch(const __half* x, const __half* w, const float* bias, 
 // ------------------------------------------------------------------------------------------------
 // scorer tail: attention across the L hypotheses (fp32 SIMT; 0.3 GFLOP total)
 // ------------------------------------------------------------------------------------------------
-// y[l, :] = in_proj(x[l, :]) : [L][512] fp32 -> [L][1536] fp32.  One CTA per row.
+// y[l, :] = W x[l, :] + b : [L][512] fp32 -> [L][n_out] fp32.  One CTA per (8 rows, n_out / gridDim.y outputs): a
+// weight row is fetched once per 8 hypotheses.  Per output the summation order (16 in-lane FMAs, then the butterfly)
+// does not depend on L or on the blocking.
+constexpr int kRowBlock = 8;
 __global__ void __launch_bounds__(256) rowwise_linear_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ bias, float* __restrict__ y,
-                                                             int n_out) {
-  __shared__ float xs[512];
-  const int l = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int c = threadIdx.x; c < 512; c += 256) xs[c] = x[(size_t)l * 512 + c];
+                                                             int L, int n_out) {
+  // x rows staged per lane: xs4[r][q][lane] = elements [16 lane + 4 q, +4) of row r (conflict-free 128-bit reads)
+  __shared__ float4 xs4[kRowBlock][4][32];
+  const int l0 = blockIdx.x * kRowBlock, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows = min(kRowBlock, L - l0);
+  for (int c = threadIdx.x; c < kRowBlock * 128; c += 256) {
+    const int r = c >> 7, c4 = c & 127;  // c4 = float4 index inside the row
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < rows) q = *reinterpret_cast<const float4*>(x + (size_t)(l0 + r) * 512 + c4 * 4);
+    xs4[r][c4 & 3][c4 >> 2] = q;
+  }
   __syncthreads();
-  for (int o = warp; o < n_out; o += 8) {
+  const int per_cta = n_out / gridDim.y;
+  const int o_end = (blockIdx.y + 1) * per_cta;
+  for (int o = blockIdx.y * per_cta + warp; o < o_end; o += 8) {
     float v[16];
     load_row16(w + (size_t)o * 512, lane, v);
-    float s = 0.f;
+    float s[kRowBlock];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) s += v[i] * xs[lane * 16 + i];
-    s = warp_sum(s);
-    if (lane == 0) y[(size_t)l * n_out + o] = s + bias[o];
+    for (int r = 0; r < kRowBlock; ++r) {
+      float acc = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 xv = xs4[r][q][lane];
+        acc += v[4 * q] * xv.x;
+        acc += v[4 * q + 1] * xv.y;
+        acc += v[4 * q + 2] * xv.z;
+        acc += v[4 * q + 3] * xv.w;
+      }
+      s[r] = warp_sum(acc);
+    }
+    if (lane == 0) {
+      const float bo = bias[o];
+      for (int r = 0; r < rows; ++r) y[(size_t)(l0 + r) * n_out + o] = s[r] + bo;
+    }
   }
 }
 
@@ -503,9 +547,9 @@ __global__ void __launch_bounds__(1024) score_linear_kernel(const float* __restr
 int score_tail_launch(const ScoreTailParams& p, cudaStream_t stream) {
   if (p.L == 0) return 0;
   FP_REQUIRE(p.L <= 4096, "score tail: L=%d too large", p.L);
-  rowwise_linear_kernel<<<p.L, 256, 0, stream>>>(p.feats, p.w_in, p.b_in, p.qkv, 1536);
+  rowwise_linear_kernel<<<dim3((p.L + kRowBlock - 1) / kRowBlock, 8), 256, 0, stream>>>(p.feats, p.w_in, p.b_in, p.qkv, p.L, 1536);
   cross_attn_kernel<<<p.L, 128, 4 * p.L * sizeof(float), stream>>>(p.qkv, p.attn, p.L, 0.08838834764831845f);
-  rowwise_linear_kernel<<<p.L, 256, 0, stream>>>(p.attn, p.w_out, p.b_out, p.proj, 512);
+  rowwise_linear_kernel<<<dim3((p.L + kRowBlock - 1) / kRowBlock, 8), 256, 0, stream>>>(p.attn, p.w_out, p.b_out, p.proj, p.L, 512);
   score_linear_kernel<<<1, 1024, 0, stream>>>(p.proj, p.w_lin, p.b_lin, p.offset, p.scores, p.best, p.L);
   g_launch_count += 4;
   FP_CUDA_OK(cudaGetLastError());

@@ -115,6 +115,7 @@ struct GemmParams {
   const float* post_add;
   int relu;
   double alg_flops;  // 2 * M * Cout * K_real of this launch (host-side bookkeeping only)
+  int dbg;           // FPOSE_GEMM_DBG timing experiments: 1 = no epilogue math/stores, 2 = no TMA store (results wrong)
 };
 
 constexpr int kBlockM = 128;
@@ -134,7 +135,8 @@ template <int BN, int CG, int SLABS>
 struct TileCfg {
   static constexpr int kBBytes = (BN / CG) * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = SLABS * kSlabBytes;
+  static constexpr int kNumSlabs = (SLABS == 2) ? 2 : 4;  // SLABS = 8: ring of 4 slabs (4 TMA stores in flight)
+  static constexpr int kStagingBytes = kNumSlabs * kSlabBytes;
   static constexpr int kRing = 196608 + 2 * kSlabBytes - kStagingBytes;
   static constexpr int kStages = (kRing / kStageBytes) > 8 ? 8 : (kRing / kStageBytes);
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
@@ -148,6 +150,8 @@ __global__ void __launch_bounds__(kTileThreads, 1)
                      const __grid_constant__ GemmParams p) {
   using Cfg = TileCfg<BN, CG, SLABS>;
   constexpr int S = Cfg::kStages;
+  constexpr int NS = Cfg::kNumSlabs;
+  constexpr bool PREFETCH = (SLABS == 4);  // whole-tile residual prefetch, one slab per 64-channel slice
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + S * Cfg::kStageBytes;  // [2][kSlabBytes], 1024-aligned
@@ -176,7 +180,7 @@ __global__ void __launch_bounds__(kTileThreads, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 256 * CG);
+      mbar_init(&tmem_empty[a], 8 * CG);
     }
     for (int a = 0; a < 4; ++a) mbar_init(&res_full[a], 1);
     tma_prefetch_desc(&map_out);
@@ -331,7 +335,7 @@ __global__ void __launch_bounds__(kTileThreads, 1)
         rc[p.odim_n] = n0;
       }
 
-      if (SLABS == 4) {
+      if (PREFETCH) {
         // one slab per 64-channel slice: fetch the whole tile's residual now, while its MMAs still run
         if (leader) {
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // last tile's stores have left the slabs
@@ -350,11 +354,14 @@ __global__ void __launch_bounds__(kTileThreads, 1)
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + grp * 32;
 #pragma unroll 1
       for (int c = 0; c < BN; c += 64, ++slab_ctr) {
-        const uint32_t buf = (SLABS == 4) ? (uint32_t)(c >> 6) : (slab_ctr & 1u);
+        const uint32_t buf = PREFETCH ? (uint32_t)(c >> 6) : (slab_ctr % (uint32_t)NS);
         uint8_t* slab = staging + buf * kSlabBytes;
-        if (SLABS == 2) {
-          // the TMA store that last used this buffer (two slabs ago) must have finished reading it
-          if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        if (!PREFETCH) {
+          // the TMA store that last used this buffer (NS slabs ago) must have finished reading it
+          if (leader) {
+            if (NS == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+          }
           asm volatile("bar.sync 1, 256;" ::: "memory");
           if (p.has_res && leader) {
             mbar_expect_tx(&res_full[buf], kSlabBytes);
@@ -367,10 +374,14 @@ __global__ void __launch_bounds__(kTileThreads, 1)
         if (c + 64 >= BN) {
           // accumulator fully read: hand the TMEM stage back to the MMA warp before the stores
           tc_fence_before();
-          if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0);
-          else mbar_arrive(&tmem_empty[acc]);
+          __syncwarp();
+          if (lane == 0) {  // one arrival per warp (a remote arrive is a DSMEM transaction)
+            if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0);
+            else mbar_arrive(&tmem_empty[acc]);
+          }
         }
-        if (p.has_res) mbar_wait(&res_full[buf], (SLABS == 4) ? (uint32_t)(it & 1) : ((slab_ctr >> 1) & 1u));
+        if (p.has_res) mbar_wait(&res_full[buf], PREFETCH ? (uint32_t)(it & 1) : ((slab_ctr / (uint32_t)NS) & 1u));
+        if (p.dbg == 1) continue;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {  // this warp's 4 chunks of 8 channels (16 B)
           const int q = grp * 4 + q4;
@@ -407,7 +418,7 @@ __global__ void __launch_bounds__(kTileThreads, 1)
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (leader) {
+        if (leader && p.dbg != 2) {
           tma_store_5d(&map_out, slab, coff + n_tile * BN + c, oc[1], oc[2], oc[3], oc[4]);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -872,6 +883,10 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
   p.post_add = L.post_add;
   p.relu = L.relu;
   {
+    const char* e = getenv("FPOSE_GEMM_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
+  {
     const double k_real = (double)taps * L.Cin;
     p.alg_flops = 2.0 * (double)L.n_img * Ho * Wo * L.Cout * k_real;
   }
@@ -949,6 +964,8 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
   if (BN == 256) {
     // residual layers: 4 staging slabs so the tile's residual is prefetched (one ring stage fewer)
     if (L.res) return CG == 2 ? launch_bn<256, 2, 4>(ma, mb, mo, mr, p, stream) : launch_bn<256, 1, 4>(ma, mb, mo, mr, p, stream);
+    // K = 512 linears are bounded by their epilogue (8 k-blocks per tile): keep 4 output stores in flight
+    if (CG == 1 && L.kind == LK_LINEAR) return launch_bn<256, 1, 8>(ma, mb, mo, mr, p, stream);
     return CG == 2 ? launch_bn<256, 2, 2>(ma, mb, mo, mr, p, stream) : launch_bn<256, 1, 2>(ma, mb, mo, mr, p, stream);
   }
   if (BN == 128) return launch_bn<128, 1, 2>(ma, mb, mo, mr, p, stream);
