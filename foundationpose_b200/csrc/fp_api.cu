@@ -56,10 +56,10 @@ constexpr int S = 160;
 constexpr int T = 400;
 constexpr size_t kCropImg = (size_t)(S + 6) * (S + 8) * 8;  // fp16 elements per padded crop image
 // The encoder's first stage runs on the A (rendered) and B (observed) crops as one batch.  The 40x40
-// layers tile two images per 128-row MMA tile, and the layer that fuses torch.cat((a, b), 1) stores A and
-// B tiles to different channel halves, so the A/B boundary must fall on a tile boundary: B starts at
-// N rounded up to 2 (one never-read pad image when N is odd).
-static inline int b_img0_of(int N) { return (N + 1) & ~1; }
+// 128-channel layers tile four images per MMA (gemm_swap_patch_kernel), and the layer that fuses
+// torch.cat((a, b), 1) stores A and B tiles to different channel halves, so the A/B boundary must fall on a tile
+// boundary: B starts at N rounded up to 4 (up to three never-read pad images).
+static inline int b_img0_of(int N) { return (N + 3) & ~3; }
 
 }  // namespace fp
 
@@ -104,7 +104,7 @@ static int ensure_capacity(fp_ctx* c, int N) {
   const size_t n = (size_t)N;
   int rc = 0;
   // the crop buffer is zeroed once: the 3-pixel border is never written afterwards
-  const size_t m = 2 * n + 1;  // A + pad + B images
+  const size_t m = 2 * n + 3;  // A + pad + B images
   rc |= dev_alloc(c->crops, m * kCropImg * 2, true);
   rc |= dev_alloc(c->act0, m * 80 * 80 * 64 * 2);
   rc |= dev_alloc(c->a1, m * 1600 * 128 * 2);

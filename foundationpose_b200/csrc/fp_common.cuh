@@ -271,6 +271,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                        // layout type: SWIZZLE_128B
   return d;
 }
+// Same layout, arbitrary start row and group stride: tcgen05 applies the 128B swizzle to absolute shared-memory
+// address bits (tools/umma_probe.cu), so `smem_addr` may be any multiple of 128 B and `sbo_bytes` any multiple of
+// 16 B; the base-offset field stays 0.
+__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16, fp16 A/B (K-major both), fp32 accumulate, M=128.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t n, uint32_t m = 128u) {
   return (1u << 4)               // c_format = F32

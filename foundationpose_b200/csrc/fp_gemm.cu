@@ -116,6 +116,18 @@ struct GemmParams {
   int relu;
   double alg_flops;  // 2 * M * Cout * K_real of this launch (host-side bookkeeping only)
   int dbg;           // FPOSE_GEMM_DBG timing experiments: 1 = no epilogue math/stores, 2 = no TMA store (results wrong)
+  // ---- patch mode (3x3 stride-1 convolutions): the A operand of every tap is a shifted VIEW of one shared-memory
+  // segment (a halo'd patch of the input tile, 128B-swizzled rows of 64 channels), fetched once per 64-channel
+  // chunk instead of once per tap.  tools/umma_probe.cu shows that tcgen05 applies the 128B swizzle to absolute
+  // shared-memory address bits, so a descriptor may start at any 128-byte row and use any group stride.
+  int seg_count, taps_per_seg;  // segments per channel chunk (1: halo'd patch, 3: one column-shifted copy per s)
+  int seg_bytes;                // bytes of one segment's TMA box
+  short seg_off[3][5];          // coordinate offsets of segment q relative to the tile origin
+  int tap_aoff[9];              // [q * taps_per_seg + t]: byte offset of the tap's first row inside the segment
+  short tap_w[9];               // [q * taps_per_seg + t]: filter tap (r * 3 + s) -> which weight k-block
+  int a_sbo;                    // bytes between consecutive 8-row groups of the A operand
+  int odim_w;                   // coordinate of the output map that receives the tile's column
+  int row_mode;                 // tile row -> pixel: 0 = (n, i, j), 1 = (i, n, j), 2 = (i, j, n)   [fastest last]
 };
 
 constexpr int kBlockM = 128;
@@ -131,7 +143,11 @@ constexpr int kSlabBytes = kBlockM * 64 * 2;  // 16 KB: one output slab (128 pix
 // SLABS = epilogue staging slabs (16 KB each).  2: slabs are recycled one by one.  4 (residual layers with
 // BN = 256): one slab per 64-channel slice of the tile, so the whole tile's residual is prefetched by TMA
 // while the tile's MMAs are still running.
-template <int BN, int CG, int SLABS>
+constexpr int kPatchSlot = 26 * 1024;  // one A segment: 10 x 10 x 2 (25,600 B) or 6 x 4 x 8 (24,576 B) rows of 128 B
+constexpr int kPatchStages = 3;
+constexpr int kSmemBudget = 232448 - 1024 - 256;  // opt-in maximum minus alignment slack and the barrier block
+
+template <int BN, int CG, int SLABS, bool PATCH = false>
 struct TileCfg {
   static constexpr int kBBytes = (BN / CG) * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -139,29 +155,37 @@ struct TileCfg {
   static constexpr int kStagingBytes = kNumSlabs * kSlabBytes;
   static constexpr int kRing = 196608 + 2 * kSlabBytes - kStagingBytes;
   static constexpr int kStages = (kRing / kStageBytes) > 8 ? 8 : (kRing / kStageBytes);
+  // patch mode: kPatchStages A segments + a ring of weight tiles
+  static constexpr int kBRing = kSmemBudget - kPatchStages * kPatchSlot - kStagingBytes;
+  static constexpr int kBStages = (kBRing / kBBytes) > 8 ? 8 : (kBRing / kBBytes);
+  static constexpr int kOperandBytes = PATCH ? (kPatchStages * kPatchSlot + kBStages * kBBytes) : (kStages * kStageBytes);
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kOperandBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int CG, int SLABS>
+template <int BN, int CG, int SLABS, bool PATCH = false>
 __global__ void __launch_bounds__(kTileThreads, 1)
     gemm_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
                      const __grid_constant__ GemmParams p) {
-  using Cfg = TileCfg<BN, CG, SLABS>;
-  constexpr int S = Cfg::kStages;
+  using Cfg = TileCfg<BN, CG, SLABS, PATCH>;
+  constexpr int S = PATCH ? Cfg::kBStages : Cfg::kStages;  // ring of (A+B) stages, or of weight tiles in patch mode
+  constexpr int SA = kPatchStages;
   constexpr int NS = Cfg::kNumSlabs;
   constexpr bool PREFETCH = (SLABS == 4);  // whole-tile residual prefetch, one slab per 64-channel slice
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* staging = smem + S * Cfg::kStageBytes;  // [2][kSlabBytes], 1024-aligned
+  uint8_t* b_ring = smem + SA * kPatchSlot;        // patch mode: [SA][kPatchSlot] segments, then [S][kBBytes] weights
+  uint8_t* staging = smem + Cfg::kOperandBytes;    // [NS][kSlabBytes], 1024-aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
   uint64_t* full = bars;                 // [S]
   uint64_t* empty = bars + S;            // [S]
   uint64_t* tmem_full = bars + 2 * S;    // [2]
   uint64_t* tmem_empty = bars + 2 * S + 2;  // [2]
   uint64_t* res_full = bars + 2 * S + 4;    // [4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 8);
+  uint64_t* a_full = bars + 2 * S + 8;      // [SA]  (patch mode)
+  uint64_t* a_empty = bars + 2 * S + 8 + SA;  // [SA]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 8 + 2 * SA);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -183,6 +207,12 @@ __global__ void __launch_bounds__(kTileThreads, 1)
       mbar_init(&tmem_empty[a], 8 * CG);
     }
     for (int a = 0; a < 4; ++a) mbar_init(&res_full[a], 1);
+    if (PATCH) {
+      for (int a = 0; a < SA; ++a) {
+        mbar_init(&a_full[a], 1);
+        mbar_init(&a_empty[a], 1);
+      }
+    }
     tma_prefetch_desc(&map_out);
     if (p.has_res) tma_prefetch_desc(&map_res);
     mbar_fence_init();
@@ -218,7 +248,55 @@ __global__ void __launch_bounds__(kTileThreads, 1)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (PATCH) {
+      if (lane == 0) {
+        int stage = 0, phase = 0, as = 0, aphase = 0;
+        const int tps = p.taps_per_seg;
+        for (int vt = vt0; vt < total_vt; vt += vt_step) {
+          int n_tile, tw, th, tn;
+          decode(vt, n_tile, tw, th, tn);
+          int base[5] = {0, 0, 0, 0, 0};
+          base[p.dim_w] += tw * p.bw;
+          base[p.dim_h] += th * p.bh;
+          base[p.dim_n] += tn * p.bn;
+          for (int cs = 0; cs < p.chunks_per_tap; ++cs) {
+            for (int q = 0; q < p.seg_count; ++q) {
+              mbar_wait(&a_empty[as], aphase ^ 1);
+              uint8_t* sa = smem + as * kPatchSlot;
+              const int c0 = cs * kBlockK, c1 = base[1] + p.seg_off[q][1], c2 = base[2] + p.seg_off[q][2],
+                        c3 = base[3] + p.seg_off[q][3], c4 = base[4] + p.seg_off[q][4];
+              if (CG == 2) {
+                if (cta_rank == 0) mbar_expect_tx(&a_full[as], 2 * p.seg_bytes);
+                tma_load_5d_2sm(&map_a, &a_full[as], sa, c0, c1, c2, c3, c4);
+              } else {
+                mbar_expect_tx(&a_full[as], p.seg_bytes);
+                tma_load_5d(&map_a, &a_full[as], sa, c0, c1, c2, c3, c4);
+              }
+              if (++as == SA) {
+                as = 0;
+                aphase ^= 1;
+              }
+              for (int t = 0; t < tps; ++t) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* sb = b_ring + stage * Cfg::kBBytes;
+                const int kcol = (p.tap_w[q * tps + t] * p.chunks_per_tap + cs) * kBlockK;
+                if (CG == 2) {
+                  if (cta_rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::kBBytes);
+                  tma_load_2d_2sm(&map_b, &full[stage], sb, kcol, n_tile * BN + cta_rank * (BN / 2));
+                } else {
+                  mbar_expect_tx(&full[stage], Cfg::kBBytes);
+                  tma_load_2d(&map_b, &full[stage], sb, kcol, n_tile * BN);
+                }
+                if (++stage == S) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+              }
+            }
+          }
+        }
+      }
+    } else if (lane == 0) {
       int stage = 0, phase = 0;
       for (int vt = vt0; vt < total_vt; vt += vt_step) {
         int n_tile, tw, th, tn;
@@ -257,7 +335,53 @@ __global__ void __launch_bounds__(kTileThreads, 1)
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && cta_rank == 0) {
+    if (PATCH) {
+      if (lane == 0 && cta_rank == 0) {
+        constexpr uint32_t idesc = umma_idesc_f16(BN, 128u * CG);
+        int stage = 0, phase = 0, as = 0, aphase = 0, it = 0;
+        const int tps = p.taps_per_seg;
+        for (int vt = vt0; vt < total_vt; vt += vt_step, ++it) {
+          const int acc = it & 1;
+          mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          uint32_t accum = 0;
+          for (int cs = 0; cs < p.chunks_per_tap; ++cs) {
+            for (int q = 0; q < p.seg_count; ++q) {
+              mbar_wait(&a_full[as], aphase);
+              const uint32_t seg = smem_u32(smem + as * kPatchSlot);
+              for (int t = 0; t < tps; ++t) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                // the tap's rows start tap_aoff bytes into the segment; 8-row groups are a_sbo bytes apart
+                const uint64_t da = umma_desc_sw128_sbo(seg + (uint32_t)p.tap_aoff[q * tps + t], (uint32_t)p.a_sbo);
+                const uint64_t db = umma_desc_sw128(smem_u32(b_ring + stage * Cfg::kBBytes));
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  if (CG == 2) umma_f16_2sm(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accum);
+                  else umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accum);
+                  accum = 1;
+                }
+                if (CG == 2) umma_commit_2sm(&empty[stage]);
+                else umma_commit(&empty[stage]);
+                if (++stage == S) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+              }
+              if (CG == 2) umma_commit_2sm(&a_empty[as]);
+              else umma_commit(&a_empty[as]);
+              if (++as == SA) {
+                as = 0;
+                aphase ^= 1;
+              }
+            }
+          }
+          if (CG == 2) umma_commit_2sm(&tmem_full[acc]);
+          else umma_commit(&tmem_full[acc]);
+        }
+      }
+    } else if (lane == 0 && cta_rank == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(BN, 128u * CG);
       int stage = 0, phase = 0;
       int it = 0;
@@ -305,8 +429,17 @@ __global__ void __launch_bounds__(kTileThreads, 1)
     const int quarter = warp & 3;       // TMEM lanes [32*quarter, +32) are the ones this warp may read
     const int grp = (warp - 2) >> 2;    // which 32-column half of every 64-channel slab this warp handles
     const int row = quarter * 32 + lane;
-    const int jj = row & (p.bw - 1);
-    const int ii = (row >> p.lg_bw) & (p.bh - 1);
+    int jj, ii;  // tile row -> pixel inside the tile (only the positional-embedding table needs it)
+    if (p.row_mode == 1) {  // (i, n, j)
+      jj = row & (p.bw - 1);
+      ii = row / (p.bw * p.bn);
+    } else if (p.row_mode == 2) {  // (i, j, n)
+      jj = (row / p.bn) & (p.bw - 1);
+      ii = row / (p.bn * p.bw);
+    } else {  // (n, i, j)
+      jj = row & (p.bw - 1);
+      ii = (row >> p.lg_bw) & (p.bh - 1);
+    }
     const bool leader = (warp == 2 && lane == 0);
     const uint32_t row_off = (uint32_t)row * 128u;
     const uint32_t sw = (uint32_t)(row & 7);
@@ -328,7 +461,7 @@ __global__ void __launch_bounds__(kTileThreads, 1)
       const float* bp = p.bias + n_tile * BN;
       // output / residual box coordinates (dim 0 = channel is added per slab)
       int oc[5] = {0, 0, 0, 0, 0}, rc[5] = {0, 0, 0, 0, 0};
-      oc[1] = rc[1] = tw * p.bw;
+      oc[p.odim_w] = rc[p.odim_w] = tw * p.bw;
       if (p.odim_h >= 0) oc[p.odim_h] = rc[p.odim_h] = th * p.bh;
       if (p.odim_n >= 0) {
         oc[p.odim_n] = n_o0;
@@ -661,6 +794,221 @@ __global__ void __launch_bounds__(kTileThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Patch variant of the swapped kernel (3x3 stride-1, 128 output channels, 8 | H, W).  The N side is ONE tile of
+// 4 images x 8 x 8 pixels whose input lives in shared memory as a halo'd patch [10 h][4 n][10 w] of 128-byte
+// rows (64 channels, 128B swizzle), fetched once per 64-channel chunk; the B descriptor of filter tap (r, s)
+// starts (r * 40 + s) rows into the patch and steps 10 rows per 8-pixel group.  Shared-memory fill per k-block
+// drops from 48 KB (W + 2 pixel tiles) to 16 KB + 51.2 KB / 9 — the 128 B/cycle shared-memory port, not the
+// tensor pipe, is what bounds these layers.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSwapPatchBytes = 10 * 4 * 10 * 128;  // 51,200 B
+constexpr int kSwapPatchStages = 2;
+constexpr int kSwapWStages = 3;
+constexpr int kSwapPatchSmem = kSwapPatchStages * kSwapPatchBytes + kSwapWStages * kABytes + kSwapStaging + 1024 + 256;
+
+__global__ void __launch_bounds__(kTileThreads, 1)
+    gemm_swap_patch_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                           const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
+                           const __grid_constant__ GemmParams p) {
+  constexpr int SX = kSwapPatchStages, SW = kSwapWStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w_ring = smem + SX * kSwapPatchBytes;
+  uint8_t* staging = w_ring + SW * kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kSwapStaging);
+  uint64_t* x_full = bars;                  // [SX]
+  uint64_t* x_empty = bars + SX;            // [SX]
+  uint64_t* w_full = bars + 2 * SX;         // [SW]
+  uint64_t* w_empty = bars + 2 * SX + SW;   // [SW]
+  uint64_t* tmem_full = bars + 2 * SX + 2 * SW;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* res_full = tmem_full + 4;  // [2]: one per epilogue warpgroup
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 6);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int c_tiles = p.Cout / 128;
+  const int total_vt = m_tiles * c_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_w);
+    tma_prefetch_desc(&map_out);
+    if (p.has_res) tma_prefetch_desc(&map_res);
+    for (int s = 0; s < SX; ++s) {
+      mbar_init(&x_full[s], 1);
+      mbar_init(&x_empty[s], 1);
+    }
+    for (int s = 0; s < SW; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 256);
+      mbar_init(&res_full[a], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
+
+  auto decode = [&](int vt, int& c_tile, int& tw, int& th, int& tn) {
+    c_tile = vt % c_tiles;
+    const int m_tile = vt / c_tiles;
+    tw = m_tile % p.tiles_w;
+    th = (m_tile / p.tiles_w) % p.tiles_h;
+    tn = m_tile / (p.tiles_w * p.tiles_h);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int ws = 0, wph = 0, xs = 0, xph = 0;
+      for (int vt = blockIdx.x; vt < total_vt; vt += gridDim.x) {
+        int c_tile, tw, th, tn;
+        decode(vt, c_tile, tw, th, tn);
+        for (int cs = 0; cs < p.chunks_per_tap; ++cs) {
+          mbar_wait(&x_empty[xs], xph ^ 1);
+          mbar_expect_tx(&x_full[xs], kSwapPatchBytes);
+          // box (64 ch, 10 w, 4 n, 10 h): halo rows / columns outside the image are zero-filled (= padding)
+          tma_load_5d(&map_a, &x_full[xs], smem + xs * kSwapPatchBytes, cs * kBlockK, tw * 8 - 1, tn * 4, th * 8 - 1, 0);
+          if (++xs == SX) {
+            xs = 0;
+            xph ^= 1;
+          }
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&w_empty[ws], wph ^ 1);
+            mbar_expect_tx(&w_full[ws], kABytes);
+            tma_load_2d(&map_w, &w_full[ws], w_ring + ws * kABytes, (tap * p.chunks_per_tap + cs) * kBlockK, c_tile * 128);
+            if (++ws == SW) {
+              ws = 0;
+              wph ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(256, 128);
+      int ws = 0, wph = 0, xs = 0, xph = 0, it = 0;
+      for (int vt = blockIdx.x; vt < total_vt; vt += gridDim.x, ++it) {
+        const int acc = it & 1, acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        uint32_t accum = 0;
+        for (int cs = 0; cs < p.chunks_per_tap; ++cs) {
+          mbar_wait(&x_full[xs], xph);
+          const uint32_t patch = smem_u32(smem + xs * kSwapPatchBytes);
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&w_full[ws], wph);
+            tc_fence_after();
+            const int r = tap / 3, sft = tap - 3 * r;
+            const uint64_t da = umma_desc_sw128(smem_u32(w_ring + ws * kABytes));                     // M = 128 channels
+            const uint64_t db = umma_desc_sw128_sbo(patch + (uint32_t)((r * 40 + sft) * 128), 1280u);  // N = 256 pixels
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accum);
+              accum = 1;
+            }
+            umma_commit(&w_empty[ws]);
+            if (++ws == SW) {
+              ws = 0;
+              wph ^= 1;
+            }
+          }
+          umma_commit(&x_empty[xs]);
+          if (++xs == SX) {
+            xs = 0;
+            xph ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // two independent epilogue warpgroups: group t owns pixel columns [128 t, 128 t + 128) of the accumulator =
+    // rows [4 t, 4 t + 4) of the 8 x 8 tile for all 4 images, i.e. one (64 ch, 8 w, 4 n, 4 h) box per channel half
+    const int quarter = warp & 3;
+    const int t = (warp - 2) >> 2;
+    const int half = quarter >> 1;
+    const int c_local = (quarter & 1) * 32 + lane;
+    const bool leader = (((warp - 2) & 3) == 0 && lane == 0);
+    const uint32_t c_chunk = (uint32_t)(c_local >> 3), c_byte = (uint32_t)(c_local & 7) * 2u;
+    uint8_t* my_staging = staging + t * 2 * kSlabBytes;
+    uint8_t* slab = my_staging + half * kSlabBytes;
+    int it = 0;
+    for (int vt = blockIdx.x; vt < total_vt; vt += gridDim.x, ++it) {
+      const int acc = it & 1, acc_phase = (it >> 1) & 1;
+      int c_tile, tw, th, tn;
+      decode(vt, c_tile, tw, th, tn);
+      const float bias = __ldg(p.bias + c_tile * 128 + quarter * 32 + lane);
+      const int n0 = tn * 4;
+      int n_o0 = n0, coff = 0;
+      if (p.out_split > 0) {
+        n_o0 = n0 % p.out_split;
+        coff = (n0 / p.out_split) * p.Cout;
+      }
+      const int ow = tw * 8, oh = th * 8 + 4 * t;  // map dims: (c, w, n, h)
+      if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (t == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (p.has_res && leader) {
+        mbar_expect_tx(&res_full[t], 2 * kSlabBytes);
+        for (int hh = 0; hh < 2; ++hh)
+          tma_load_5d(&map_res, &res_full[t], my_staging + hh * kSlabBytes, c_tile * 128 + hh * 64, ow, n0, oh, 0);
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      if (p.has_res) mbar_wait(&res_full[t], it & 1);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256 + t * 128;
+#pragma unroll 1
+      for (int c = 0; c < 128; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c, v);
+        tmem_ld_wait();
+        if (c == 96) {
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[acc]);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const uint32_t px = (uint32_t)(c + i);
+          __half* cell = reinterpret_cast<__half*>(slab + px * 128u + ((c_chunk ^ (px & 7u)) << 4) + c_byte);
+          float a = __uint_as_float(v[i]) + bias;
+          if (p.has_res) a += __half2float(*cell);
+          if (p.relu) a = fmaxf(a, 0.f);
+          *cell = __float2half_rn(a);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (t == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (leader) {
+        for (int hh = 0; hh < 2; ++hh)
+          tma_store_5d(&map_out, my_staging + hh * kSlabBytes, coff + c_tile * 128 + hh * 64, ow, n_o0, oh, 0);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 static int g_num_sms = 0;
@@ -734,13 +1082,13 @@ static int ilog2(int v) {
 
 static int g_cta_group = -1;  // FPOSE_CTA_GROUP=1 falls back to single-CTA MMAs (A/B checks)
 
-template <int BN, int CG, int SLABS>
+template <int BN, int CG, int SLABS, bool PATCH = false>
 static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mr,
                      const GemmParams& p, cudaStream_t stream) {
-  using Cfg = TileCfg<BN, CG, SLABS>;
+  using Cfg = TileCfg<BN, CG, SLABS, PATCH>;
   static bool attr_set = false;
   if (!attr_set) {
-    FP_CUDA_OK(cudaFuncSetAttribute(gemm_tile_kernel<BN, CG, SLABS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FP_CUDA_OK(cudaFuncSetAttribute(gemm_tile_kernel<BN, CG, SLABS, PATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -754,15 +1102,14 @@ static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtenso
   const int slots = g_num_sms / CG;
   const int grid = CG * (total_vt < slots ? total_vt : slots);
   prof_mark_begin(0, p.alg_flops, stream);
-  FP_CUDA_OK(launch_pdl(gemm_tile_kernel<BN, CG, SLABS>, dim3(grid), dim3(kTileThreads), Cfg::kSmemBytes, stream, CG, ma, mb, mo, mr,
-                        p));
+  FP_CUDA_OK(launch_pdl(gemm_tile_kernel<BN, CG, SLABS, PATCH>, dim3(grid), dim3(kTileThreads), Cfg::kSmemBytes, stream, CG, ma, mb,
+                        mo, mr, p));
   prof_mark_end(stream);
   ++g_launch_count;
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-static int g_swap_ab = -1;  // FPOSE_SWAP_AB=0 disables the swapped 128-channel kernel (A/B checks)
 
 static int launch_swap(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mo, const CUtensorMap& mr,
                        const GemmParams& p, cudaStream_t stream) {
@@ -787,12 +1134,41 @@ static int launch_swap(const CUtensorMap& ma, const CUtensorMap& mw, const CUten
   return 0;
 }
 
+static int launch_swap_patch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mo, const CUtensorMap& mr,
+                             const GemmParams& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    FP_CUDA_OK(cudaFuncSetAttribute(gemm_swap_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSwapPatchSmem));
+    attr_set = true;
+  }
+  const int sms = num_sms();
+  FP_REQUIRE(sms > 0, "no CUDA device");
+  const int total_vt = p.tiles_w * p.tiles_h * p.tiles_n * (p.Cout / 128);
+  const int grid = total_vt < sms ? total_vt : sms;
+  prof_mark_begin(0, p.alg_flops, stream);
+  FP_CUDA_OK(launch_pdl(gemm_swap_patch_kernel, dim3(grid), dim3(kTileThreads), kSwapPatchSmem, stream, 1, ma, mw, mo, mr, p));
+  prof_mark_end(stream);
+  ++g_launch_count;
+  FP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int stem_conv_launch(const GemmLayer& L, cudaStream_t stream);  // fp_stem.cu
+
+static int g_swap_ab = -1;  // FPOSE_SWAP_AB=0 disables the swapped 128-channel kernels (A/B checks)
+static int g_patch = -1;    // FPOSE_PATCH=0 falls back to one TMA box per filter tap (A/B checks)
 
 int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
   if (L.kind == LK_CONV7_S2) return stem_conv_launch(L, stream);
   GemmParams p;
   memset(&p, 0, sizeof(p));
+  p.odim_w = 1;
+  bool patch = false, swap_patch = false;
+  int out_bh = 0;  // rows of the output / residual box (0: the tile's bh)
+  if (g_swap_ab < 0) {
+    const char* e = getenv("FPOSE_SWAP_AB");
+    g_swap_ab = (e && e[0] == '0') ? 0 : 1;
+  }
   CUtensorMap ma, mb;
   const uint64_t E = 2;  // bytes per fp16
   int Ho, Wo, taps, ktot;
@@ -823,15 +1199,72 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
       if (Wo % 8 == 0 && Ho % 8 == 0) { p.bw = 8; p.bh = 8; p.bn = 2; }
       else if (Wo % 4 == 0 && Ho % 4 == 0) { p.bw = 4; p.bh = 4; p.bn = 8; }
       else FP_REQUIRE(false, "CONV3_S1: unsupported spatial size %dx%d", Ho, Wo);
-      p.dim_w = 1; p.dim_h = 2; p.dim_n = 3;
-      dims[0] = L.Cin; dims[1] = L.Win; dims[2] = L.Hin; dims[3] = L.n_img; dims[4] = 1;
-      str[0] = L.Cin * E; str[1] = str[0] * L.Win; str[2] = str[1] * L.Hin; str[3] = str[2] * L.n_img;
-      box[0] = 64; box[1] = p.bw; box[2] = p.bh; box[3] = p.bn; box[4] = 1;
-      for (int r = 0; r < 3; ++r)
-        for (int s = 0; s < 3; ++s) {
-          p.tap_off[r * 3 + s][1] = (short)(s - 1);
-          p.tap_off[r * 3 + s][2] = (short)(r - 1);
+      if (g_patch < 0) {
+        const char* e = getenv("FPOSE_PATCH");
+        g_patch = e ? atoi(e) : 1;
+      }
+      // measured (profiles/r01e_gemm_probe_patch.log): +6 % on the 40 x 40 / 256-channel layers; the 20 x 20 layers
+      // (three column-shifted copies, FPOSE_PATCH=2) are 2 % slower than the per-tap boxes and stay on those
+      patch = g_patch && L.Cout % 256 == 0 && (p.bw == 8 || g_patch == 2);
+      swap_patch = g_patch && g_swap_ab && L.Cout == 128 && p.bw == 8 && !L.post_add && L.out_split % 4 == 0;
+      const uint64_t sw_ = (uint64_t)L.Cin * E, sh_ = sw_ * L.Win, sn_ = sh_ * L.Hin;
+      if (swap_patch) {
+        // gemm_swap_patch_kernel: the N side is 4 images x 8 x 8 pixels out of one (64 ch, 10 w, 4 n, 10 h) patch
+        p.bn = 4;
+        p.dim_w = 1; p.dim_n = 2; p.dim_h = 3;
+        dims[0] = L.Cin; dims[1] = L.Win; dims[2] = L.n_img; dims[3] = L.Hin; dims[4] = 1;
+        str[0] = sw_; str[1] = sn_; str[2] = sh_; str[3] = sn_ * L.n_img;
+        box[0] = 64; box[1] = 10; box[2] = 4; box[3] = 10; box[4] = 1;
+        p.row_mode = 1;
+        out_bh = 4;  // each epilogue warpgroup stores half of the tile's rows
+      } else if (patch && p.bw == 8) {
+        // one halo'd patch per 64-channel chunk: box (64 ch, 10 w, bn images, 10 h), rows ordered (h, n, w); tap
+        // (r, s) starts (r * bn * 10 + s) rows into it and its 8-pixel row groups are 10 rows apart
+        p.dim_w = 1; p.dim_n = 2; p.dim_h = 3;
+        dims[0] = L.Cin; dims[1] = L.Win; dims[2] = L.n_img; dims[3] = L.Hin; dims[4] = 1;
+        str[0] = sw_; str[1] = sn_; str[2] = sh_; str[3] = sn_ * L.n_img;
+        box[0] = 64; box[1] = 10; box[2] = p.bn; box[3] = 10; box[4] = 1;
+        p.seg_count = 1; p.taps_per_seg = 9;
+        p.seg_bytes = 10 * p.bn * 10 * 128;
+        p.seg_off[0][1] = -1; p.seg_off[0][3] = -1;
+        for (int r = 0; r < 3; ++r)
+          for (int s = 0; s < 3; ++s) {
+            p.tap_aoff[r * 3 + s] = (r * p.bn * 10 + s) * 128;
+            p.tap_w[r * 3 + s] = (short)(r * 3 + s);
+          }
+        p.a_sbo = 10 * 128;
+        p.row_mode = 1;
+      } else if (patch) {
+        // 20 x 20 maps (tile = 4 x 4 pixels x 8 images): 8 consecutive rows are the 8 images of one pixel, so a
+        // halo in w would break the constant group stride; instead one column-shifted copy per filter column s:
+        // box (64 ch, 8 images, 4 w, 6 h), rows ordered (h, w, n); tap (r, s) = copy s, r * 32 rows in
+        p.dim_n = 1; p.dim_w = 2; p.dim_h = 3;
+        dims[0] = L.Cin; dims[1] = L.n_img; dims[2] = L.Win; dims[3] = L.Hin; dims[4] = 1;
+        str[0] = sn_; str[1] = sw_; str[2] = sh_; str[3] = sn_ * L.n_img;
+        box[0] = 64; box[1] = 8; box[2] = 4; box[3] = 6; box[4] = 1;
+        p.seg_count = 3; p.taps_per_seg = 3;
+        p.seg_bytes = 8 * 4 * 6 * 128;
+        for (int sft = 0; sft < 3; ++sft) {
+          p.seg_off[sft][2] = (short)(sft - 1);
+          p.seg_off[sft][3] = -1;
+          for (int r = 0; r < 3; ++r) {
+            p.tap_aoff[sft * 3 + r] = r * 4 * 8 * 128;
+            p.tap_w[sft * 3 + r] = (short)(r * 3 + sft);
+          }
         }
+        p.a_sbo = 1024;
+        p.row_mode = 2;
+      } else {
+        p.dim_w = 1; p.dim_h = 2; p.dim_n = 3;
+        dims[0] = L.Cin; dims[1] = L.Win; dims[2] = L.Hin; dims[3] = L.n_img; dims[4] = 1;
+        str[0] = sw_; str[1] = sh_; str[2] = sn_; str[3] = sn_ * L.n_img;
+        box[0] = 64; box[1] = p.bw; box[2] = p.bh; box[3] = p.bn; box[4] = 1;
+        for (int r = 0; r < 3; ++r)
+          for (int s = 0; s < 3; ++s) {
+            p.tap_off[r * 3 + s][1] = (short)(s - 1);
+            p.tap_off[r * 3 + s][2] = (short)(r - 1);
+          }
+      }
       p.tiles_w = Wo / p.bw; p.tiles_h = Ho / p.bh; p.tiles_n = (L.n_img + p.bn - 1) / p.bn;
       break;
     }
@@ -907,10 +1340,6 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
   // Measured on B200 (profiles/r01_gemm_probe_cta_pair.log): the CTA-pair MMA (cta_group::2, each CTA stages half
   // of the weight tile) is 8-10 % faster on the 256-wide, deep-K convolutions (up to 1.52 PFLOP/s) and slower on
   // the narrow / shallow-K layers, whose bound is the shared-memory port, not the TMA fill.
-  if (g_swap_ab < 0) {
-    const char* e = getenv("FPOSE_SWAP_AB");
-    g_swap_ab = (e && e[0] == '0') ? 0 : 1;
-  }
   const bool swap_ab = g_swap_ab && BN == 128 && L.Cout == 128 && !L.post_add &&
                        (L.kind == LK_CONV3_S1 || L.kind == LK_CONV3_S2);
   static int cg2_min_kb = -1;
@@ -931,23 +1360,34 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
     const int n_out = L.out_split > 0 ? (L.n_img - L.out_split) : L.n_img;
     FP_REQUIRE(n_out > 0, "out_split=%d leaves no output images (n_img=%d)", L.out_split, L.n_img);
     auto fill = [&](int ld, int nimg) {
+      const uint64_t sw_ = (uint64_t)ld * E, sh_ = sw_ * Wo, sn_ = sh_ * Ho;
       od[0] = (uint64_t)ld;
-      od[1] = (uint64_t)Wo;
-      od[2] = lin ? 1 : (uint64_t)Ho;
-      od[3] = lin ? 1 : (uint64_t)nimg;
-      od[4] = 1;
-      os[0] = (uint64_t)ld * E;
-      os[1] = os[0] * Wo;
-      os[2] = lin ? os[1] : os[1] * Ho;
-      os[3] = lin ? os[1] : os[2] * nimg;
       ob[0] = 64;
-      ob[1] = (uint32_t)p.bw;
-      ob[2] = lin ? 1 : (uint32_t)p.bh;
-      ob[3] = lin ? 1 : (uint32_t)p.bn;
+      od[4] = 1;
       ob[4] = 1;
+      if (lin) {
+        od[1] = (uint64_t)Wo; od[2] = 1; od[3] = 1;
+        os[0] = sw_; os[1] = sh_; os[2] = sh_; os[3] = sh_;
+        ob[1] = (uint32_t)p.bw; ob[2] = 1; ob[3] = 1;
+      } else if (p.row_mode == 1) {  // tile rows ordered (h, n, w)
+        od[1] = (uint64_t)Wo; od[2] = (uint64_t)nimg; od[3] = (uint64_t)Ho;
+        os[0] = sw_; os[1] = sn_; os[2] = sh_; os[3] = sn_ * nimg;
+        ob[1] = (uint32_t)p.bw; ob[2] = (uint32_t)p.bn; ob[3] = (uint32_t)(out_bh ? out_bh : p.bh);
+      } else if (p.row_mode == 2) {  // tile rows ordered (h, w, n)
+        od[1] = (uint64_t)nimg; od[2] = (uint64_t)Wo; od[3] = (uint64_t)Ho;
+        os[0] = sn_; os[1] = sw_; os[2] = sh_; os[3] = sn_ * nimg;
+        ob[1] = (uint32_t)p.bn; ob[2] = (uint32_t)p.bw; ob[3] = (uint32_t)p.bh;
+      } else {  // (n, h, w)
+        od[1] = (uint64_t)Wo; od[2] = (uint64_t)Ho; od[3] = (uint64_t)nimg;
+        os[0] = sw_; os[1] = sh_; os[2] = sn_; os[3] = sn_ * nimg;
+        ob[1] = (uint32_t)p.bw; ob[2] = (uint32_t)p.bh; ob[3] = (uint32_t)p.bn;
+      }
     };
+    p.odim_w = 1;
     p.odim_h = lin ? -1 : 2;
     p.odim_n = lin ? -1 : 3;
+    if (p.row_mode == 1) { p.odim_n = 2; p.odim_h = 3; }
+    if (p.row_mode == 2) { p.odim_n = 1; p.odim_w = 2; p.odim_h = 3; }
     fill(L.out_ld, n_out);
     rc = encode_map(&mo, L.out, 5, od, os, ob);
     if (rc) return rc;
@@ -960,7 +1400,13 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
     }
   }
 
+  if (swap_patch) return launch_swap_patch(ma, mb, mo, mr, p, stream);
   if (swap_ab) return launch_swap(ma, mb, mo, mr, p, stream);
+  if (patch) {
+    FP_REQUIRE(BN == 256, "patch mode is built for the 256-wide tile only");
+    if (L.res) return CG == 2 ? launch_bn<256, 2, 4, true>(ma, mb, mo, mr, p, stream) : launch_bn<256, 1, 4, true>(ma, mb, mo, mr, p, stream);
+    return CG == 2 ? launch_bn<256, 2, 2, true>(ma, mb, mo, mr, p, stream) : launch_bn<256, 1, 2, true>(ma, mb, mo, mr, p, stream);
+  }
   if (BN == 256) {
     // residual layers: 4 staging slabs so the tile's residual is prefetched (one ring stage fewer)
     if (L.res) return CG == 2 ? launch_bn<256, 2, 4>(ma, mb, mo, mr, p, stream) : launch_bn<256, 1, 4>(ma, mb, mo, mr, p, stream);
