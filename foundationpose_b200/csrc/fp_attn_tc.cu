@@ -1,15 +1,16 @@
 // fp_attn_tc.cu — softmax(Q K^T / sqrt(128)) V on the 5th-generation tensor cores (tcgen05).
 //
 // Replaces the SDPA inside nn.MultiheadAttention (refine_network.py:56-70 `trans_head` / `rot_head`,
-// score_network.py:53 `att`) for T = 400 tokens and 4 heads of 128.  One CTA per (sequence, head[, group]):
+// score_network.py:53 `att`) for T = 400 tokens and 4 heads of 128.  Persistent CTAs walk the (sequence, head[, group])
+// items; per item:
 //
 //   smem   K of the head, resident: 2 slabs [400 keys][64 dims] (K-major, 128B swizzle)      100 KB
 //          Q tile, 128 query rows:  2 slabs [128][64]                                          32 KB
 //          V ring, 3 x 80 keys:     2 slabs [80 keys][64 dims] each (MN-major B operand)       60 KB
 //          O staging for the TMA store: 2 slabs [128][64]                                      32 KB
-//   TMEM   S = Q K^T  fp32, columns [0, 400)        (two MMAs: N = 208 + 192, K = 128)
+//   TMEM   S = Q K^T  fp32, columns [0, 400)        (three key ranges: N = 208 + 176 + 16, K = 128)
 //          P = softmax numerators, fp16 pairs, columns [0, 200)   (overwrites S in place)
-//          O = P V    fp32, columns [256, 384)      (A operand = P read straight from TMEM)
+//          O = P V    fp32, columns [384, 512)      (A operand = P read straight from TMEM)
 //   warps  0 = TMA producer, 1 = MMA issuer (one thread), 2..5 = softmax + epilogue (thread = query row:
 //          the row maximum / sum need no cross-thread reduction)
 //
@@ -23,6 +24,7 @@ namespace fp {
 
 int encode_map_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box);
+int num_sms();
 
 namespace {
 
@@ -40,7 +42,7 @@ constexpr int kOffO = kOffV + kVStages * 2 * kVSlab;   // 196608
 constexpr int kOffBar = kOffO + 2 * kQSlab;            // 229376
 constexpr int kSmem = kOffBar + 256 + 1024;
 constexpr int kTmemCols = 512;
-constexpr uint32_t kColO = 256;
+constexpr uint32_t kColO = 384;
 constexpr int kThreadsTc = 192;
 
 // instruction descriptors (cute::UMMA::InstrDescriptor): fp16 x fp16 -> fp32, M = 128
@@ -112,12 +114,30 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
                : "memory");
 }
 
+// two softmax numerators: p = exp2(s * c - m * c) in fp32 (MUFU.EX2; an ex2.approx.f16x2 variant was measured: the
+// SASS is two scalar MUFU.EX2.F16, no gain), packed to the fp16 pair that the PV MMA reads from TMEM
+__device__ __forceinline__ uint32_t exp2_pair(uint32_t s0, uint32_t s1, float c, float mc, float& l) {
+  const float p0 = exp2f(fmaf(__uint_as_float(s0), c, -mc));
+  const float p1 = exp2f(fmaf(__uint_as_float(s1), c, -mc));
+  l += p0 + p1;
+  return pack_half2(p0, p1);
+}
+
 struct TcParams {
-  int q_col, k_col, v_col;  // column of head 0 inside a qkv row (group offset added per CTA)
+  int q_col, k_col, v_col;  // column of head 0 inside a qkv row (group offset added per work item)
   int group_col_stride;
   float scale_log2e;        // softmax scale * log2(e)
+  int B, H, G;              // work items: (sequence, head, group)
 };
 
+// Persistent: one CTA per SM walks the (sequence, head, group) items.  Per 128-row query tile
+//   MMA warp    S_a = Q K[0,208)^T | S_b = Q K[208,384)^T | (after the previous tile's O left TMEM) S_c = Q K[384,400)^T
+//               ... P ready ...  O = P V  (5 V chunks)
+//   softmax     max over S_a while S_b is still being computed, max over S_b, S_c; exp pass (P over S in place);
+//               ... O ready ...  O -> registers -> smem -> TMA store
+// O lives in TMEM columns [384, 512): the next tile's S_a / S_b (columns [0, 384)) are issued right behind the PV
+// MMAs, so they run while the softmax warps are still draining O; only the 16-key tail S_c waits for that.
+// K of the next item is fetched as soon as the last S MMA of the current item has retired.
 __global__ void __launch_bounds__(kThreadsTc, 1)
     attn_tc_kernel(const __grid_constant__ CUtensorMap map_qk,  // (cols, T, B), box (64, 200, 1): K halves
                    const __grid_constant__ CUtensorMap map_q,   // (cols, T, B), box (64, 128, 1)
@@ -128,19 +148,21 @@ __global__ void __launch_bounds__(kThreadsTc, 1)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* k_full = bars + 0;
-  uint64_t* q_full = bars + 1;
-  uint64_t* q_empty = bars + 2;
-  uint64_t* s_full = bars + 3;
-  uint64_t* p_ready = bars + 4;
-  uint64_t* o_full = bars + 5;
-  uint64_t* s_free = bars + 6;
-  uint64_t* v_full = bars + 7;               // [3]
-  uint64_t* v_empty = bars + 7 + kVStages;   // [3]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7 + 2 * kVStages);
+  uint64_t* k_empty = bars + 1;
+  uint64_t* q_full = bars + 2;
+  uint64_t* q_empty = bars + 3;
+  uint64_t* sa_full = bars + 4;
+  uint64_t* sb_full = bars + 5;
+  uint64_t* sc_full = bars + 6;
+  uint64_t* p_ready = bars + 7;
+  uint64_t* o_full = bars + 8;
+  uint64_t* s_free = bars + 9;
+  uint64_t* v_full = bars + 10;               // [3]
+  uint64_t* v_empty = bars + 10 + kVStages;   // [3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * kVStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x, h = blockIdx.y, g = blockIdx.z;
-  const int gcol = g * p.group_col_stride + h * DH;
+  const int total = p.B * p.H * p.G;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_qk);
@@ -148,9 +170,12 @@ __global__ void __launch_bounds__(kThreadsTc, 1)
     tma_prefetch_desc(&map_v);
     tma_prefetch_desc(&map_o);
     mbar_init(k_full, 1);
+    mbar_init(k_empty, 1);
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
-    mbar_init(s_full, 1);
+    mbar_init(sa_full, 1);
+    mbar_init(sb_full, 1);
+    mbar_init(sc_full, 1);
     mbar_init(p_ready, 128);
     mbar_init(o_full, 1);
     mbar_init(s_free, 128);
@@ -168,71 +193,96 @@ __global__ void __launch_bounds__(kThreadsTc, 1)
   pdl_trigger();
   pdl_wait();
 
+  auto item = [&](int w, int& b, int& h, int& g, int& gcol) {
+    b = w % p.B;
+    h = (w / p.B) % p.H;
+    g = w / (p.B * p.H);
+    gcol = g * p.group_col_stride + h * DH;
+  };
+
   if (warp == 0) {
     if (lane == 0) {
-      // K of this (sequence, head): 2 dim-slabs x 2 row halves
-      mbar_expect_tx(k_full, 2 * kKSlab);
-      for (int s = 0; s < 2; ++s)
-        for (int half = 0; half < 2; ++half)
-          tma_load_3d(&map_qk, k_full, smem + kOffK + s * kKSlab + half * 200 * 128, gcol + p.k_col + s * 64, half * 200, b);
-      int vs = 0, vph = 0;
-      for (int qt = 0; qt < 4; ++qt) {
-        mbar_wait(q_empty, (qt & 1) ^ 1);
-        mbar_expect_tx(q_full, 2 * kQSlab);
+      int vs = 0, vph = 0, it = 0, tc = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        int b, h, g, gcol;
+        item(w, b, h, g, gcol);
+        // K of this (sequence, head): 2 dim-slabs x 2 row halves; the buffer is free once the previous item's last
+        // S MMA has retired
+        mbar_wait(k_empty, (it & 1) ^ 1);
+        mbar_expect_tx(k_full, 2 * kKSlab);
         for (int s = 0; s < 2; ++s)
-          tma_load_3d(&map_q, q_full, smem + kOffQ + s * kQSlab, gcol + p.q_col + s * 64, qt * 128, b);
-        for (int c = 0; c < T / kVKeys; ++c) {
-          mbar_wait(&v_empty[vs], vph ^ 1);
-          mbar_expect_tx(&v_full[vs], 2 * kVSlab);
+          for (int half = 0; half < 2; ++half)
+            tma_load_3d(&map_qk, k_full, smem + kOffK + s * kKSlab + half * 200 * 128, gcol + p.k_col + s * 64, half * 200, b);
+        for (int qt = 0; qt < 4; ++qt, ++tc) {
+          mbar_wait(q_empty, (tc & 1) ^ 1);
+          mbar_expect_tx(q_full, 2 * kQSlab);
           for (int s = 0; s < 2; ++s)
-            tma_load_3d(&map_v, &v_full[vs], smem + kOffV + (vs * 2 + s) * kVSlab, gcol + p.v_col + s * 64, c * kVKeys, b);
-          if (++vs == kVStages) {
-            vs = 0;
-            vph ^= 1;
+            tma_load_3d(&map_q, q_full, smem + kOffQ + s * kQSlab, gcol + p.q_col + s * 64, qt * 128, b);
+          for (int c = 0; c < T / kVKeys; ++c) {
+            mbar_wait(&v_empty[vs], vph ^ 1);
+            mbar_expect_tx(&v_full[vs], 2 * kVSlab);
+            for (int s = 0; s < 2; ++s)
+              tma_load_3d(&map_v, &v_full[vs], smem + kOffV + (vs * 2 + s) * kVSlab, gcol + p.v_col + s * 64, c * kVKeys, b);
+            if (++vs == kVStages) {
+              vs = 0;
+              vph ^= 1;
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t id_s0 = idesc(208, 0), id_s1 = idesc(192, 0), id_pv = idesc(128, 1);
-      mbar_wait(k_full, 0);
-      int vs = 0, vph = 0;
-      for (int qt = 0; qt < 4; ++qt) {
-        mbar_wait(q_full, qt & 1);
-        mbar_wait(s_free, (qt & 1) ^ 1);  // previous tile's O has been read out of TMEM
-        tc_fence_after();
-        // S = Q K^T : keys [0,208) and [208,400), K = 128 = 2 slabs x 4 k-steps
-        for (int half = 0; half < 2; ++half) {
-          const uint32_t d_tmem = tmem + (half ? 208u : 0u);
-          for (int ks = 0; ks < 8; ++ks) {
-            const int s = ks >> 2, k = ks & 3;
-            const uint64_t da = umma_desc_sw128(smem_u32(smem + kOffQ + s * kQSlab)) + (uint64_t)(2 * k);
-            const uint64_t db = umma_desc_sw128(smem_u32(smem + kOffK + s * kKSlab + (half ? 208 * 128 : 0))) + (uint64_t)(2 * k);
-            umma_f16(d_tmem, da, db, half ? id_s1 : id_s0, ks > 0 ? 1u : 0u);
-          }
-        }
-        umma_commit(q_empty);  // Q tile consumed
-        umma_commit(s_full);
-        // O = P V, P (fp16) read from TMEM columns [0,200), V chunks of 80 keys from the ring
-        mbar_wait(p_ready, qt & 1);
-        tc_fence_after();
-        for (int c = 0; c < T / kVKeys; ++c) {
-          mbar_wait(&v_full[vs], vph);
+      constexpr uint32_t id_sa = idesc(208, 0), id_sb = idesc(176, 0), id_sc = idesc(16, 0), id_pv = idesc(128, 1);
+      int vs = 0, vph = 0, it = 0, tc = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        mbar_wait(k_full, it & 1);
+        for (int qt = 0; qt < 4; ++qt, ++tc) {
+          mbar_wait(q_full, tc & 1);
+          // P of the previous tile (TMEM columns [0, 200)) is the A operand of its PV MMAs: let them retire before
+          // S_a overwrites those columns
+          if (tc > 0) mbar_wait(o_full, (tc - 1) & 1);
           tc_fence_after();
-          const uint32_t vbase = smem_u32(smem + kOffV + vs * 2 * kVSlab);
-          for (int k = 0; k < kVKeys / 16; ++k) {
-            const uint64_t db = umma_desc_mn_sw128(vbase + k * 16 * 128, kVSlab);
-            const uint32_t a_tmem = tmem + (uint32_t)((c * kVKeys + k * 16) >> 1);
-            umma_f16_ts(tmem + kColO, a_tmem, db, id_pv, (c > 0 || k > 0) ? 1u : 0u);
+          // S = Q K^T in three key ranges: [0,208), [208,384), [384,400); K = 128 = 2 slabs x 4 k-steps
+          auto s_group = [&](uint32_t key0, uint32_t id) {
+            for (int ks = 0; ks < 8; ++ks) {
+              const int s = ks >> 2, k = ks & 3;
+              const uint64_t da = umma_desc_sw128(smem_u32(smem + kOffQ + s * kQSlab)) + (uint64_t)(2 * k);
+              const uint64_t db = umma_desc_sw128(smem_u32(smem + kOffK + s * kKSlab + key0 * 128)) + (uint64_t)(2 * k);
+              umma_f16(tmem + key0, da, db, id, ks > 0 ? 1u : 0u);
+            }
+          };
+          s_group(0, id_sa);
+          umma_commit(sa_full);
+          s_group(208, id_sb);
+          umma_commit(sb_full);
+          // columns [384, 400) overlap the previous tile's O: wait until the softmax warps have read it out
+          mbar_wait(s_free, (tc & 1) ^ 1);
+          tc_fence_after();
+          s_group(384, id_sc);
+          umma_commit(sc_full);
+          umma_commit(q_empty);               // Q tile consumed
+          if (qt == 3) umma_commit(k_empty);  // K consumed: the next item's K may land
+          // O = P V, P (fp16) read from TMEM columns [0,200), V chunks of 80 keys from the ring
+          mbar_wait(p_ready, tc & 1);
+          tc_fence_after();
+          for (int c = 0; c < T / kVKeys; ++c) {
+            mbar_wait(&v_full[vs], vph);
+            tc_fence_after();
+            const uint32_t vbase = smem_u32(smem + kOffV + vs * 2 * kVSlab);
+            for (int k = 0; k < kVKeys / 16; ++k) {
+              const uint64_t db = umma_desc_mn_sw128(vbase + k * 16 * 128, kVSlab);
+              const uint32_t a_tmem = tmem + (uint32_t)((c * kVKeys + k * 16) >> 1);
+              umma_f16_ts(tmem + kColO, a_tmem, db, id_pv, (c > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&v_empty[vs]);
+            if (++vs == kVStages) {
+              vs = 0;
+              vph ^= 1;
+            }
           }
-          umma_commit(&v_empty[vs]);
-          if (++vs == kVStages) {
-            vs = 0;
-            vph ^= 1;
-          }
+          umma_commit(o_full);
         }
-        umma_commit(o_full);
       }
     }
   } else {
@@ -241,94 +291,99 @@ __global__ void __launch_bounds__(kThreadsTc, 1)
     const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
     const bool leader = (warp == 2 && lane == 0);
     const uint32_t row_off = (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
-    for (int qt = 0; qt < 4; ++qt) {
-      mbar_wait(s_full, qt & 1);
-      tc_fence_after();
-      // pass 1: row maximum
-      float m = -INFINITY;
+    int tc = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      int b, h, g, gcol;
+      item(w, b, h, g, gcol);
+      for (int qt = 0; qt < 4; ++qt, ++tc) {
+        // pass 1: row maximum, range by range as the S MMAs retire
+        float m = -INFINITY;
+        auto max32 = [&](uint32_t c) {
+          uint32_t v[32];
+          tmem_ld32(lane_base + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
+        };
+        auto max16 = [&](uint32_t c) {
+          uint32_t v[16];
+          tmem_ld16(lane_base + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) m = fmaxf(m, __uint_as_float(v[i]));
+        };
+        mbar_wait(sa_full, tc & 1);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 384; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(lane_base + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
-      }
-      {
-        uint32_t v[16];
-        tmem_ld16(lane_base + 384, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) m = fmaxf(m, __uint_as_float(v[i]));
-      }
-      const float mc = m * p.scale_log2e;
-      // pass 2: p = exp2(s*c - m*c), row sum, P (fp16 pairs) written over S, chunk by chunk behind the reads
-      float l = 0.f;
+        for (uint32_t c = 0; c < 192; c += 32) max32(c);
+        max16(192);
+        mbar_wait(sb_full, tc & 1);
+        tc_fence_after();
+        max16(208);
 #pragma unroll 1
-      for (int c = 0; c < 384; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(lane_base + c, v);
-        tmem_ld_wait();
-        uint32_t o[16];
+        for (uint32_t c = 224; c < 384; c += 32) max32(c);
+        mbar_wait(sc_full, tc & 1);
+        tc_fence_after();
+        max16(384);
+        const float mc = m * p.scale_log2e;
+        // pass 2: p = exp2(s*c - m*c), row sum, P (fp16 pairs) written over S, chunk by chunk behind the reads
+        float l = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 384; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(lane_base + c, v);
+          tmem_ld_wait();
+          uint32_t o[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = exp2f(__uint_as_float(v[2 * i]) * p.scale_log2e - mc);
-          const float p1 = exp2f(__uint_as_float(v[2 * i + 1]) * p.scale_log2e - mc);
-          l += p0 + p1;
-          o[i] = pack_half2(p0, p1);
+          for (int i = 0; i < 16; ++i) o[i] = exp2_pair(v[2 * i], v[2 * i + 1], p.scale_log2e, mc, l);
+          tmem_st16(lane_base + (c >> 1), o);
         }
-        tmem_st16(lane_base + (c >> 1), o);
-      }
-      {
-        uint32_t v[16];
-        tmem_ld16(lane_base + 384, v);
-        tmem_ld_wait();
-        uint32_t o[8];
+        {
+          uint32_t v[16];
+          tmem_ld16(lane_base + 384, v);
+          tmem_ld_wait();
+          uint32_t o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float p0 = exp2f(__uint_as_float(v[2 * i]) * p.scale_log2e - mc);
-          const float p1 = exp2f(__uint_as_float(v[2 * i + 1]) * p.scale_log2e - mc);
-          l += p0 + p1;
-          o[i] = pack_half2(p0, p1);
+          for (int i = 0; i < 8; ++i) o[i] = exp2_pair(v[2 * i], v[2 * i + 1], p.scale_log2e, mc, l);
+          tmem_st8(lane_base + 192, o);
         }
-        tmem_st8(lane_base + 192, o);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(p_ready);
-      const float inv_l = 1.f / l;
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_ready);
+        const float inv_l = 1.f / l;
 
-      // O tile: TMEM -> registers -> fp16 -> swizzled smem slabs -> TMA store
-      mbar_wait(o_full, qt & 1);
-      tc_fence_after();
-      if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging free again
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+        // O tile: TMEM -> registers -> fp16 -> swizzled smem slabs -> TMA store
+        mbar_wait(o_full, tc & 1);
+        tc_fence_after();
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging free again
+        asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll 1
-      for (int s = 0; s < 2; ++s) {
-        uint32_t v0[32], v1[32];
-        tmem_ld32(lane_base + kColO + s * 64, v0);
-        tmem_ld32(lane_base + kColO + s * 64 + 32, v1);
-        tmem_ld_wait();
-        uint8_t* slab = smem + kOffO + s * kQSlab;
+        for (int s = 0; s < 2; ++s) {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(lane_base + kColO + s * 64, v0);
+          tmem_ld32(lane_base + kColO + s * 64 + 32, v1);
+          tmem_ld_wait();
+          uint8_t* slab = smem + kOffO + s * kQSlab;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          uint32_t w[4];
+          for (int q = 0; q < 8; ++q) {
+            uint32_t wv[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float a0 = __uint_as_float(q < 4 ? v0[(q & 3) * 8 + 2 * k] : v1[(q & 3) * 8 + 2 * k]) * inv_l;
-            const float a1 = __uint_as_float(q < 4 ? v0[(q & 3) * 8 + 2 * k + 1] : v1[(q & 3) * 8 + 2 * k + 1]) * inv_l;
-            w[k] = pack_half2(a0, a1);
+            for (int k = 0; k < 4; ++k) {
+              const float a0 = __uint_as_float(q < 4 ? v0[(q & 3) * 8 + 2 * k] : v1[(q & 3) * 8 + 2 * k]) * inv_l;
+              const float a1 = __uint_as_float(q < 4 ? v0[(q & 3) * 8 + 2 * k + 1] : v1[(q & 3) * 8 + 2 * k + 1]) * inv_l;
+              wv[k] = pack_half2(a0, a1);
+            }
+            *reinterpret_cast<uint4*>(slab + row_off + (((uint32_t)q ^ sw) << 4)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
           }
-          *reinterpret_cast<uint4*>(slab + row_off + (((uint32_t)q ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
-      }
-      tc_fence_before();
-      mbar_arrive(s_free);  // S/P/O columns may be overwritten by the next tile
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (leader) {
-        for (int s = 0; s < 2; ++s) tma_store_4d(&map_o, smem + kOffO + s * kQSlab, h * DH + s * 64, qt * 128, b, g);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(s_free);  // O has left TMEM: the next tile's S_c may overwrite columns [384, 400)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (leader) {
+          for (int s = 0; s < 2; ++s) tma_store_4d(&map_o, smem + kOffO + s * kQSlab, h * DH + s * 64, qt * 128, b, g);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
       }
     }
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -376,7 +431,13 @@ int attn_tc_launch(const AttnParams& p, cudaStream_t stream) {
   tp.v_col = p.v_off;
   tp.group_col_stride = p.group_col_stride;
   tp.scale_log2e = p.scale * 1.4426950408889634f;
-  dim3 grid(p.B, p.n_heads, p.n_groups);
+  tp.B = p.B;
+  tp.H = p.n_heads;
+  tp.G = p.n_groups;
+  const int total = p.B * p.n_heads * p.n_groups;
+  const int sms = num_sms();
+  FP_REQUIRE(sms > 0, "no CUDA device");
+  dim3 grid(total < sms ? total : sms);
   FP_CUDA_OK(launch_pdl(attn_tc_kernel, grid, dim3(kThreadsTc), kSmem, stream, 1, mk, mq, mv, mo, tp));
   ++g_launch_count;
   FP_CUDA_OK(cudaGetLastError());

@@ -115,7 +115,6 @@ struct GemmParams {
   const float* post_add;
   int relu;
   double alg_flops;  // 2 * M * Cout * K_real of this launch (host-side bookkeeping only)
-  int dbg;           // FPOSE_GEMM_DBG timing experiments: 1 = no epilogue math/stores, 2 = no TMA store (results wrong)
   // ---- patch mode (3x3 stride-1 convolutions): the A operand of every tap is a shifted VIEW of one shared-memory
   // segment (a halo'd patch of the input tile, 128B-swizzled rows of 64 channels), fetched once per 64-channel
   // chunk instead of once per tap.  tools/umma_probe.cu shows that tcgen05 applies the 128B swizzle to absolute
@@ -514,7 +513,6 @@ __global__ void __launch_bounds__(kTileThreads, 1)
           }
         }
         if (p.has_res) mbar_wait(&res_full[buf], PREFETCH ? (uint32_t)(it & 1) : ((slab_ctr / (uint32_t)NS) & 1u));
-        if (p.dbg == 1) continue;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {  // this warp's 4 chunks of 8 channels (16 B)
           const int q = grp * 4 + q4;
@@ -551,7 +549,7 @@ __global__ void __launch_bounds__(kTileThreads, 1)
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (leader && p.dbg != 2) {
+        if (leader) {
           tma_store_5d(&map_out, slab, coff + n_tile * BN + c, oc[1], oc[2], oc[3], oc[4]);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -1315,10 +1313,6 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
   p.out_split = L.out_split;
   p.post_add = L.post_add;
   p.relu = L.relu;
-  {
-    const char* e = getenv("FPOSE_GEMM_DBG");
-    p.dbg = e ? atoi(e) : 0;
-  }
   {
     const double k_real = (double)taps * L.Cin;
     p.alg_flops = 2.0 * (double)L.n_img * Ho * Wo * L.Cout * k_real;

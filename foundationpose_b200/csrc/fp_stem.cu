@@ -55,7 +55,6 @@ struct StemParams {
   int tiles_w, tiles_h, n_img, total_tiles;
   const float* bias;
   int relu;
-  int align_test;
 };
 
 // un-swizzled K-major operand: 8 rows at 16 B, row groups `sbo` bytes apart, the two 8-element K chunks
@@ -157,8 +156,7 @@ __global__ void __launch_bounds__(kThreadsStem, 1)
 #pragma unroll
           for (int s = 0; s < 4; ++s) {
             // A: rows j at 16 B from pair j + s of padded row 2i + r; row groups i two padded rows apart
-            const uint64_t da = p.align_test ? umma_desc_linear(patch + r * 256, 128, 512)  // timing experiment only
-                                             : umma_desc_linear(patch + r * kRowStride + s * 16, kParStride, 2 * kRowStride);
+            const uint64_t da = umma_desc_linear(patch + r * kRowStride + s * 16, kParStride, 2 * kRowStride);
             // B: [E/O][64 ch][8]: rows (channels) at 16 B, groups of 8 channels 128 B apart, K chunks 1 KB apart
             const uint64_t db = umma_desc_linear(w_addr + (r * 4 + s) * kWTileBytes, 1024, 128);
             umma_f16(d_tmem, da, db, idesc, (r | s) ? 1u : 0u);
@@ -275,7 +273,6 @@ int stem_conv_launch(const GemmLayer& L, cudaStream_t stream) {
   p.total_tiles = p.tiles_w * p.tiles_h * L.n_img;
   p.bias = L.bias;
   p.relu = L.relu;
-  p.align_test = getenv("FPOSE_STEM_ALIGN_TEST") != nullptr;
   static bool attr_set = false;
   if (!attr_set) {
     FP_CUDA_OK(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem));

@@ -34,7 +34,7 @@ def main():
     e.set_frame(rgb, depth, K, filter_depth=True)
     poses_all, _ = e.start_poses(mask, est.rot_grid)
     base = None
-    for world in (1, 2, 4, 8):
+    for world in [int(w) for w in os.environ.get("FP_WORLDS", "1,2,4,8").split(",")]:
         n = (252 + world - 1) // world
         poses = poses_all[:n].contiguous()
         for _ in range(3):
