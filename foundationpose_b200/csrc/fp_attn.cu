@@ -471,8 +471,9 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const float* __restrict
 #pragma unroll
   for (int i = 0; i < 4; ++i) qr[i] = qv[lane * 4 + i];
   float mx = -INFINITY;
+#pragma unroll 6  // independent key rows: keep several L2 loads in flight (the loop is latency-bound)
   for (int k = 0; k < L; ++k) {
-    const float4 kv = *reinterpret_cast<const float4*>(qkv + (size_t)k * 1536 + 512 + h * 128 + lane * 4);
+    const float4 kv = __ldg(reinterpret_cast<const float4*>(qkv + (size_t)k * 1536 + 512 + h * 128 + lane * 4));
     float d = qr[0] * kv.x + qr[1] * kv.y + qr[2] * kv.z + qr[3] * kv.w;
     d = warp_sum(d) * scale;
     if (lane == 0) s[k] = d;
@@ -488,9 +489,10 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const float* __restrict
   sum = warp_sum(sum);
   __syncwarp();
   float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 6
   for (int k = 0; k < L; ++k) {
     const float pk = s[k];
-    const float4 vv = *reinterpret_cast<const float4*>(qkv + (size_t)k * 1536 + 1024 + h * 128 + lane * 4);
+    const float4 vv = __ldg(reinterpret_cast<const float4*>(qkv + (size_t)k * 1536 + 1024 + h * 128 + lane * 4));
     o[0] += pk * vv.x;
     o[1] += pk * vv.y;
     o[2] += pk * vv.z;

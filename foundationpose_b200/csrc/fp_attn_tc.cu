@@ -305,6 +305,14 @@ __global__ void __launch_bounds__(kThreadsTc, 1)
 #pragma unroll
           for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
         };
+        auto max64 = [&](uint32_t c) {  // two loads in flight per wait
+          uint32_t v[32], u[32];
+          tmem_ld32(lane_base + c, v);
+          tmem_ld32(lane_base + c + 32, u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) m = fmaxf(m, fmaxf(__uint_as_float(v[i]), __uint_as_float(u[i])));
+        };
         auto max16 = [&](uint32_t c) {
           uint32_t v[16];
           tmem_ld16(lane_base + c, v);
@@ -315,13 +323,14 @@ __global__ void __launch_bounds__(kThreadsTc, 1)
         mbar_wait(sa_full, tc & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (uint32_t c = 0; c < 192; c += 32) max32(c);
+        for (uint32_t c = 0; c < 192; c += 64) max64(c);
         max16(192);
         mbar_wait(sb_full, tc & 1);
         tc_fence_after();
         max16(208);
+        max32(224);
 #pragma unroll 1
-        for (uint32_t c = 224; c < 384; c += 32) max32(c);
+        for (uint32_t c = 256; c < 384; c += 64) max64(c);
         mbar_wait(sc_full, tc & 1);
         tc_fence_after();
         max16(384);
@@ -329,14 +338,18 @@ __global__ void __launch_bounds__(kThreadsTc, 1)
         // pass 2: p = exp2(s*c - m*c), row sum, P (fp16 pairs) written over S, chunk by chunk behind the reads
         float l = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < 384; c += 32) {
-          uint32_t v[32];
+        for (int c = 0; c < 384; c += 64) {
+          uint32_t v[32], u[32];
           tmem_ld32(lane_base + c, v);
+          tmem_ld32(lane_base + c + 32, u);
           tmem_ld_wait();
           uint32_t o[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) o[i] = exp2_pair(v[2 * i], v[2 * i + 1], p.scale_log2e, mc, l);
           tmem_st16(lane_base + (c >> 1), o);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = exp2_pair(u[2 * i], u[2 * i + 1], p.scale_log2e, mc, l);
+          tmem_st16(lane_base + (c >> 1) + 16, o);
         }
         {
           uint32_t v[16];
