@@ -297,13 +297,13 @@ def main():
     _lib.prof_enable(False)
     tf_ach = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     gb_ach = c_bytes / (c_ms * 1e-3) / 1e9 if c_ms > 0 else 0.0
-    roofline = {"kernel": "gemm_tile_kernel<BN> (tcgen05 implicit GEMM: 15 conv + linear layers)", "bound": "tensor",
+    roofline = {"kernel": "tcgen05 implicit-GEMM kernels: gemm_tile_kernel<BN,CG,SLABS,PATCH>, gemm_swap(_patch)_kernel, stem_conv_kernel (15 conv + linear layers)", "bound": "tensor",
                 "achieved": tf_ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": tf_ach / peaks["tf_sustained"],
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); kernel timed inside a long step",
                 "launches_timed": g_n, "avg_launch_ms": g_ms / max(g_n, 1), "share_of_step": (g_ms / 2) / ms,
                 "traffic": 373.1e6,
                 "traffic_note": "dram read+write of ONE representative launch (256-channel 3x3 conv, gemm_tile_kernel<256,2,2>) from profiles/r01c_prof3_gemm256cg2_details.csv (ncu --set full); algorithmic bytes of that launch: 413 MB"}
-    roofline_raster = {"kernel": "crop_kernel (raster + warp + normalise)", "bound": "hbm", "achieved": gb_ach,
+    roofline_raster = {"kernel": "crop producer: vertex_kernel + raster_kernel + shade_kernel (raster + warp + normalise)", "bound": "hbm", "achieved": gb_ach,
                        "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gb_ach / peaks["hbm_gbs"], "launches_timed": c_n,
                        "avg_launch_ms": c_ms / max(c_n, 1), "share_of_step": (c_ms / 2) / ms, "traffic": None}
 
