@@ -301,8 +301,8 @@ def main():
                 "achieved": tf_ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": tf_ach / peaks["tf_sustained"],
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); kernel timed inside a long step",
                 "launches_timed": g_n, "avg_launch_ms": g_ms / max(g_n, 1), "share_of_step": (g_ms / 2) / ms,
-                "traffic": 373.1e6,
-                "traffic_note": "dram read+write of ONE representative launch (256-channel 3x3 conv, gemm_tile_kernel<256,2,2>) from profiles/r01c_prof3_gemm256cg2_details.csv (ncu --set full); algorithmic bytes of that launch: 413 MB"}
+                "traffic": 371.2e6,
+                "traffic_note": "dram read+write of ONE representative launch (256-channel 3x3 conv, gemm_tile_kernel<256,2,2,patch>) from profiles/r01f_prof5_conv256_patch_details.csv (ncu --set full); algorithmic bytes of that launch: 413 MB"}
     roofline_raster = {"kernel": "crop producer: vertex_kernel + raster_kernel + shade_kernel (raster + warp + normalise)", "bound": "hbm", "achieved": gb_ach,
                        "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gb_ach / peaks["hbm_gbs"], "launches_timed": c_n,
                        "avg_launch_ms": c_ms / max(c_n, 1), "share_of_step": (c_ms / 2) / ms, "traffic": None}

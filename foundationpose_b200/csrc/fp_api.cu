@@ -94,7 +94,7 @@ struct fp_ctx {
   bool use_graphs = true;
   fp::DevBuf lt_buf, lr_buf, feat_buf, pose_stage;
   fp::DevBuf vtx_a, vtx_b, win_buf;  // crop producer workspaces: [cap_n][V] x 16 B each, [cap_n][8]
-  fp::DevBuf mask_buf, tab_buf, zbuf;
+  fp::DevBuf mask_buf, mask_stats, tab_buf, zbuf;
 };
 
 namespace fp {
@@ -426,7 +426,7 @@ int fp_destroy(fp_ctx* c) {
   for (auto& kv : c->graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
-  DevBuf* more[] = {&c->lt_buf, &c->lr_buf, &c->feat_buf, &c->pose_stage, &c->vtx_a, &c->vtx_b, &c->win_buf, &c->mask_buf, &c->tab_buf, &c->zbuf};
+  DevBuf* more[] = {&c->lt_buf, &c->lr_buf, &c->feat_buf, &c->pose_stage, &c->vtx_a, &c->vtx_b, &c->win_buf, &c->mask_buf, &c->mask_stats, &c->tab_buf, &c->zbuf};
   for (DevBuf* b : more)
     if (b->p) cudaFree(b->p);
   delete c;
@@ -607,8 +607,9 @@ int fp_start_poses(fp_ctx* c, const unsigned char* mask, int mask_on_device, con
     FP_CUDA_OK(cudaMemcpyAsync(c->mask_buf.p, mask, npix, cudaMemcpyHostToDevice, st));
     mdev = reinterpret_cast<const unsigned char*>(c->mask_buf.p);
   }
-  return start_poses_launch(c->depth_cur, mdev, c->H, c->W, c->K[0], c->K[4], c->K[2], c->K[5], rot_grid, N, poses_out,
-                            info_out, st);
+  FP_TRY(dev_alloc(c->mask_stats, 64));
+  return start_poses_launch(c->depth_cur, mdev, c->H, c->W, c->K[0], c->K[4], c->K[2], c->K[5], rot_grid, N,
+                            reinterpret_cast<unsigned int*>(c->mask_stats.p), poses_out, info_out, st);
 }
 
 int fp_make_crops(fp_ctx* c, const float* poses, int N, int mode, void* crops_out, float* dbg_out, float* win_out,

@@ -94,7 +94,7 @@ int bilateral_depth_launch(const float* depth, float* out, int H, int W, int rad
 
 // ------------------------------------------------------------------------------------------------
 // start poses on the device: guess_translation (estimater.py:137-156) + rot_grid with that translation
-// (estimater.py:127-134, :203-209).  One CTA; the median of the masked valid depths is an exact radix
+// (estimater.py:127-134, :203-209).  The median of the masked valid depths is an exact radix
 // select over the float bit patterns (depths are positive, so the patterns are ordered), np.median's
 // mean of the two middle elements for an even count included.
 // ------------------------------------------------------------------------------------------------
@@ -137,35 +137,55 @@ __device__ unsigned int radix_select(const float* __restrict__ depth, const unsi
   return prefix;
 }
 
-__global__ void __launch_bounds__(1024) start_poses_kernel(const float* __restrict__ depth,
-                                                           const unsigned char* __restrict__ mask, int H, int W, float fx,
-                                                           float fy, float cx, float cy, const float* __restrict__ rot_grid,
-                                                           int N, float* __restrict__ poses_out, float* __restrict__ info) {
-  __shared__ unsigned int hist[256];
-  __shared__ unsigned int sh[2];
-  __shared__ int bb[4];  // umin, umax, vmin, vmax
-  __shared__ unsigned int cnt[2];
-  __shared__ float tvec[3];
+// pass 1 (grid-wide): mask bounding box and pixel counts.  All six statistics are max / sum reductions over values
+// that start at 0 (the box minima are stored mirrored), so one 24-byte memset initialises them.
+__global__ void __launch_bounds__(256) mask_stats_kernel(const float* __restrict__ depth,
+                                                         const unsigned char* __restrict__ mask, int H, int W,
+                                                         unsigned int* __restrict__ stats) {
   const int npix = H * W;
-  if (threadIdx.x == 0) {
-    bb[0] = W; bb[1] = -1; bb[2] = H; bb[3] = -1;
-    cnt[0] = 0; cnt[1] = 0;
-  }
-  __syncthreads();
-  int umin = W, umax = -1, vmin = H, vmax = -1;
-  unsigned int n_mask = 0, n_valid = 0;
-  for (int i = threadIdx.x; i < npix; i += blockDim.x) {
+  unsigned int mu0 = 0, u1 = 0, mv0 = 0, v1 = 0, n_mask = 0, n_valid = 0;  // mu0 = W - 1 - umin, mv0 = H - 1 - vmin
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
     if (mask[i]) {
       const int v = i / W, u = i - v * W;
-      umin = min(umin, u); umax = max(umax, u); vmin = min(vmin, v); vmax = max(vmax, v);
+      mu0 = max(mu0, (unsigned)(W - 1 - u) + 1u);  // +1: 0 stays "no pixel"
+      u1 = max(u1, (unsigned)u + 1u);
+      mv0 = max(mv0, (unsigned)(H - 1 - v) + 1u);
+      v1 = max(v1, (unsigned)v + 1u);
       ++n_mask;
       if (depth[i] >= 0.001f) ++n_valid;
     }
   }
-  atomicMin(&bb[0], umin); atomicMax(&bb[1], umax); atomicMin(&bb[2], vmin); atomicMax(&bb[3], vmax);
-  atomicAdd(&cnt[0], n_mask); atomicAdd(&cnt[1], n_valid);
-  __syncthreads();
-  const unsigned int nm = cnt[0], nv = cnt[1];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mu0 = max(mu0, __shfl_xor_sync(0xffffffffu, mu0, o));
+    u1 = max(u1, __shfl_xor_sync(0xffffffffu, u1, o));
+    mv0 = max(mv0, __shfl_xor_sync(0xffffffffu, mv0, o));
+    v1 = max(v1, __shfl_xor_sync(0xffffffffu, v1, o));
+    n_mask += __shfl_xor_sync(0xffffffffu, n_mask, o);
+    n_valid += __shfl_xor_sync(0xffffffffu, n_valid, o);
+  }
+  if ((threadIdx.x & 31) == 0 && n_mask) {
+    atomicMax(&stats[0], mu0);
+    atomicMax(&stats[1], u1);
+    atomicMax(&stats[2], mv0);
+    atomicMax(&stats[3], v1);
+    atomicAdd(&stats[4], n_mask);
+    atomicAdd(&stats[5], n_valid);
+  }
+}
+
+// pass 2 (one CTA): exact median over the bounding box, translation, start poses
+__global__ void __launch_bounds__(1024) start_poses_kernel(const float* __restrict__ depth,
+                                                           const unsigned char* __restrict__ mask, int H, int W, float fx,
+                                                           float fy, float cx, float cy, const float* __restrict__ rot_grid,
+                                                           int N, const unsigned int* __restrict__ stats,
+                                                           float* __restrict__ poses_out, float* __restrict__ info) {
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int sh[2];
+  __shared__ float tvec[3];
+  const unsigned int nm = stats[4], nv = stats[5];
+  // umin, umax, vmin, vmax
+  const int bb[4] = {W - (int)stats[0], (int)stats[1] - 1, H - (int)stats[2], (int)stats[3] - 1};
   float zc = 0.f;
   if (nm > 0 && nv > 0) {  // uniform branch
     const int u0 = bb[0], v0 = bb[2], bw = bb[1] - bb[0] + 1, bh = bb[3] - bb[2] + 1;
@@ -197,9 +217,12 @@ __global__ void __launch_bounds__(1024) start_poses_kernel(const float* __restri
 }
 
 int start_poses_launch(const float* depth, const unsigned char* mask, int H, int W, float fx, float fy, float cx, float cy,
-                       const float* rot_grid, int N, float* poses_out, float* info, cudaStream_t stream) {
-  start_poses_kernel<<<1, 1024, 0, stream>>>(depth, mask, H, W, fx, fy, cx, cy, rot_grid, N, poses_out, info);
-  ++g_launch_count;
+                       const float* rot_grid, int N, unsigned int* stats /*6 words of device scratch*/, float* poses_out,
+                       float* info, cudaStream_t stream) {
+  FP_CUDA_OK(cudaMemsetAsync(stats, 0, 6 * sizeof(unsigned int), stream));
+  mask_stats_kernel<<<148, 256, 0, stream>>>(depth, mask, H, W, stats);
+  start_poses_kernel<<<1, 1024, 0, stream>>>(depth, mask, H, W, fx, fy, cx, cy, rot_grid, N, stats, poses_out, info);
+  g_launch_count += 2;
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -8,5 +8,6 @@ int erode_depth_launch(const float* depth, float* out, int H, int W, int radius,
 int bilateral_depth_launch(const float* depth, float* out, int H, int W, int radius, float zfar, float sigmaD,
                            float sigmaR, cudaStream_t stream);
 int start_poses_launch(const float* depth, const unsigned char* mask, int H, int W, float fx, float fy, float cx, float cy,
-                       const float* rot_grid, int N, float* poses_out, float* info, cudaStream_t stream);
+                       const float* rot_grid, int N, unsigned int* stats, float* poses_out, float* info,
+                       cudaStream_t stream);
 }  // namespace fp
