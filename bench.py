@@ -138,6 +138,24 @@ def cpu_nets_rate(budget_s=20.0):
                          f"{t_ref * 1e3:.1f} ms/hyp-iter refine, {t_sc * 1e3:.1f} ms/hyp score; extrapolated to {N_ITER} iters + 1 score; raster/warp not included")
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Keep fd 1 for the ONE JSON line: everything else that writes to stdout (NCCL's version banner comes from C
+    code and ignores NCCL_DEBUG_FILE on some boxes) is sent to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path (its own networks; the
     raster/warp stage has no CPU implementation in the reference) on the host cores."""
@@ -169,7 +187,7 @@ def run_reference(args, rank, world):
     value = n / dt
     sample = (f"{n} hypotheses per step through RefineNet x{N_ITER} + ScoreNetMultiPair (oracle port of the reference modules, fp32 torch CPU, "
               f"{cores} threads) on pre-built 160x160 crops; the reference has no CPU raster/warp")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "hyp/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -177,7 +195,7 @@ def run_reference(args, rank, world):
                    "hypotheses_per_step": n},
         "cpu_baseline": {"value": value, "unit": "hyp/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "hyp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def main():
@@ -193,6 +211,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    claim_stdout()
 
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -338,7 +357,7 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
