@@ -16,7 +16,7 @@ import os
 import numpy as np
 import torch
 
-from . import hypotheses, synth, weights
+from . import hypotheses, meshprep, synth, weights
 from .engine import Engine
 
 
@@ -162,6 +162,15 @@ class FoundationPose:
         mesh.vertices = mesh.vertices - self.model_center.reshape(1, 3)
         self.diameter = synth.mesh_diameter(mesh.vertices)
         self.vox_size = max(self.diameter / 20.0, 0.003)
+        self.dist_bin = self.vox_size / 2
+        self.angle_bin = 20  # deg
+        # estimater.py:59-64: voxel-down-sampled model points / normals (used by callers for ADD-style metrics)
+        pts, nrm = meshprep.voxel_down_sample(mesh.vertices, self.vox_size, normals=model_normals)
+        self.max_xyz = pts.max(axis=0)
+        self.min_xyz = pts.min(axis=0)
+        self.pts = torch.tensor(pts, dtype=torch.float32, device="cuda")
+        self.normals = torch.nn.functional.normalize(torch.tensor(nrm, dtype=torch.float32, device="cuda"), dim=-1)
+        self.mesh_path = None  # the reference exports a temporary .obj for its debug tooling; not needed here
         self.mesh = mesh
         self.mesh_tensors = make_mesh_tensors(mesh)
         mt = self.mesh_tensors

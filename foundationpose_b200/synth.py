@@ -88,13 +88,10 @@ def make_mesh(subdivisions=5, tex_seed=0, tex_size=1024):
 
 
 def mesh_diameter(vertices):
-    """Largest pairwise vertex distance (Utils.py:559-574 without the random sub-sampling)."""
-    v = np.asarray(vertices, dtype=np.float64)
-    if len(v) > 4000:
-        rng = np.random.default_rng(0)
-        v = v[rng.choice(len(v), 4000, replace=False)]
-    d2 = ((v[None] - v[:, None]) ** 2).sum(-1)
-    return float(np.sqrt(d2.max()))
+    """Largest pairwise vertex distance (Utils.py:559-574), exact: see meshprep.mesh_diameter."""
+    from .meshprep import mesh_diameter as _exact
+
+    return _exact(vertices)
 
 
 DEFAULT_K = np.array([[615.0, 0, 320.0], [0, 615.0, 240.0], [0, 0, 1.0]])

@@ -124,3 +124,31 @@ def test_gather_rows_world2_gloo():
         for p in procs:
             p.join(timeout=60)
         assert all(ok for _, ok in res), res
+
+
+def test_meshprep_diameter_and_voxel_downsample():
+    """reset_object helpers (estimater.py:43-64, Utils.py:559-574) without open3d: exact diameter, voxel means."""
+    from foundationpose_b200 import meshprep, synth
+
+    rng = np.random.default_rng(0)
+    for k in range(4):
+        p = rng.normal(size=(400, 3)) * rng.uniform(0.1, 3.0, 3)
+        brute = float(np.sqrt(((p[None] - p[:, None]) ** 2).sum(-1).max()))
+        assert abs(meshprep.mesh_diameter(p) - brute) < 1e-12
+    assert meshprep.mesh_diameter(np.zeros((1, 3))) == 0.0
+    m = synth.make_mesh(3)
+    assert abs(meshprep.mesh_diameter(m.vertices) - 2 * synth.RADII.max()) < 1e-9
+    # voxel grid: every output point is the mean of the inputs of one voxel (origin = min bound - voxel / 2)
+    vox = 0.02
+    q, n = meshprep.voxel_down_sample(m.vertices, vox, normals=m.vertex_normals)
+    assert q.shape == n.shape and 1 < len(q) < len(m.vertices)
+    origin = m.vertices.min(axis=0) - vox / 2
+    idx_in = np.floor((m.vertices - origin) / vox).astype(np.int64)
+    idx_out = np.floor((q - origin) / vox).astype(np.int64)
+    assert len(np.unique(idx_in, axis=0)) == len(q) == len(np.unique(idx_out, axis=0))
+    k0 = idx_out[0]
+    sel = (idx_in == k0).all(1)
+    np.testing.assert_allclose(q[0], m.vertices[sel].mean(0), atol=1e-12)
+    np.testing.assert_allclose(n[0], m.vertex_normals[sel].mean(0), atol=1e-12)
+    single, _ = meshprep.voxel_down_sample(m.vertices, 10.0)
+    np.testing.assert_allclose(single, m.vertices.mean(0)[None], atol=1e-12)
