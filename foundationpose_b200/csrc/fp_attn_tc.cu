@@ -154,12 +154,12 @@ __global__ void __launch_bounds__(kThreadsTc, 1)
   uint64_t* sa_full = bars + 4;
   uint64_t* sb_full = bars + 5;
   uint64_t* sc_full = bars + 6;
-  uint64_t* p_ready = bars + 7;
-  uint64_t* o_full = bars + 8;
-  uint64_t* s_free = bars + 9;
-  uint64_t* v_full = bars + 10;               // [3]
-  uint64_t* v_empty = bars + 10 + kVStages;   // [3]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * kVStages);
+  uint64_t* p_ready = bars + 7;               // [3]: keys [0,160), [160,320), [320,400) of P are in TMEM
+  uint64_t* o_full = bars + 10;
+  uint64_t* s_free = bars + 11;
+  uint64_t* v_full = bars + 12;               // [3]
+  uint64_t* v_empty = bars + 12 + kVStages;   // [3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12 + 2 * kVStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total = p.B * p.H * p.G;
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1)
     mbar_init(sa_full, 1);
     mbar_init(sb_full, 1);
     mbar_init(sc_full, 1);
-    mbar_init(p_ready, 128);
+    for (int i = 0; i < 3; ++i) mbar_init(&p_ready[i], 128);
     mbar_init(o_full, 1);
     mbar_init(s_free, 128);
     for (int i = 0; i < kVStages; ++i) {
@@ -264,9 +264,12 @@ __global__ void __launch_bounds__(kThreadsTc, 1)
           umma_commit(q_empty);               // Q tile consumed
           if (qt == 3) umma_commit(k_empty);  // K consumed: the next item's K may land
           // O = P V, P (fp16) read from TMEM columns [0,200), V chunks of 80 keys from the ring
-          mbar_wait(p_ready, tc & 1);
-          tc_fence_after();
           for (int c = 0; c < T / kVKeys; ++c) {
+            // the exp pass publishes P in three steps (chunks 0-1, 2-3, 4): PV starts behind it
+            if (c == 0 || c == 2 || c == 4) {
+              mbar_wait(&p_ready[c >> 1], tc & 1);
+              tc_fence_after();
+            }
             mbar_wait(&v_full[vs], vph);
             tc_fence_after();
             const uint32_t vbase = smem_u32(smem + kOffV + vs * 2 * kVSlab);
@@ -335,34 +338,37 @@ __global__ void __launch_bounds__(kThreadsTc, 1)
         tc_fence_after();
         max16(384);
         const float mc = m * p.scale_log2e;
-        // pass 2: p = exp2(s*c - m*c), row sum, P (fp16 pairs) written over S, chunk by chunk behind the reads
+        // pass 2: p = exp2(s*c - m*c), row sum, P (fp16 pairs) written over S, chunk by chunk behind the reads.
+        // The 16-key tail (columns [384,400), the only part of S that O's columns overlap) is consumed FIRST and
+        // held in registers, so the PV MMAs of the first keys may start while this pass is still running.
         float l = 0.f;
+        uint32_t tail[8];
+        {
+          uint32_t v[16];
+          tmem_ld16(lane_base + 384, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) tail[i] = exp2_pair(v[2 * i], v[2 * i + 1], p.scale_log2e, mc, l);
+        }
+        auto publish = [&](int part) {
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&p_ready[part]);
+        };
 #pragma unroll 1
-        for (int c = 0; c < 384; c += 64) {
-          uint32_t v[32], u[32];
+        for (int c = 0; c < 384; c += 32) {
+          uint32_t v[32];
           tmem_ld32(lane_base + c, v);
-          tmem_ld32(lane_base + c + 32, u);
           tmem_ld_wait();
           uint32_t o[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) o[i] = exp2_pair(v[2 * i], v[2 * i + 1], p.scale_log2e, mc, l);
           tmem_st16(lane_base + (c >> 1), o);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = exp2_pair(u[2 * i], u[2 * i + 1], p.scale_log2e, mc, l);
-          tmem_st16(lane_base + (c >> 1) + 16, o);
+          if (c == 128) publish(0);  // keys [0,160)
+          if (c == 288) publish(1);  // keys [160,320)
         }
-        {
-          uint32_t v[16];
-          tmem_ld16(lane_base + 384, v);
-          tmem_ld_wait();
-          uint32_t o[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = exp2_pair(v[2 * i], v[2 * i + 1], p.scale_log2e, mc, l);
-          tmem_st8(lane_base + 192, o);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(p_ready);
+        tmem_st8(lane_base + 192, tail);
+        publish(2);  // keys [320,400)
         const float inv_l = 1.f / l;
 
         // O tile: TMEM -> registers -> fp16 -> swizzled smem slabs -> TMA store
