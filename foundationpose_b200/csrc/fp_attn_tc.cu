@@ -301,20 +301,29 @@ __global__ void __launch_bounds__(kThreadsTc, 1)
       for (int qt = 0; qt < 4; ++qt, ++tc) {
         // pass 1: row maximum, range by range as the S MMAs retire
         float m = -INFINITY;
-        auto max32 = [&](uint32_t c) {
-          uint32_t v[32];
-          tmem_ld32(lane_base + c, v);
-          tmem_ld_wait();
+        auto fold32 = [&](const uint32_t (&v)[32]) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; i += 2) m = fmaxf(m, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
         };
-        auto max64 = [&](uint32_t c) {  // two loads in flight per wait
-          uint32_t v[32], u[32];
-          tmem_ld32(lane_base + c, v);
-          tmem_ld32(lane_base + c + 32, u);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) m = fmaxf(m, fmaxf(__uint_as_float(v[i]), __uint_as_float(u[i])));
+        // n chunks of 32 columns from column c0, software-pipelined: the next chunk's load is in flight while the
+        // current one is reduced
+        auto max_range = [&](uint32_t c0, int n) {
+          uint32_t va[32], vb[32];
+          tmem_ld32(lane_base + c0, va);
+          int k = 0;
+#pragma unroll 1
+          for (; k + 1 < n; k += 2) {
+            tmem_ld_wait();
+            tmem_ld32(lane_base + c0 + (uint32_t)(k + 1) * 32u, vb);
+            fold32(va);
+            tmem_ld_wait();
+            if (k + 2 < n) tmem_ld32(lane_base + c0 + (uint32_t)(k + 2) * 32u, va);
+            fold32(vb);
+          }
+          if (k < n) {
+            tmem_ld_wait();
+            fold32(va);
+          }
         };
         auto max16 = [&](uint32_t c) {
           uint32_t v[16];
@@ -325,15 +334,12 @@ __global__ void __launch_bounds__(kThreadsTc, 1)
         };
         mbar_wait(sa_full, tc & 1);
         tc_fence_after();
-#pragma unroll 1
-        for (uint32_t c = 0; c < 192; c += 64) max64(c);
+        max_range(0, 6);
         max16(192);
         mbar_wait(sb_full, tc & 1);
         tc_fence_after();
         max16(208);
-        max32(224);
-#pragma unroll 1
-        for (uint32_t c = 256; c < 384; c += 64) max64(c);
+        max_range(224, 5);
         mbar_wait(sc_full, tc & 1);
         tc_fence_after();
         max16(384);
@@ -355,17 +361,25 @@ __global__ void __launch_bounds__(kThreadsTc, 1)
           tc_fence_before();
           mbar_arrive(&p_ready[part]);
         };
+        // software-pipelined: the load of the next 32 columns is in flight while the current 32 are exponentiated
+        {
+          uint32_t va[32], vb[32], o[16];
+          tmem_ld32(lane_base, va);
 #pragma unroll 1
-        for (int c = 0; c < 384; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(lane_base + c, v);
-          tmem_ld_wait();
-          uint32_t o[16];
+          for (int c = 0; c < 384; c += 64) {
+            tmem_ld_wait();
+            tmem_ld32(lane_base + c + 32, vb);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = exp2_pair(v[2 * i], v[2 * i + 1], p.scale_log2e, mc, l);
-          tmem_st16(lane_base + (c >> 1), o);
-          if (c == 128) publish(0);  // keys [0,160)
-          if (c == 288) publish(1);  // keys [160,320)
+            for (int i = 0; i < 16; ++i) o[i] = exp2_pair(va[2 * i], va[2 * i + 1], p.scale_log2e, mc, l);
+            tmem_st16(lane_base + (c >> 1), o);
+            if (c == 128) publish(0);  // keys [0,160)
+            tmem_ld_wait();
+            if (c + 64 < 384) tmem_ld32(lane_base + c + 64, va);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = exp2_pair(vb[2 * i], vb[2 * i + 1], p.scale_log2e, mc, l);
+            tmem_st16(lane_base + (c >> 1) + 16, o);
+            if (c == 256) publish(1);  // keys [160,320)
+          }
         }
         tmem_st8(lane_base + 192, tail);
         publish(2);  // keys [320,400)
