@@ -304,7 +304,7 @@ static int make_crops(fp_ctx* c, const float* poses, int N, int mode, float* dbg
   FP_TRY(dev_alloc(c->vtx_b, (size_t)c->cap_n * c->V * 16));
   FP_TRY(dev_alloc(c->win_buf, (size_t)c->cap_n * 8 * 4));
   FP_TRY(dev_alloc(c->tab_buf, (size_t)c->cap_n * 6 * 160 * 4));
-  FP_TRY(dev_alloc(c->zbuf, (size_t)c->cap_n * 160 * 160 * 8));
+  FP_TRY(dev_alloc(c->zbuf, (size_t)c->cap_n * 160 * 160 * 8, /*zero=*/true));  // kept all-zero between launches
   CropParams p;
   p.vtx_a = reinterpret_cast<VtxA*>(c->vtx_a.p);
   p.vtx_b = reinterpret_cast<VtxB*>(c->vtx_b.p);

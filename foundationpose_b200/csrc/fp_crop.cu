@@ -176,6 +176,8 @@ struct __align__(16) VtxB {  // what shading additionally needs
 __global__ void __launch_bounds__(256) vertex_kernel(const CropParams p) {
   __shared__ float sP[16];
   __shared__ Window sW;
+  pdl_trigger();
+  pdl_wait();  // poses come from the previous iteration's pose update; vtx / tab buffers are still read by its shade
   const int n = blockIdx.y;
   if (threadIdx.x < 16) sP[threadIdx.x] = p.poses[(size_t)n * 16 + threadIdx.x];
   __syncthreads();
@@ -384,6 +386,7 @@ __global__ void __launch_bounds__(256) shade_kernel(const CropParams p) {
     float ar = 0.f, ag = 0.f, ab = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
     const unsigned long long key = p.zbuf[(size_t)n * S * S + pix];
     if (key != 0ull) {
+      p.zbuf[(size_t)n * S * S + pix] = 0ull;  // leave the z-buffer clean for the next launch (no separate clear pass)
       const int f = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
       const int i0 = __ldg(p.faces + 3 * f), i1 = __ldg(p.faces + 3 * f + 1), i2 = __ldg(p.faces + 3 * f + 2);
       const VtxA a = va[i0], b = va[i1], c = va[i2];
@@ -502,8 +505,8 @@ int crop_launch(const CropParams& p, cudaStream_t stream) {
   if (p.N == 0) return 0;
   // algorithmic bytes: the two 6-channel fp16 crops each hypothesis produces
   prof_mark_begin(1, (double)p.N * 2.0 * 6.0 * S * S * 2.0, stream);
-  FP_CUDA_OK(cudaMemsetAsync(p.zbuf, 0, (size_t)p.N * S * S * sizeof(unsigned long long), stream));
-  vertex_kernel<<<dim3((p.V + 255) / 256, p.N), 256, 0, stream>>>(p);
+  // the z-buffer is all-zero here: allocated zeroed, and shade_kernel clears every cell it consumes
+  FP_CUDA_OK(launch_pdl(vertex_kernel, dim3((p.V + 255) / 256, p.N), dim3(256), 0, stream, 1, p));
   FP_CUDA_OK(launch_pdl(raster_kernel, dim3((p.F + 255) / 256, p.N), dim3(256), 0, stream, 1, p));
   FP_CUDA_OK(launch_pdl(shade_kernel, dim3((S * S + 255) / 256, p.N), dim3(256), 0, stream, 1, p));
   prof_mark_end(stream);
