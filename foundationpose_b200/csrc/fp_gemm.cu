@@ -10,15 +10,20 @@
 //
 // Design (B200-first, no library GEMM):
 //   * D[128 x BN] tiles, fp16 operands, fp32 accumulators in TMEM (double buffered, 2 x BN columns).
-//   * Warp-specialised persistent CTA (one per SM): warp 0 = TMA producer, warp 1 = single-thread
-//     tcgen05.mma issuer, warps 2..5 = epilogue (TMEM -> registers -> +bias/+residual/ReLU/+PE ->
-//     fp16 NHWC stores).  smem ring of STAGES x (A 16 KB + B BN*128 B), 128-byte swizzle.
+//   * Warp-specialised persistent CTA (one per SM, or a CTA pair issuing cta_group::2 MMAs): warp 0 = TMA
+//     producer, warp 1 = single-thread tcgen05.mma issuer, warps 2..9 = epilogue (TMEM -> registers ->
+//     +bias/+residual/ReLU/+PE -> fp16 -> swizzled smem slab -> TMA tensor store).  smem ring of STAGES x
+//     (A 16 KB + B BN*128 B), 128-byte swizzle.
 //   * The convolution is an *implicit* GEMM: the A tile for k-block (tap, 64-channel chunk) is one
 //     5-D TMA box over the NHWC activation tensor, displaced by the tap offset; out-of-bounds
 //     coordinates are zero-filled by the TMA unit, which implements the zero padding.  Stride-2
 //     convolutions use a (2C, W/2, 2, H/2, N) view of the same memory so that every tap is again a
 //     dense box; the 7x7/s2 stem has its own kernel (fp_stem.cu).  No im2col buffer is ever
 //     materialised.
+//   * What bounds these main loops on B200 is the SM's 128 B/cycle shared-memory port (TMA fills + MMA
+//     operand reads + epilogue staging), hence: CTA pairs (half of B per CTA), the swapped kernel for the
+//     128-channel layers, and the PATCH mode, in which the nine taps of a 3x3 convolution are nine shifted
+//     descriptors into ONE input patch per 64-channel chunk (see GemmParams).
 #include "fp_gemm.cuh"
 
 #include <stdarg.h>
@@ -132,7 +137,6 @@ struct GemmParams {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
-constexpr int kThreads = 192;       // swap kernel: producer, MMA, 4 epilogue warps
 constexpr int kTileThreads = 320;   // tile kernel: producer, MMA, 8 epilogue warps (two per TMEM lane quarter)
 constexpr int kSlabBytes = kBlockM * 64 * 2;  // 16 KB: one output slab (128 pixels x 64 channels, 128B-swizzled)
 
@@ -420,7 +424,7 @@ __global__ void __launch_bounds__(kTileThreads, 1)
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
     // TMEM -> registers -> (+bias, +residual, ReLU, +pos.emb.) -> fp16 -> 128B-swizzled smem slab ->
     // one TMA tensor store per 128-pixel x 64-channel slab.  The residual slab arrives the same way
     // (TMA load into the slab buffer), so every global access of the epilogue is a bulk, fully
