@@ -52,8 +52,10 @@ __device__ __forceinline__ void crop_window(const float* __restrict__ pose, floa
   const float top = rintf(__fsub_rn(v[0], radius)), bottom = rintf(__fadd_rn(v[0], radius));
   w.left = left;
   w.top = top;
-  w.sx = __fdiv_rn((float)S, __fsub_rn(right, left));
-  w.sy = __fdiv_rn((float)S, __fsub_rn(bottom, top));
+  // Utils.py:594-595 `out_size[0] / (right - left)` is int / Tensor = Tensor.__rtruediv__ = reciprocal() * 160 in
+  // torch: two roundings, not one division (tests/golden/geometry_golden.npz pins the bits)
+  w.sx = __fmul_rn(__frcp_rn(__fsub_rn(right, left)), (float)S);
+  w.sy = __fmul_rn(__frcp_rn(__fsub_rn(bottom, top)), (float)S);
   // predict_pose_refine.py:44-45: render window = crop corners (0,0)-(159,159) mapped back to the image
   w.umin = left;
   w.vmin = top;

@@ -1,5 +1,6 @@
-"""CPU restatement of the geometry around the networks (TEST INFRASTRUCTURE; PARITY UNPINNED — the
-reference functions cannot be imported here, see oracle/__init__.py).
+"""CPU restatement of the geometry around the networks (TEST INFRASTRUCTURE; PARTLY PINNED: crop_window,
+depth2xyzmap, the pose composition and normalise_xyz against the reference's own function bodies, see
+oracle/__init__.py; so3_exp_map, warp_perspective and the depth filters are PARITY UNPINNED).
 
 Each function cites the reference lines it follows.  fp32 throughout, like the reference's CUDA
 tensors; operation order is kept explicit where a rounding decides an integer (crop window edges).
@@ -29,8 +30,10 @@ def crop_window(poses, K, mesh_diameter, crop_ratio=1.2, out_size=160):
     right = np.round(u[:, 0] + radius).astype(f32)
     top = np.round(v[:, 0] - radius).astype(f32)
     bottom = np.round(v[:, 0] + radius).astype(f32)
-    sx = (f32(out_size) / (right - left)).astype(f32)
-    sy = (f32(out_size) / (bottom - top)).astype(f32)
+    # `out_size[0] / (right - left)` with a Python int on the left is Tensor.__rtruediv__ = reciprocal() * 160:
+    # two fp32 roundings (pinned bit-exactly by tests/golden/geometry_golden.npz)
+    sx = ((f32(1) / (right - left)).astype(f32) * f32(out_size)).astype(f32)
+    sy = ((f32(1) / (bottom - top)).astype(f32) * f32(out_size)).astype(f32)
     tf = np.zeros((len(poses), 3, 3), dtype=f32)
     tf[:, 0, 0] = sx
     tf[:, 1, 1] = sy
