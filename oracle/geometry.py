@@ -1,6 +1,6 @@
-"""CPU restatement of the geometry around the networks (TEST INFRASTRUCTURE; PARTLY PINNED: crop_window,
-depth2xyzmap, the pose composition and normalise_xyz against the reference's own function bodies, see
-oracle/__init__.py; so3_exp_map, warp_perspective and the depth filters are PARITY UNPINNED).
+"""CPU restatement of the geometry around the networks (TEST INFRASTRUCTURE; PINNED against the reference's own
+function bodies — crop_window, depth2xyzmap, pose composition, normalise_xyz, erode / bilateral depth filters, see
+oracle/__init__.py — except so3_exp_map (pytorch3d) and warp_perspective (kornia), which are PARITY UNPINNED).
 
 Each function cites the reference lines it follows.  fp32 throughout, like the reference's CUDA
 tensors; operation order is kept explicit where a rounding decides an integer (crop window edges).

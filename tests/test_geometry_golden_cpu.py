@@ -76,3 +76,22 @@ def test_raster_pixel_mapping_matches_reference_projection_and_bbox_crop():
     X, Y, Z, iz, xi, yi = raster._project(np.eye(4), G["pj_pts_cam"].astype(np.float32), G["pj_K"], umin, vmin, rsx, rsy)
     np.testing.assert_allclose(xi / 256.0, G["pj_px"], rtol=0, atol=2e-3 + 1 / 512)
     np.testing.assert_allclose(yi / 256.0, S - G["pj_py_from_bottom"], rtol=0, atol=2e-3 + 1 / 512)
+
+
+def test_scorer_normalise_xyz_matches_reference_triplet_transform():
+    """TripletH5Dataset.transform_depth_to_xyzmap (h5_dataset.py:137-170): invalid = z < 0.1 for the scorer."""
+    gotA = geometry.normalise_xyz(torch.from_numpy(G["ns_xyzA"]), torch.from_numpy(G["nx_t"]), float(G["nx_diameter"]), 0.1)
+    gotB = geometry.normalise_xyz(torch.from_numpy(G["nx_xyzB"]), torch.from_numpy(G["nx_t"]), float(G["nx_diameter"]), 0.1)
+    np.testing.assert_allclose(gotA.numpy(), G["ns_outA"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(gotB.numpy(), G["ns_outB"], rtol=0, atol=1e-6)
+    assert (G["ns_outA"][:, :, 10:12] == 0).all() and (G["nx_outA"][:, :, 10:12] != 0).any()  # 0.05 m: scorer-only invalid
+
+
+def test_depth_filters_match_reference_warp_kernel_bodies():
+    """erode_depth_kernel / bilateral_filter_depth_kernel (Utils.py:304-384) executed thread by thread as plain Python
+    (fp64 scalars; Warp and the oracle compute in fp32, hence 2e-6)."""
+    er = geometry.erode_depth(G["df_depth"])
+    np.testing.assert_allclose(er, G["df_eroded"], rtol=0, atol=0)  # erosion only selects values: exact
+    bl = geometry.bilateral_filter_depth(G["df_eroded"])
+    np.testing.assert_allclose(bl, G["df_bilateral"], rtol=0, atol=2e-6)
+    assert (G["df_eroded"] == 0).sum() > (G["df_depth"] == 0).sum()  # the fixture really erodes something

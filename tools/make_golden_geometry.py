@@ -11,6 +11,9 @@ and writes inputs + outputs to tests/golden/geometry_golden.npz:
   egocentric_delta_pose_to_pose             Utils.py:848-855            -> oracle.geometry.pose_update (pose composition)
   FoundationPose.guess_translation          estimater.py:137-156        -> hypotheses.guess_translation, start_poses_kernel
   PairH5Dataset.transform_depth_to_xyzmap   h5_dataset.py:79-114        -> oracle.geometry.normalise_xyz (tau = 0.001)
+  TripletH5Dataset.transform_depth_to_xyzmap h5_dataset.py:137-170      -> oracle.geometry.normalise_xyz (tau = 0.1)
+  erode_depth_kernel / bilateral_filter_depth_kernel (Warp kernel bodies run as plain Python, Utils.py:304-384)
+                                                                         -> oracle.geometry.erode_depth / bilateral_filter_depth
   projection_matrix_from_intrinsics + the bbox2d crop of nvdiffrast_render (Utils.py:159-181, 752-802)
                                                                          -> the pixel mapping oracle/raster.py assumes
 
@@ -38,7 +41,9 @@ def extract(path, name, cls=None):
     body = tree.body
     if cls is not None:
         body = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == cls).body
-    fn = next(n for n in body if isinstance(n, ast.FunctionDef) and n.name == name)
+    fn = next((n for n in body if isinstance(n, ast.FunctionDef) and n.name == name), None)
+    if fn is None and cls is None:  # e.g. the Warp kernels, nested under `if wp is not None:`
+        fn = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == name)
     fn.decorator_list = []
     for a in list(fn.args.args) + list(fn.args.kwonlyargs):  # annotations name types we do not import
         a.annotation = None
@@ -58,12 +63,35 @@ class _TorchProxy(types.ModuleType):
         return None
 
 
+class _WarpStub:
+    """Just enough of `warp` to run a kernel body as ordinary Python, one thread at a time (Warp computes in fp32, this
+    runs in fp64: the goldens are compared with 2e-6)."""
+    _tid = (0, 0)
+    exp = staticmethod(__import__("math").exp)
+
+    @staticmethod
+    def tid():
+        return _WarpStub._tid
+
+    @staticmethod
+    def launch(kernel, H, W, *args):
+        for h in range(H):
+            for w in range(W):
+                _WarpStub._tid = (h, w)
+                kernel(*args)
+
+
 def load_reference_functions():
-    ns = {"np": np, "torch": _TorchProxy("torch"), "logging": logging, "kornia": None, "F": torch.nn.functional}
+    ns = {"np": np, "torch": _TorchProxy("torch"), "logging": logging, "kornia": None, "F": torch.nn.functional, "wp": _WarpStub}
     for name in ("compute_crop_window_tf_batch", "depth2xyzmap", "depth2xyzmap_batch", "egocentric_delta_pose_to_pose",
                  "projection_matrix_from_intrinsics"):
         exec(extract(os.path.join(REF, "Utils.py"), name), ns)
+    for name in ("erode_depth_kernel", "bilateral_filter_depth_kernel"):  # Warp kernel bodies, run as plain Python
+        exec(extract(os.path.join(REF, "Utils.py"), name), ns)
     exec(extract(os.path.join(REF, "estimater.py"), "guess_translation", cls="FoundationPose"), ns)
+    ns_t = dict(ns)
+    exec(extract(os.path.join(REF, "learning/datasets/h5_dataset.py"), "transform_depth_to_xyzmap", cls="TripletH5Dataset"), ns_t)
+    ns["transform_depth_to_xyzmap_scorer"] = ns_t["transform_depth_to_xyzmap"]
     exec(extract(os.path.join(REF, "learning/datasets/h5_dataset.py"), "transform_depth_to_xyzmap", cls="PairH5Dataset"), ns)
     return ns
 
@@ -145,6 +173,27 @@ def main():
     fake_ds = types.SimpleNamespace(cfg={"normalize_xyz": True})
     nb = ref["transform_depth_to_xyzmap"](fake_ds, batch, 480, 640)
     out.update(nx_xyzA=xyzA, nx_xyzB=xyzB, nx_t=tA, nx_diameter=np.float32(0.19), nx_outA=nb.xyz_mapAs.numpy(), nx_outB=nb.xyz_mapBs.numpy())
+
+    # ---- scorer xyz normalisation (TripletH5Dataset.transform_depth_to_xyzmap, tau = 0.1; ready xyz maps)
+    xyzA2 = xyzA.copy()
+    xyzA2[:, 2, 10:12] = 0.05  # 0.001 <= z < 0.1: invalid for the scorer only
+    batch2 = types.SimpleNamespace(rgbAs=torch.zeros(bs, 3, 20, 20), mesh_diameters=torch.full((bs,), 0.19), tf_to_crops=torch.eye(3)[None].repeat(bs, 1, 1),
+                                   poseA=torch.from_numpy(poseA), Ks=torch.eye(3)[None].repeat(bs, 1, 1), xyz_mapAs=torch.from_numpy(xyzA2.copy()),
+                                   xyz_mapBs=torch.from_numpy(xyzB.copy()), depthAs=None, depthBs=None)
+    nb2 = ref["transform_depth_to_xyzmap_scorer"](fake_ds, batch2, 480, 640)
+    out.update(ns_xyzA=xyzA2, ns_outA=nb2.xyz_mapAs.numpy(), ns_outB=nb2.xyz_mapBs.numpy())
+
+    # ---- depth filters: the reference's Warp kernel bodies executed thread by thread
+    dimg = (0.6 + 0.05 * np.sin(np.arange(64)[None] / 7.0) + 0.03 * np.cos(np.arange(48)[:, None] / 5.0)).astype(np.float32)
+    dimg += rng.normal(0, 0.0005, dimg.shape).astype(np.float32)
+    dimg[rng.random(dimg.shape) < 0.06] = 0.0          # holes
+    dimg[10:20, 30:40] += 0.05                          # a step edge
+    dimg[rng.random(dimg.shape) < 0.02] += 0.2          # outliers
+    er = np.zeros_like(dimg)
+    _WarpStub.launch(ref["erode_depth_kernel"], 48, 64, dimg, er, 2, 0.001, 0.8, 100.0)
+    bl = np.zeros_like(dimg)
+    _WarpStub.launch(ref["bilateral_filter_depth_kernel"], 48, 64, er, bl, 2, 100.0, 2.0, 100000.0)
+    out.update(df_depth=dimg, df_eroded=er, df_bilateral=bl)
 
     # ---- projection + bbox2d crop of nvdiffrast_render (Utils.py:159-181): where does a camera point land in the crop?
     H, W = 480, 640
