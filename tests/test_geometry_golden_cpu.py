@@ -95,3 +95,20 @@ def test_depth_filters_match_reference_warp_kernel_bodies():
     bl = geometry.bilateral_filter_depth(G["df_eroded"])
     np.testing.assert_allclose(bl, G["df_bilateral"], rtol=0, atol=2e-6)
     assert (G["df_eroded"] == 0).sum() > (G["df_depth"] == 0).sum()  # the fixture really erodes something
+
+
+def test_make_mesh_tensors_matches_reference():
+    """Utils.py:104-130 vs the product's host-side estimater.make_mesh_tensors (pure numpy part; no GPU involved):
+    v-flipped uv, RGB texture (the 1/255 scale is applied inside the shading kernel), vertex colours / 255."""
+    from foundationpose_b200 import synth
+    from foundationpose_b200.estimater import make_mesh_tensors
+
+    m = synth.SimpleMesh(G["mt_vertices"], G["mt_faces"], G["mt_normals"], uv=G["mt_uv_in"], texture=G["mt_tex_in"])
+    mt = make_mesh_tensors(m)
+    np.testing.assert_array_equal(mt["pos"], G["mt_pos"])
+    np.testing.assert_array_equal(mt["faces"], G["mt_faces_out"])
+    np.testing.assert_array_equal(mt["normals"], G["mt_vnormals"])
+    np.testing.assert_array_equal(mt["uv"], G["mt_uv"])
+    np.testing.assert_allclose(mt["tex"].astype(np.float32) / 255.0, G["mt_tex"][0], rtol=0, atol=1e-7)
+    mc = synth.SimpleMesh(G["mt_vertices"], G["mt_faces"], G["mt_normals"], vertex_colors=G["mt_vcolor_in"])
+    np.testing.assert_allclose(make_mesh_tensors(mc)["vcolor"], G["mt_vertex_color"], rtol=0, atol=1e-7)

@@ -14,6 +14,7 @@ and writes inputs + outputs to tests/golden/geometry_golden.npz:
   TripletH5Dataset.transform_depth_to_xyzmap h5_dataset.py:137-170      -> oracle.geometry.normalise_xyz (tau = 0.1)
   erode_depth_kernel / bilateral_filter_depth_kernel (Warp kernel bodies run as plain Python, Utils.py:304-384)
                                                                          -> oracle.geometry.erode_depth / bilateral_filter_depth
+  make_mesh_tensors                          Utils.py:104-130            -> estimater.make_mesh_tensors (product host code)
   projection_matrix_from_intrinsics + the bbox2d crop of nvdiffrast_render (Utils.py:159-181, 752-802)
                                                                          -> the pixel mapping oracle/raster.py assumes
 
@@ -63,6 +64,13 @@ class _TorchProxy(types.ModuleType):
         return None
 
 
+class _TextureVisuals:
+    """Stands in for trimesh.visual.texture.TextureVisuals in make_mesh_tensors' isinstance check."""
+
+
+_TRIMESH = types.SimpleNamespace(visual=types.SimpleNamespace(texture=types.SimpleNamespace(TextureVisuals=_TextureVisuals)))
+
+
 class _WarpStub:
     """Just enough of `warp` to run a kernel body as ordinary Python, one thread at a time (Warp computes in fp32, this
     runs in fp64: the goldens are compared with 2e-6)."""
@@ -82,10 +90,11 @@ class _WarpStub:
 
 
 def load_reference_functions():
-    ns = {"np": np, "torch": _TorchProxy("torch"), "logging": logging, "kornia": None, "F": torch.nn.functional, "wp": _WarpStub}
+    ns = {"np": np, "torch": _TorchProxy("torch"), "logging": logging, "kornia": None, "F": torch.nn.functional, "wp": _WarpStub, "trimesh": _TRIMESH}
     for name in ("compute_crop_window_tf_batch", "depth2xyzmap", "depth2xyzmap_batch", "egocentric_delta_pose_to_pose",
                  "projection_matrix_from_intrinsics"):
         exec(extract(os.path.join(REF, "Utils.py"), name), ns)
+    exec(extract(os.path.join(REF, "Utils.py"), "make_mesh_tensors"), ns)
     for name in ("erode_depth_kernel", "bilateral_filter_depth_kernel"):  # Warp kernel bodies, run as plain Python
         exec(extract(os.path.join(REF, "Utils.py"), name), ns)
     exec(extract(os.path.join(REF, "estimater.py"), "guess_translation", cls="FoundationPose"), ns)
@@ -194,6 +203,23 @@ def main():
     bl = np.zeros_like(dimg)
     _WarpStub.launch(ref["bilateral_filter_depth_kernel"], 48, 64, er, bl, 2, 100.0, 2.0, 100000.0)
     out.update(df_depth=dimg, df_eroded=er, df_bilateral=bl)
+
+    # ---- make_mesh_tensors (Utils.py:104-130) on a textured and on a vertex-coloured mesh
+    from PIL import Image
+
+    m2 = synth.make_mesh(1, tex_size=16)
+    vis = _TextureVisuals()
+    vis.uv = m2.visual.uv
+    vis.material = types.SimpleNamespace(image=Image.fromarray(m2.visual.image))
+    tmesh = types.SimpleNamespace(vertices=m2.vertices, faces=m2.faces, vertex_normals=m2.vertex_normals, visual=vis)
+    mt = ref["make_mesh_tensors"](tmesh, device="cpu")
+    vc = rng.integers(0, 256, size=(len(m2.vertices), 4)).astype(np.uint8)
+    cmesh = types.SimpleNamespace(vertices=m2.vertices, faces=m2.faces, vertex_normals=m2.vertex_normals,
+                                  visual=types.SimpleNamespace(vertex_colors=vc))
+    mc = ref["make_mesh_tensors"](cmesh, device="cpu")
+    out.update(mt_vertices=m2.vertices, mt_faces=m2.faces, mt_normals=m2.vertex_normals, mt_uv_in=m2.visual.uv, mt_tex_in=m2.visual.image,
+               mt_pos=mt["pos"].numpy(), mt_faces_out=mt["faces"].numpy(), mt_vnormals=mt["vnormals"].numpy(), mt_uv=mt["uv"].numpy(),
+               mt_tex=mt["tex"].numpy(), mt_vcolor_in=vc, mt_vertex_color=mc["vertex_color"].numpy())
 
     # ---- projection + bbox2d crop of nvdiffrast_render (Utils.py:159-181): where does a camera point land in the crop?
     H, W = 480, 640
