@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfpose.so")
+# FPOSE_LIB_PATH: load another in-tree build of the same sources (A/B experiments with compile-time variants)
+LIB_PATH = os.environ.get("FPOSE_LIB_PATH") or os.path.join(_HERE, "lib", "libfpose.so")
 
 
 class FposeError(RuntimeError):

@@ -1,8 +1,12 @@
 // fp_api.cu — the product C ABI (include/fpose.h): context, weights, mesh, frame, and the per-frame
 // hot loop (crops -> encoder -> heads -> pose update, K times; then scoring) enqueued on one stream
 // with no host synchronisation.
+#include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
+#include <algorithm>
+#include <exception>
 #include <map>
 #include <string>
 #include <tuple>
@@ -23,19 +27,30 @@ struct DevBuf {
   size_t bytes = 0;
 };
 
-// bumped whenever a device pointer or by-value kernel parameter that a captured CUDA graph may hold
-// changes (re-allocation, new mesh / weights / intrinsics): cached graphs older than this are rebuilt
-static unsigned long long g_epoch = 1;
-
-static int dev_alloc(DevBuf& b, size_t bytes, bool zero = false) {
+// (Re)allocates `b` to at least `bytes`.  `epoch` is the owning context's graph epoch: it is bumped whenever a device
+// pointer or by-value kernel parameter that a captured CUDA graph may hold changes (re-allocation, new mesh /
+// weights / intrinsics), and cached graphs older than it are rebuilt.  Never called while a stream is capturing:
+// every workspace is sized by ensure_capacity / fp_set_mesh / fp_set_frame BEFORE run_graphed.
+static int dev_alloc(unsigned long long& epoch, DevBuf& b, size_t bytes, bool zero = false) {
   if (b.bytes >= bytes && b.p) return 0;
-  ++g_epoch;
+  ++epoch;
   if (b.p) cudaFree(b.p);
   b.p = nullptr;
   b.bytes = 0;
   FP_CUDA_OK(cudaMalloc(&b.p, bytes));
   b.bytes = bytes;
-  if (zero) FP_CUDA_OK(cudaMemset(b.p, 0, bytes));
+  if (zero) {
+    // legacy-stream memset + full synchronisation: the consumers run on the caller's (possibly non-blocking) stream
+    FP_CUDA_OK(cudaMemset(b.p, 0, bytes));
+    FP_CUDA_OK(cudaDeviceSynchronize());
+  }
+  return 0;
+}
+template <class T>
+static int upload(unsigned long long& epoch, DevBuf& b, const std::vector<T>& v) {
+  const size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+  if (dev_alloc(epoch, b, bytes)) return -2;
+  if (!v.empty()) FP_CUDA_OK(cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -48,6 +63,8 @@ struct Tensor {
 struct Net {
   std::map<std::string, Tensor> t;
   bool loaded = false;
+  // fp_load_network verified that every name the execution plan uses is present; a miss is a programming error
+  // and surfaces as an exception that the extern "C" wrappers turn into an error code
   const __half* h(const char* name) const { return reinterpret_cast<const __half*>(t.at(name).p); }
   const float* f(const char* name) const { return reinterpret_cast<const float*>(t.at(name).p); }
 };
@@ -66,11 +83,14 @@ static inline int b_img0_of(int N) { return (N + 3) & ~3; }
 struct fp_ctx {
   int device = 0;
   fp::Net net[2];  // 0 = refiner, 1 = scorer
-  // mesh
-  fp::DevBuf vpos, vnrm, vuv, vcol, faces, tex;
-  int V = 0, F = 0, Ht = 0, Wt = 0;
+  unsigned long long epoch = 1;  // graph epoch (see dev_alloc)
+  // mesh (fp_meshlet.cu layout)
+  fp::DevBuf vpos, vnrm, vatt, faces, meshlets, ml_verts, ml_tris, tex;
+  int V = 0, F = 0, Ht = 0, Wt = 0, n_meshlets = 0, front_sign = 0, mesh_closed = 0;
+  float mesh_bs[4] = {0.f, 0.f, 0.f, 0.f};
   bool has_tex = false, has_mesh = false;
-  float diameter = 0.f, crop_ratio = 1.2f, rot_normalizer = 0.3490658503988659f;
+  float diameter = 0.f, rot_normalizer = 0.3490658503988659f;
+  float crop_ratio[2] = {1.2f, 1.2f};  // per predictor: each reads its own config.yml (predict_pose_refine.py:117, predict_score.py:137)
   // frame
   fp::DevBuf rgb_raw, rgba, depth_raw, depth_a, depth_b, xyz;
   const float* depth_cur = nullptr;
@@ -92,9 +112,16 @@ struct fp_ctx {
   std::map<std::tuple<int, int, int>, int> graph_nodes;
   cudaStream_t cap_stream = nullptr;
   bool use_graphs = true;
+  bool cull_backfaces = true;  // FPOSE_NO_CULL=1: render both sides even for closed meshes (A/B checks)
+  bool track_valid = false;
   fp::DevBuf lt_buf, lr_buf, feat_buf, pose_stage;
-  fp::DevBuf vtx_a, vtx_b, win_buf;  // crop producer workspaces: [cap_n][V] x 16 B each, [cap_n][8]
-  fp::DevBuf mask_buf, mask_stats, tab_buf, zbuf;
+  fp::DevBuf mask_buf, mask_stats, crop_stats;
+  // fp_track: pinned host staging (frame in, pose out) so that the whole frame is ONE graph launch
+  void* stage_rgb = nullptr;
+  void* stage_depth = nullptr;
+  float* stage_pose = nullptr;
+  size_t stage_npix = 0;
+  fp::DevBuf track_pose;
 };
 
 namespace fp {
@@ -105,32 +132,32 @@ static int ensure_capacity(fp_ctx* c, int N) {
   int rc = 0;
   // the crop buffer is zeroed once: the 3-pixel border is never written afterwards
   const size_t m = 2 * n + 3;  // A + pad + B images
-  rc |= dev_alloc(c->crops, m * kCropImg * 2, true);
-  rc |= dev_alloc(c->act0, m * 80 * 80 * 64 * 2);
-  rc |= dev_alloc(c->a1, m * 1600 * 128 * 2);
-  rc |= dev_alloc(c->a2, m * 1600 * 128 * 2);
-  rc |= dev_alloc(c->a3, m * 1600 * 128 * 2);
-  rc |= dev_alloc(c->ab0, n * 1600 * 256 * 2);
-  rc |= dev_alloc(c->ab1, n * 1600 * 256 * 2);
-  rc |= dev_alloc(c->ab2, n * 1600 * 256 * 2);
-  rc |= dev_alloc(c->c0, n * T * 512 * 2);
-  rc |= dev_alloc(c->c1, n * T * 512 * 2);
-  rc |= dev_alloc(c->c2, n * T * 512 * 2);
-  rc |= dev_alloc(c->tok, n * T * 512 * 2);
-  rc |= dev_alloc(c->qkv, n * T * 3072 * 2);
-  rc |= dev_alloc(c->att, 2 * n * T * 512 * 2);
-  rc |= dev_alloc(c->x1pre, n * T * 512 * 2);
-  rc |= dev_alloc(c->x1, n * T * 512 * 2);
-  rc |= dev_alloc(c->ff, n * T * 512 * 2);
-  rc |= dev_alloc(c->x2pre, n * T * 512 * 2);
-  rc |= dev_alloc(c->head_out, 2 * n * 3 * 4);
-  rc |= dev_alloc(c->poses_a, n * 16 * 4);
-  rc |= dev_alloc(c->poses_b, n * 16 * 4);
-  rc |= dev_alloc(c->feats, n * 512 * 4);
-  rc |= dev_alloc(c->lt_buf, n * 3 * 4);
-  rc |= dev_alloc(c->lr_buf, n * 9 * 4);
-  rc |= dev_alloc(c->feat_buf, n * 512 * 4);
-  rc |= dev_alloc(c->pose_stage, n * 16 * 4);
+  rc |= dev_alloc(c->epoch, c->crops, m * kCropImg * 2, true);
+  rc |= dev_alloc(c->epoch, c->act0, m * 80 * 80 * 64 * 2);
+  rc |= dev_alloc(c->epoch, c->a1, m * 1600 * 128 * 2);
+  rc |= dev_alloc(c->epoch, c->a2, m * 1600 * 128 * 2);
+  rc |= dev_alloc(c->epoch, c->a3, m * 1600 * 128 * 2);
+  rc |= dev_alloc(c->epoch, c->ab0, n * 1600 * 256 * 2);
+  rc |= dev_alloc(c->epoch, c->ab1, n * 1600 * 256 * 2);
+  rc |= dev_alloc(c->epoch, c->ab2, n * 1600 * 256 * 2);
+  rc |= dev_alloc(c->epoch, c->c0, n * T * 512 * 2);
+  rc |= dev_alloc(c->epoch, c->c1, n * T * 512 * 2);
+  rc |= dev_alloc(c->epoch, c->c2, n * T * 512 * 2);
+  rc |= dev_alloc(c->epoch, c->tok, n * T * 512 * 2);
+  rc |= dev_alloc(c->epoch, c->qkv, n * T * 3072 * 2);
+  rc |= dev_alloc(c->epoch, c->att, 2 * n * T * 512 * 2);
+  rc |= dev_alloc(c->epoch, c->x1pre, n * T * 512 * 2);
+  rc |= dev_alloc(c->epoch, c->x1, n * T * 512 * 2);
+  rc |= dev_alloc(c->epoch, c->ff, n * T * 512 * 2);
+  rc |= dev_alloc(c->epoch, c->x2pre, n * T * 512 * 2);
+  rc |= dev_alloc(c->epoch, c->head_out, 2 * n * 3 * 4);
+  rc |= dev_alloc(c->epoch, c->poses_a, n * 16 * 4);
+  rc |= dev_alloc(c->epoch, c->poses_b, n * 16 * 4);
+  rc |= dev_alloc(c->epoch, c->feats, n * 512 * 4);
+  rc |= dev_alloc(c->epoch, c->lt_buf, n * 3 * 4);
+  rc |= dev_alloc(c->epoch, c->lr_buf, n * 9 * 4);
+  rc |= dev_alloc(c->epoch, c->feat_buf, n * 512 * 4);
+  rc |= dev_alloc(c->epoch, c->pose_stage, n * 16 * 4);
   if (rc) return -2;
   c->cap_n = N;
   return 0;
@@ -139,11 +166,11 @@ static int ensure_capacity(fp_ctx* c, int N) {
 static int ensure_tail(fp_ctx* c, int L) {
   if (L <= c->tail_cap) return 0;
   int rc = 0;
-  rc |= dev_alloc(c->tail_qkv, (size_t)L * 1536 * 4);
-  rc |= dev_alloc(c->tail_attn, (size_t)L * 512 * 4);
-  rc |= dev_alloc(c->tail_proj, (size_t)L * 512 * 4);
-  rc |= dev_alloc(c->scores, (size_t)L * 4);
-  rc |= dev_alloc(c->best, 16);
+  rc |= dev_alloc(c->epoch, c->tail_qkv, (size_t)L * 1536 * 4);
+  rc |= dev_alloc(c->epoch, c->tail_attn, (size_t)L * 512 * 4);
+  rc |= dev_alloc(c->epoch, c->tail_proj, (size_t)L * 512 * 4);
+  rc |= dev_alloc(c->epoch, c->scores, (size_t)L * 4);
+  rc |= dev_alloc(c->epoch, c->best, 16);
   if (rc) return -2;
   c->tail_cap = L;
   return 0;
@@ -297,21 +324,12 @@ static int crops_export(fp_ctx* c, void* ext, int N, cudaStream_t st) {
   return 0;
 }
 
-static int make_crops(fp_ctx* c, const float* poses, int N, int mode, float* dbg, float* win, cudaStream_t st) {
+static int make_crops(fp_ctx* c, const float* poses, int N, int mode, float* dbg, float* win, int* stats,
+                      cudaStream_t st) {
   FP_REQUIRE(c->has_mesh, "no mesh: call fp_set_mesh first");
   FP_REQUIRE(c->has_frame, "no frame: call fp_set_frame first");
-  FP_TRY(dev_alloc(c->vtx_a, (size_t)c->cap_n * c->V * 16));
-  FP_TRY(dev_alloc(c->vtx_b, (size_t)c->cap_n * c->V * 16));
-  FP_TRY(dev_alloc(c->win_buf, (size_t)c->cap_n * 8 * 4));
-  FP_TRY(dev_alloc(c->tab_buf, (size_t)c->cap_n * 6 * 160 * 4));
-  FP_TRY(dev_alloc(c->zbuf, (size_t)c->cap_n * 160 * 160 * 8, /*zero=*/true));  // kept all-zero between launches
+  // only launches below: this body is also what run_graphed captures (no allocation, no synchronisation)
   CropParams p;
-  p.vtx_a = reinterpret_cast<VtxA*>(c->vtx_a.p);
-  p.vtx_b = reinterpret_cast<VtxB*>(c->vtx_b.p);
-  p.win_buf = reinterpret_cast<float*>(c->win_buf.p);
-  p.tab_buf = reinterpret_cast<float*>(c->tab_buf.p);
-  p.zbuf = reinterpret_cast<unsigned long long*>(c->zbuf.p);
-  p.V = c->V;
   p.poses = poses;
   p.N = N;
   p.fx = c->K[0];
@@ -320,34 +338,46 @@ static int make_crops(fp_ctx* c, const float* poses, int N, int mode, float* dbg
   p.cy = c->K[5];
   p.H = c->H;
   p.W = c->W;
-  p.r3 = (float)((double)c->diameter * (double)c->crop_ratio / 2.0);
+  p.r3 = (float)((double)c->diameter * (double)c->crop_ratio[mode ? 1 : 0] / 2.0);
   p.inv_radius = 1.0f / (c->diameter / 2.0f);
-  p.znear = 0.001f;
-  p.vpos = reinterpret_cast<const float*>(c->vpos.p);
-  p.vnrm = reinterpret_cast<const float*>(c->vnrm.p);
-  p.vuv = c->has_tex ? reinterpret_cast<const float*>(c->vuv.p) : nullptr;
-  p.vcol = c->has_tex ? nullptr : reinterpret_cast<const float*>(c->vcol.p);
-  p.faces = reinterpret_cast<const int*>(c->faces.p);
-  p.F = c->F;
+  p.znear = 0.001f;  // Utils.py:161
+  p.zfar = 100.f;
+  p.mesh.vpos = reinterpret_cast<const float4*>(c->vpos.p);
+  p.mesh.vnrm = reinterpret_cast<const float4*>(c->vnrm.p);
+  p.mesh.vatt = reinterpret_cast<const float4*>(c->vatt.p);
+  p.mesh.faces = reinterpret_cast<const int4*>(c->faces.p);
+  p.mesh.meshlets = reinterpret_cast<const Meshlet*>(c->meshlets.p);
+  p.mesh.ml_verts = reinterpret_cast<const int*>(c->ml_verts.p);
+  p.mesh.ml_tris = reinterpret_cast<const uint2*>(c->ml_tris.p);
+  p.mesh.n_meshlets = c->n_meshlets;
+  p.mesh.V = c->V;
+  p.mesh.F = c->F;
+  p.mesh.front_sign = c->cull_backfaces ? c->front_sign : 0;
+  p.mesh.bs_x = c->mesh_bs[0];
+  p.mesh.bs_y = c->mesh_bs[1];
+  p.mesh.bs_z = c->mesh_bs[2];
+  p.mesh.bs_r = c->mesh_bs[3];
+  p.has_tex = c->has_tex ? 1 : 0;
   p.tex = c->has_tex ? reinterpret_cast<const uchar4*>(c->tex.p) : nullptr;
   p.Ht = c->Ht;
   p.Wt = c->Wt;
   p.rgb = reinterpret_cast<const uchar4*>(c->rgba.p);
-  p.xyz_map = reinterpret_cast<const float*>(c->xyz.p);
+  p.xyz_map = reinterpret_cast<const float4*>(c->xyz.p);
   p.depth = c->depth_cur;
   p.mode = mode;
   p.crops = reinterpret_cast<__half*>(c->crops.p);
   p.b_img0 = b_img0_of(N);
   p.dbg = dbg;
   p.win_out = win;
+  p.stats = stats;
   return crop_launch(p, st);
 }
 
-
-// Runs `body(stream)` — a fixed sequence of kernel launches on ctx-owned buffers — through a cached
-// CUDA graph: first sight of a key runs eagerly (sets function attributes, sizes workspaces), the second
+// Runs `body(stream)` — a fixed sequence of kernel launches (and fixed-address copies) on ctx-owned buffers —
+// through a cached CUDA graph: first sight of a key runs eagerly (sets function attributes), the second
 // captures + instantiates, later calls replay.  Replay removes ~170 launch + 60 tensor-map-encode host
-// calls per register(), which is what bounds track_one() and small per-GPU shards.
+// calls per register(), which is what bounds track_one() and small per-GPU shards.  The body never allocates:
+// callers size every workspace first, so a capture after an epoch bump (new mesh, new N) is safe.
 template <class Body>
 static int run_graphed(fp_ctx* c, int kind, int N, int iters, cudaStream_t st, Body body) {
   if (!c->use_graphs || g_prof_on) return body(st);
@@ -358,18 +388,24 @@ static int run_graphed(fp_ctx* c, int kind, int N, int iters, cudaStream_t st, B
     return body(st);
   }
   fp_ctx::GraphEntry& g = it->second;
-  if (g.exec == nullptr || g.epoch != g_epoch) {
+  if (g.exec == nullptr || g.epoch != c->epoch) {
     if (g.exec) {
       cudaGraphExecDestroy(g.exec);
       g.exec = nullptr;
     }
     if (!c->cap_stream) FP_CUDA_OK(cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
-    const unsigned long long launches_before = g_launch_count;
     FP_CUDA_OK(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal));
-    const int rc = body(c->cap_stream);
+    set_capturing(true);  // nothing runs during capture: launches are counted per replay
+    int rc = 0;
+    try {
+      rc = body(c->cap_stream);
+    } catch (...) {
+      rc = -3;
+      set_last_error("exception while capturing the launch sequence");
+    }
+    set_capturing(false);
     cudaGraph_t graph = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(c->cap_stream, &graph);
-    g_launch_count = launches_before;  // nothing ran during capture
     if (rc != 0) {
       if (graph) cudaGraphDestroy(graph);
       return rc;
@@ -377,14 +413,93 @@ static int run_graphed(fp_ctx* c, int kind, int N, int iters, cudaStream_t st, B
     FP_CUDA_OK(ce);
     size_t n_nodes = 0;
     cudaGraphGetNodes(graph, nullptr, &n_nodes);
+    size_t n_kernels = 0;
+    {
+      std::vector<cudaGraphNode_t> nodes(n_nodes);
+      if (n_nodes && cudaGraphGetNodes(graph, nodes.data(), &n_nodes) == cudaSuccess)
+        for (auto nd : nodes) {
+          cudaGraphNodeType ty;
+          if (cudaGraphNodeGetType(nd, &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel) ++n_kernels;
+        }
+    }
     const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
     cudaGraphDestroy(graph);
     FP_CUDA_OK(ie);
-    g.epoch = g_epoch;
-    c->graph_nodes[key] = (int)n_nodes;
+    g.epoch = c->epoch;
+    c->graph_nodes[key] = (int)n_kernels;
   }
   FP_CUDA_OK(cudaGraphLaunch(g.exec, st));
-  g_launch_count += (unsigned long long)c->graph_nodes[key];
+  note_launches(c->graph_nodes[key]);
+  return 0;
+}
+
+// RAII: make the context's device current for the duration of an entry point
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+static int set_frame_launches(fp_ctx* c, const unsigned char* rgb_dev, const float* depth_dev, int flags, float zfar,
+                              cudaStream_t st) {
+  const int H = c->H, W = c->W;
+  const size_t npix = (size_t)H * W;
+  FP_TRY(rgb_to_rgba_launch(rgb_dev, reinterpret_cast<uchar4*>(c->rgba.p), (int)npix, st));
+  if (flags & FP_FRAME_FILTER_DEPTH) {
+    // estimater.py:173-174: erode_depth(radius=2) then bilateral_filter_depth(radius=2)
+    FP_TRY(erode_depth_launch(depth_dev, reinterpret_cast<float*>(c->depth_a.p), H, W, 2, 0.001f, 0.8f, 100.f, st));
+    FP_TRY(bilateral_depth_launch(reinterpret_cast<const float*>(c->depth_a.p), reinterpret_cast<float*>(c->depth_b.p), H,
+                                  W, 2, 100.f, 2.f, 100000.f, st));
+  } else {
+    FP_CUDA_OK(cudaMemcpyAsync(c->depth_b.p, depth_dev, npix * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  c->depth_cur = reinterpret_cast<const float*>(c->depth_b.p);
+  FP_TRY(depth_to_xyz_launch(c->depth_cur, reinterpret_cast<float4*>(c->xyz.p), H, W, c->K[0], c->K[4], c->K[2], c->K[5],
+                             zfar, st));
+  return 0;
+}
+
+// frame buffers + intrinsics; bumps the epoch when a by-value kernel parameter changes
+static int prepare_frame(fp_ctx* c, const float* K, int H, int W, bool need_raw) {
+  const size_t npix = (size_t)H * W;
+  FP_TRY(dev_alloc(c->epoch, c->rgba, npix * 4));
+  FP_TRY(dev_alloc(c->epoch, c->depth_a, npix * 4));
+  FP_TRY(dev_alloc(c->epoch, c->depth_b, npix * 4));
+  FP_TRY(dev_alloc(c->epoch, c->xyz, npix * 16));
+  if (need_raw) {
+    FP_TRY(dev_alloc(c->epoch, c->rgb_raw, npix * 3));
+    FP_TRY(dev_alloc(c->epoch, c->depth_raw, npix * 4));
+  }
+  bool same = (c->H == H && c->W == W);
+  for (int i = 0; i < 9; ++i) same = same && (c->K[i] == K[i]);
+  if (!same) ++c->epoch;  // intrinsics / frame size are by-value kernel parameters
+  for (int i = 0; i < 9; ++i) c->K[i] = K[i];
+  c->H = H;
+  c->W = W;
+  return 0;
+}
+
+static int refine_body(fp_ctx* c, int N, int iterations, cudaStream_t s2) {
+  float* cur = reinterpret_cast<float*>(c->poses_a.p);
+  float* nxt = reinterpret_cast<float*>(c->poses_b.p);
+  const float* ho = reinterpret_cast<const float*>(c->head_out.p);
+  for (int it = 0; it < iterations; ++it) {
+    FP_TRY(make_crops(c, cur, N, 0, nullptr, nullptr, nullptr, s2));
+    FP_TRY(run_encoder(c, c->net[0], reinterpret_cast<const __half*>(c->crops.p), N, s2));
+    FP_TRY(run_refine_heads(c, c->net[0], N, s2));
+    const bool last = it == iterations - 1;
+    FP_TRY(pose_update_launch(cur, ho, ho + (size_t)N * 3, nxt, last ? reinterpret_cast<float*>(c->lt_buf.p) : nullptr,
+                              last ? reinterpret_cast<float*>(c->lr_buf.p) : nullptr, N, c->diameter / 2.0f,
+                              c->rot_normalizer, s2));
+    float* t = cur;
+    cur = nxt;
+    nxt = t;
+  }
   return 0;
 }
 
@@ -392,9 +507,23 @@ static int run_graphed(fp_ctx* c, int kind, int N, int iters, cudaStream_t st, B
 
 using namespace fp;
 
+// every entry point: exceptions never cross the C boundary, the context's device is current inside
+#define FP_API_BEGIN try {
+#define FP_API_END                                                        \
+  }                                                                       \
+  catch (const std::exception& e) {                                       \
+    fp::set_last_error("%s: exception: %s", __func__, e.what());          \
+    return -3;                                                            \
+  }                                                                       \
+  catch (...) {                                                           \
+    fp::set_last_error("%s: unknown exception", __func__);                \
+    return -3;                                                            \
+  }
+
 extern "C" {
 
 int fp_create(fp_ctx** out) {
+  FP_API_BEGIN
   if (!out) {
     set_last_error("fp_create: null output");
     return -1;
@@ -408,44 +537,59 @@ int fp_create(fp_ctx** out) {
   c->device = dev;
   const char* ng = getenv("FPOSE_NO_GRAPH");
   c->use_graphs = !(ng && ng[0] == '1');
+  const char* nc = getenv("FPOSE_NO_CULL");
+  c->cull_backfaces = !(nc && nc[0] == '1');
   *out = c;
   return 0;
+  FP_API_END
 }
 
 int fp_destroy(fp_ctx* c) {
+  FP_API_BEGIN
   if (!c) return 0;
+  DeviceGuard dg(c->device);
+  cudaDeviceSynchronize();
   for (auto& net : c->net)
     for (auto& kv : net.t) cudaFree(kv.second.p);
-  DevBuf* bufs[] = {&c->vpos, &c->vnrm, &c->vuv, &c->vcol, &c->faces, &c->tex, &c->rgb_raw, &c->rgba, &c->depth_raw,
-                    &c->depth_a, &c->depth_b, &c->xyz, &c->crops, &c->act0, &c->a1, &c->a2, &c->a3, &c->ab0, &c->ab1,
-                    &c->ab2, &c->c0, &c->c1, &c->c2, &c->tok, &c->qkv, &c->att, &c->x1pre, &c->x1, &c->ff, &c->x2pre,
-                    &c->head_out, &c->poses_a, &c->poses_b, &c->feats, &c->tail_qkv, &c->tail_attn, &c->tail_proj,
-                    &c->scores, &c->best};
+  DevBuf* bufs[] = {&c->vpos, &c->vnrm, &c->vatt, &c->faces, &c->meshlets, &c->ml_verts, &c->ml_tris, &c->tex, &c->rgb_raw,
+                    &c->rgba, &c->depth_raw, &c->depth_a, &c->depth_b, &c->xyz, &c->crops, &c->act0, &c->a1, &c->a2,
+                    &c->a3, &c->ab0, &c->ab1, &c->ab2, &c->c0, &c->c1, &c->c2, &c->tok, &c->qkv, &c->att, &c->x1pre,
+                    &c->x1, &c->ff, &c->x2pre, &c->head_out, &c->poses_a, &c->poses_b, &c->feats, &c->tail_qkv,
+                    &c->tail_attn, &c->tail_proj, &c->scores, &c->best, &c->lt_buf, &c->lr_buf, &c->feat_buf,
+                    &c->pose_stage, &c->mask_buf, &c->mask_stats, &c->crop_stats, &c->track_pose};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (auto& kv : c->graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
-  DevBuf* more[] = {&c->lt_buf, &c->lr_buf, &c->feat_buf, &c->pose_stage, &c->vtx_a, &c->vtx_b, &c->win_buf, &c->mask_buf, &c->mask_stats, &c->tab_buf, &c->zbuf};
-  for (DevBuf* b : more)
-    if (b->p) cudaFree(b->p);
+  if (c->stage_rgb) cudaFreeHost(c->stage_rgb);
+  if (c->stage_depth) cudaFreeHost(c->stage_depth);
+  if (c->stage_pose) cudaFreeHost(c->stage_pose);
   delete c;
   return 0;
+  FP_API_END
 }
 
-int fp_set_config(fp_ctx* c, float crop_ratio, float rot_normalizer) {
+int fp_set_config(fp_ctx* c, int which, float crop_ratio, float rot_normalizer) {
+  FP_API_BEGIN
   FP_REQUIRE(c, "null ctx");
-  c->crop_ratio = crop_ratio;
-  c->rot_normalizer = rot_normalizer;
-  ++g_epoch;
+  FP_REQUIRE(which == 0 || which == 1, "fp_set_config: which must be 0 (refiner) or 1 (scorer)");
+  FP_REQUIRE(crop_ratio > 0.f, "fp_set_config: crop_ratio must be positive");
+  c->crop_ratio[which] = crop_ratio;
+  if (which == 0) c->rot_normalizer = rot_normalizer;
+  ++c->epoch;
   return 0;
+  FP_API_END
 }
 
 int fp_load_network(fp_ctx* c, int which, const fp_tensor_t* tensors, int n) {
+  FP_API_BEGIN
   FP_REQUIRE(c && tensors, "fp_load_network: null argument");
   FP_REQUIRE(which == 0 || which == 1, "fp_load_network: which must be 0 (refiner) or 1 (scorer)");
+  DeviceGuard dg(c->device);
   Net& net = c->net[which];
-  ++g_epoch;
+  ++c->epoch;
+  FP_CUDA_OK(cudaDeviceSynchronize());
   for (auto& kv : net.t) cudaFree(kv.second.p);
   net.t.clear();
   net.loaded = false;
@@ -458,6 +602,8 @@ int fp_load_network(fp_ctx* c, int which, const fp_tensor_t* tensors, int n) {
     const size_t bytes = (size_t)t.numel * (t.dtype == 1 ? 2 : 4);
     FP_CUDA_OK(cudaMalloc(&d.p, bytes));
     FP_CUDA_OK(cudaMemcpy(d.p, t.data, bytes, cudaMemcpyHostToDevice));
+    auto old = net.t.find(t.name);
+    if (old != net.t.end()) cudaFree(old->second.p);
     net.t[t.name] = d;
     if (which == 1 && std::string(t.name) == "lin.b" && t.dtype == 0) c->lin_b_host = *reinterpret_cast<const float*>(t.data);
   }
@@ -501,25 +647,32 @@ int fp_load_network(fp_ctx* c, int which, const fp_tensor_t* tensors, int n) {
   }
   net.loaded = true;
   return 0;
+  FP_API_END
 }
 
 int fp_set_mesh(fp_ctx* c, int V, int F, const float* pos, const float* nrm, const float* uv, const float* vcol,
                 const int* faces, const unsigned char* tex_rgb, int Ht, int Wt, float diameter) {
+  FP_API_BEGIN
   FP_REQUIRE(c && pos && nrm && faces, "fp_set_mesh: null argument");
   FP_REQUIRE(V > 0 && F > 0 && diameter > 0.f, "fp_set_mesh: empty mesh");
   FP_REQUIRE((uv && tex_rgb && Ht > 0 && Wt > 0) || vcol, "fp_set_mesh: need (uv + texture) or vertex colours");
   for (int i = 0; i < 3 * F; ++i) FP_REQUIRE(faces[i] >= 0 && faces[i] < V, "fp_set_mesh: face index out of range");
+  DeviceGuard dg(c->device);
+  // graphs captured for the previous mesh may still be running on the caller's stream
+  FP_CUDA_OK(cudaDeviceSynchronize());
   c->has_mesh = false;
-  FP_TRY(dev_alloc(c->vpos, (size_t)V * 12));
-  FP_TRY(dev_alloc(c->vnrm, (size_t)V * 12));
-  FP_TRY(dev_alloc(c->faces, (size_t)F * 12));
-  FP_CUDA_OK(cudaMemcpy(c->vpos.p, pos, (size_t)V * 12, cudaMemcpyHostToDevice));
-  FP_CUDA_OK(cudaMemcpy(c->vnrm.p, nrm, (size_t)V * 12, cudaMemcpyHostToDevice));
-  FP_CUDA_OK(cudaMemcpy(c->faces.p, faces, (size_t)F * 12, cudaMemcpyHostToDevice));
-  c->has_tex = (uv && tex_rgb);
-  if (c->has_tex) {
-    FP_TRY(dev_alloc(c->vuv, (size_t)V * 8));
-    FP_CUDA_OK(cudaMemcpy(c->vuv.p, uv, (size_t)V * 8, cudaMemcpyHostToDevice));
+  const bool has_tex = (uv && tex_rgb);
+  MeshHost mh;
+  FP_TRY(build_mesh_host(V, F, pos, nrm, has_tex ? uv : vcol, has_tex ? 2 : 3, faces, mh));
+  FP_TRY(upload(c->epoch, c->vpos, mh.vpos));
+  FP_TRY(upload(c->epoch, c->vnrm, mh.vnrm));
+  FP_TRY(upload(c->epoch, c->vatt, mh.vatt));
+  FP_TRY(upload(c->epoch, c->faces, mh.faces));
+  FP_TRY(upload(c->epoch, c->meshlets, mh.meshlets));
+  FP_TRY(upload(c->epoch, c->ml_verts, mh.ml_verts));
+  FP_TRY(upload(c->epoch, c->ml_tris, mh.ml_tris));
+  c->has_tex = has_tex;
+  if (has_tex) {
     std::vector<unsigned char> rgba((size_t)Ht * Wt * 4);
     for (size_t i = 0; i < (size_t)Ht * Wt; ++i) {
       rgba[4 * i] = tex_rgb[3 * i];
@@ -527,105 +680,141 @@ int fp_set_mesh(fp_ctx* c, int V, int F, const float* pos, const float* nrm, con
       rgba[4 * i + 2] = tex_rgb[3 * i + 2];
       rgba[4 * i + 3] = 255;
     }
-    FP_TRY(dev_alloc(c->tex, rgba.size()));
-    FP_CUDA_OK(cudaMemcpy(c->tex.p, rgba.data(), rgba.size(), cudaMemcpyHostToDevice));
+    FP_TRY(upload(c->epoch, c->tex, rgba));
     c->Ht = Ht;
     c->Wt = Wt;
-  } else {
-    FP_TRY(dev_alloc(c->vcol, (size_t)V * 12));
-    FP_CUDA_OK(cudaMemcpy(c->vcol.p, vcol, (size_t)V * 12, cudaMemcpyHostToDevice));
   }
   c->V = V;
   c->F = F;
+  c->n_meshlets = (int)mh.meshlets.size();
+  c->front_sign = mh.front_sign;
+  c->mesh_closed = mh.closed;
+  for (int i = 0; i < 4; ++i) c->mesh_bs[i] = mh.bs[i];
   c->diameter = diameter;
   c->has_mesh = true;
-  ++g_epoch;
+  ++c->epoch;
   return 0;
+  FP_API_END
+}
+
+int fp_mesh_info(fp_ctx* c, int* info) {
+  FP_API_BEGIN
+  FP_REQUIRE(c && info && c->has_mesh, "fp_mesh_info: no mesh");
+  info[0] = c->n_meshlets;
+  info[1] = c->mesh_closed;
+  info[2] = c->cull_backfaces ? c->front_sign : 0;
+  info[3] = c->V;
+  info[4] = c->F;
+  return 0;
+  FP_API_END
 }
 
 int fp_set_frame(fp_ctx* c, const unsigned char* rgb, const float* depth, const float* K, int H, int W, int flags,
                  float zfar, void* stream) {
+  FP_API_BEGIN
   FP_REQUIRE(c && rgb && depth && K, "fp_set_frame: null argument");
   FP_REQUIRE(H > 0 && W > 0, "fp_set_frame: empty frame");
+  DeviceGuard dg(c->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t npix = (size_t)H * W;
   c->has_frame = false;
-  FP_TRY(dev_alloc(c->rgba, npix * 4));
-  FP_TRY(dev_alloc(c->depth_a, npix * 4));
-  FP_TRY(dev_alloc(c->depth_b, npix * 4));
-  FP_TRY(dev_alloc(c->xyz, npix * 12));
+  const bool on_dev = (flags & FP_FRAME_ON_DEVICE) != 0;
+  FP_TRY(prepare_frame(c, K, H, W, !on_dev));
   const unsigned char* rgb_dev = rgb;
   const float* depth_dev = depth;
-  if (!(flags & FP_FRAME_ON_DEVICE)) {
-    FP_TRY(dev_alloc(c->rgb_raw, npix * 3));
-    FP_TRY(dev_alloc(c->depth_raw, npix * 4));
+  if (!on_dev) {
     FP_CUDA_OK(cudaMemcpyAsync(c->rgb_raw.p, rgb, npix * 3, cudaMemcpyHostToDevice, st));
     FP_CUDA_OK(cudaMemcpyAsync(c->depth_raw.p, depth, npix * 4, cudaMemcpyHostToDevice, st));
     rgb_dev = reinterpret_cast<const unsigned char*>(c->rgb_raw.p);
     depth_dev = reinterpret_cast<const float*>(c->depth_raw.p);
   }
-  bool same = (c->H == H && c->W == W);
-  for (int i = 0; i < 9; ++i) same = same && (c->K[i] == K[i]);
-  if (!same) ++g_epoch;  // intrinsics / frame size are by-value kernel parameters
-  for (int i = 0; i < 9; ++i) c->K[i] = K[i];
-  c->H = H;
-  c->W = W;
-  FP_TRY(rgb_to_rgba_launch(rgb_dev, reinterpret_cast<uchar4*>(c->rgba.p), (int)npix, st));
-  if (flags & FP_FRAME_FILTER_DEPTH) {
-    // estimater.py:173-174: erode_depth(radius=2) then bilateral_filter_depth(radius=2)
-    FP_TRY(erode_depth_launch(depth_dev, reinterpret_cast<float*>(c->depth_a.p), H, W, 2, 0.001f, 0.8f, 100.f, st));
-    FP_TRY(bilateral_depth_launch(reinterpret_cast<const float*>(c->depth_a.p), reinterpret_cast<float*>(c->depth_b.p), H,
-                                  W, 2, 100.f, 2.f, 100000.f, st));
-    c->depth_cur = reinterpret_cast<const float*>(c->depth_b.p);
-  } else {
-    FP_CUDA_OK(cudaMemcpyAsync(c->depth_b.p, depth_dev, npix * 4, cudaMemcpyDeviceToDevice, st));
-    c->depth_cur = reinterpret_cast<const float*>(c->depth_b.p);
-  }
-  FP_TRY(depth_to_xyz_launch(c->depth_cur, reinterpret_cast<float*>(c->xyz.p), H, W, K[0], K[4], K[2], K[5], zfar, st));
+  FP_TRY(set_frame_launches(c, rgb_dev, depth_dev, flags, zfar, st));
   c->has_frame = true;
   return 0;
+  FP_API_END
+}
+
+int fp_set_xyz_map(fp_ctx* c, const float* xyz, void* stream) {
+  FP_API_BEGIN
+  FP_REQUIRE(c && xyz, "fp_set_xyz_map: null argument");
+  FP_REQUIRE(c->has_frame, "fp_set_xyz_map: no frame (call fp_set_frame first)");
+  DeviceGuard dg(c->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // [H][W][3] (host or device) -> the float4-per-pixel layout the crop kernel samples
+  FP_CUDA_OK(cudaMemcpy2DAsync(c->xyz.p, 16, xyz, 12, 12, (size_t)c->H * c->W, cudaMemcpyDefault, st));
+  return 0;
+  FP_API_END
 }
 
 int fp_get_depth(fp_ctx* c, float* depth_out_dev, float* xyz_out_dev, void* stream) {
+  FP_API_BEGIN
   FP_REQUIRE(c && c->has_frame, "fp_get_depth: no frame");
+  DeviceGuard dg(c->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t npix = (size_t)c->H * c->W;
   if (depth_out_dev) FP_CUDA_OK(cudaMemcpyAsync(depth_out_dev, c->depth_cur, npix * 4, cudaMemcpyDeviceToDevice, st));
-  if (xyz_out_dev) FP_CUDA_OK(cudaMemcpyAsync(xyz_out_dev, c->xyz.p, npix * 12, cudaMemcpyDeviceToDevice, st));
+  // internal layout is float4 per pixel; the hook returns the reference's [H][W][3]
+  if (xyz_out_dev)
+    FP_CUDA_OK(cudaMemcpy2DAsync(xyz_out_dev, 12, c->xyz.p, 16, 12, npix, cudaMemcpyDeviceToDevice, st));
   return 0;
+  FP_API_END
 }
 
 int fp_start_poses(fp_ctx* c, const unsigned char* mask, int mask_on_device, const float* rot_grid, int N, float* poses_out,
                    float* info_out, void* stream) {
+  FP_API_BEGIN
   FP_REQUIRE(c && mask && rot_grid && poses_out && info_out && N >= 0, "fp_start_poses: bad argument");
   FP_REQUIRE(c->has_frame, "fp_start_poses: no frame (call fp_set_frame first)");
+  DeviceGuard dg(c->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t npix = (size_t)c->H * c->W;
   const unsigned char* mdev = mask;
   if (!mask_on_device) {
-    FP_TRY(dev_alloc(c->mask_buf, npix));
+    FP_TRY(dev_alloc(c->epoch, c->mask_buf, npix));
     FP_CUDA_OK(cudaMemcpyAsync(c->mask_buf.p, mask, npix, cudaMemcpyHostToDevice, st));
     mdev = reinterpret_cast<const unsigned char*>(c->mask_buf.p);
   }
-  FP_TRY(dev_alloc(c->mask_stats, 64));
+  FP_TRY(dev_alloc(c->epoch, c->mask_stats, 64));
   return start_poses_launch(c->depth_cur, mdev, c->H, c->W, c->K[0], c->K[4], c->K[2], c->K[5], rot_grid, N,
                             reinterpret_cast<unsigned int*>(c->mask_stats.p), poses_out, info_out, st);
+  FP_API_END
 }
 
 int fp_make_crops(fp_ctx* c, const float* poses, int N, int mode, void* crops_out, float* dbg_out, float* win_out,
                   void* stream) {
+  FP_API_BEGIN
   FP_REQUIRE(c && poses && N >= 0, "fp_make_crops: bad argument");
+  FP_REQUIRE(mode == 0 || mode == 1, "fp_make_crops: mode must be 0 (refiner) or 1 (scorer)");
+  DeviceGuard dg(c->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (N == 0) return 0;
   FP_TRY(ensure_capacity(c, N));
-  FP_TRY(make_crops(c, poses, N, mode, dbg_out, win_out, st));
+  FP_TRY(make_crops(c, poses, N, mode, dbg_out, win_out, nullptr, st));
   if (crops_out) FP_TRY(crops_export(c, crops_out, N, st));
   return 0;
+  FP_API_END
+}
+
+int fp_crop_stats(fp_ctx* c, const float* poses, int N, int mode, int* stats_out_host, void* stream) {
+  FP_API_BEGIN
+  FP_REQUIRE(c && poses && stats_out_host && N > 0, "fp_crop_stats: bad argument");
+  DeviceGuard dg(c->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  FP_TRY(ensure_capacity(c, N));
+  FP_TRY(dev_alloc(c->epoch, c->crop_stats, 16));
+  FP_CUDA_OK(cudaMemsetAsync(c->crop_stats.p, 0, 16, st));
+  FP_TRY(make_crops(c, poses, N, mode, nullptr, nullptr, reinterpret_cast<int*>(c->crop_stats.p), st));
+  FP_CUDA_OK(cudaMemcpyAsync(stats_out_host, c->crop_stats.p, 16, cudaMemcpyDeviceToHost, st));
+  FP_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+  FP_API_END
 }
 
 int fp_op_refine_net(fp_ctx* c, const void* crops, int N, float* trans_out, float* rot_out, void* stream) {
+  FP_API_BEGIN
   FP_REQUIRE(c && crops && trans_out && rot_out, "fp_op_refine_net: null argument");
   FP_REQUIRE(c->net[0].loaded, "refiner weights not loaded");
+  DeviceGuard dg(c->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (N == 0) return 0;
   FP_TRY(ensure_capacity(c, N));
@@ -636,11 +825,14 @@ int fp_op_refine_net(fp_ctx* c, const void* crops, int N, float* trans_out, floa
   FP_CUDA_OK(cudaMemcpyAsync(trans_out, ho, (size_t)N * 12, cudaMemcpyDeviceToDevice, st));
   FP_CUDA_OK(cudaMemcpyAsync(rot_out, ho + (size_t)N * 3, (size_t)N * 12, cudaMemcpyDeviceToDevice, st));
   return 0;
+  FP_API_END
 }
 
 int fp_op_score_feats(fp_ctx* c, const void* crops, int N, float* feats_out, void* stream) {
+  FP_API_BEGIN
   FP_REQUIRE(c && crops && feats_out, "fp_op_score_feats: null argument");
   FP_REQUIRE(c->net[1].loaded, "scorer weights not loaded");
+  DeviceGuard dg(c->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (N == 0) return 0;
   FP_TRY(ensure_capacity(c, N));
@@ -648,11 +840,14 @@ int fp_op_score_feats(fp_ctx* c, const void* crops, int N, float* feats_out, voi
   FP_TRY(run_encoder(c, c->net[1], reinterpret_cast<const __half*>(c->crops.p), N, st));
   FP_TRY(run_score_feats(c, c->net[1], N, feats_out, st));
   return 0;
+  FP_API_END
 }
 
 int fp_op_tokens(fp_ctx* c, int which, const void* crops, int N, void* tokens_out, void* stream) {
+  FP_API_BEGIN
   FP_REQUIRE(c && crops && tokens_out && (which == 0 || which == 1), "fp_op_tokens: bad argument");
   FP_REQUIRE(c->net[which].loaded, "weights not loaded");
+  DeviceGuard dg(c->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (N == 0) return 0;
   FP_TRY(ensure_capacity(c, N));
@@ -660,37 +855,23 @@ int fp_op_tokens(fp_ctx* c, int which, const void* crops, int N, void* tokens_ou
   FP_TRY(run_encoder(c, c->net[which], reinterpret_cast<const __half*>(c->crops.p), N, st));
   FP_CUDA_OK(cudaMemcpyAsync(tokens_out, c->tok.p, (size_t)N * T * 512 * 2, cudaMemcpyDeviceToDevice, st));
   return 0;
+  FP_API_END
 }
 
 int fp_refine(fp_ctx* c, const float* poses_in, int N, int iterations, float* poses_out, float* last_trans,
               float* last_rot, void* stream) {
+  FP_API_BEGIN
   FP_REQUIRE(c && poses_in && poses_out && N >= 0 && iterations >= 0, "fp_refine: bad argument");
   FP_REQUIRE(c->net[0].loaded, "refiner weights not loaded");
+  FP_REQUIRE(c->has_mesh && c->has_frame, "fp_refine: needs fp_set_mesh and fp_set_frame first");
+  DeviceGuard dg(c->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (N == 0) return 0;
   FP_TRY(ensure_capacity(c, N));
   float* pa = reinterpret_cast<float*>(c->poses_a.p);
   float* pb = reinterpret_cast<float*>(c->poses_b.p);
   FP_CUDA_OK(cudaMemcpyAsync(pa, poses_in, (size_t)N * 64, cudaMemcpyDeviceToDevice, st));
-  auto body = [&](cudaStream_t s2) -> int {
-    float* cur = pa;
-    float* nxt = pb;
-    const float* ho = reinterpret_cast<const float*>(c->head_out.p);
-    for (int it = 0; it < iterations; ++it) {
-      FP_TRY(make_crops(c, cur, N, 0, nullptr, nullptr, s2));
-      FP_TRY(run_encoder(c, c->net[0], reinterpret_cast<const __half*>(c->crops.p), N, s2));
-      FP_TRY(run_refine_heads(c, c->net[0], N, s2));
-      const bool last = it == iterations - 1;
-      FP_TRY(pose_update_launch(cur, ho, ho + (size_t)N * 3, nxt, last ? reinterpret_cast<float*>(c->lt_buf.p) : nullptr,
-                                last ? reinterpret_cast<float*>(c->lr_buf.p) : nullptr, N, c->diameter / 2.0f,
-                                c->rot_normalizer, s2));
-      float* t = cur;
-      cur = nxt;
-      nxt = t;
-    }
-    return 0;
-  };
-  FP_TRY(run_graphed(c, 0, N, iterations, st, body));
+  FP_TRY(run_graphed(c, 0, N, iterations, st, [&](cudaStream_t s2) -> int { return refine_body(c, N, iterations, s2); }));
   const float* fin = (iterations % 2 == 0) ? pa : pb;
   FP_CUDA_OK(cudaMemcpyAsync(poses_out, fin, (size_t)N * 64, cudaMemcpyDeviceToDevice, st));
   if (iterations > 0) {
@@ -698,11 +879,15 @@ int fp_refine(fp_ctx* c, const float* poses_in, int N, int iterations, float* po
     if (last_rot) FP_CUDA_OK(cudaMemcpyAsync(last_rot, c->lr_buf.p, (size_t)N * 36, cudaMemcpyDeviceToDevice, st));
   }
   return 0;
+  FP_API_END
 }
 
 int fp_score_features(fp_ctx* c, const float* poses, int N, float* feats_out, void* stream) {
+  FP_API_BEGIN
   FP_REQUIRE(c && poses && feats_out && N >= 0, "fp_score_features: bad argument");
   FP_REQUIRE(c->net[1].loaded, "scorer weights not loaded");
+  FP_REQUIRE(c->has_mesh && c->has_frame, "fp_score_features: needs fp_set_mesh and fp_set_frame first");
+  DeviceGuard dg(c->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (N == 0) return 0;
   FP_TRY(ensure_capacity(c, N));
@@ -710,19 +895,24 @@ int fp_score_features(fp_ctx* c, const float* poses, int N, float* feats_out, vo
   float* fb = reinterpret_cast<float*>(c->feat_buf.p);
   FP_CUDA_OK(cudaMemcpyAsync(ps, poses, (size_t)N * 64, cudaMemcpyDeviceToDevice, st));
   auto body = [&](cudaStream_t s2) -> int {
-    FP_TRY(make_crops(c, ps, N, 1, nullptr, nullptr, s2));
+    FP_TRY(make_crops(c, ps, N, 1, nullptr, nullptr, nullptr, s2));
     FP_TRY(run_encoder(c, c->net[1], reinterpret_cast<const __half*>(c->crops.p), N, s2));
     FP_TRY(run_score_feats(c, c->net[1], N, fb, s2));
     return 0;
   };
   FP_TRY(run_graphed(c, 1, N, 0, st, body));
-  FP_CUDA_OK(cudaMemcpyAsync(feats_out, fb, (size_t)N * 2048, cudaMemcpyDeviceToDevice, st));
+  // feats_out may live on another GPU of the same process (peer access enabled by fp_group_create): the gather of
+  // the sharded register is this copy, device to device over NVLink
+  FP_CUDA_OK(cudaMemcpyAsync(feats_out, fb, (size_t)N * 2048, cudaMemcpyDefault, st));
   return 0;
+  FP_API_END
 }
 
 int fp_score_tail(fp_ctx* c, const float* feats, int L, float* scores_out, int* best_out, void* stream) {
+  FP_API_BEGIN
   FP_REQUIRE(c && feats && scores_out && L >= 0, "fp_score_tail: bad argument");
   FP_REQUIRE(c->net[1].loaded, "scorer weights not loaded");
+  DeviceGuard dg(c->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (L == 0) return 0;
   FP_TRY(ensure_tail(c, L));
@@ -743,19 +933,25 @@ int fp_score_tail(fp_ctx* c, const float* feats, int L, float* scores_out, int* 
   p.scores = scores_out;
   p.best = best_out;
   return score_tail_launch(p, st);
+  FP_API_END
 }
 
 int fp_score(fp_ctx* c, const float* poses, int N, float* scores_out, int* best_out, void* stream) {
+  FP_API_BEGIN
   FP_REQUIRE(c && poses && scores_out && N >= 0, "fp_score: bad argument");
   if (N == 0) return 0;
+  DeviceGuard dg(c->device);
   FP_TRY(ensure_capacity(c, N));
   FP_TRY(fp_score_features(c, poses, N, reinterpret_cast<float*>(c->feats.p), stream));
   return fp_score_tail(c, reinterpret_cast<const float*>(c->feats.p), N, scores_out, best_out, stream);
+  FP_API_END
 }
 
 int fp_register(fp_ctx* c, const float* poses_host, int N, int iterations, float* poses_out_host, float* scores_out_host,
                 int* best_out_host, void* stream) {
+  FP_API_BEGIN
   FP_REQUIRE(c && poses_host && poses_out_host && scores_out_host && best_out_host && N > 0, "fp_register: bad argument");
+  DeviceGuard dg(c->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   FP_TRY(ensure_capacity(c, N));
   FP_TRY(ensure_tail(c, N));
@@ -773,20 +969,83 @@ int fp_register(fp_ctx* c, const float* poses_host, int N, int iterations, float
   FP_CUDA_OK(cudaMemcpyAsync(best_out_host, c->best.p, 4, cudaMemcpyDeviceToHost, st));
   FP_CUDA_OK(cudaStreamSynchronize(st));
   return 0;
+  FP_API_END
+}
+
+int fp_track(fp_ctx* c, const unsigned char* rgb_host, const float* depth_host, const float* K, int H, int W,
+             const float* pose_in_dev, int iterations, float* pose_out_dev, float* pose_out_host, void* stream) {
+  FP_API_BEGIN
+  FP_REQUIRE(c && rgb_host && depth_host && K && H > 0 && W > 0 && iterations >= 0, "fp_track: bad argument");
+  FP_REQUIRE(c->net[0].loaded, "refiner weights not loaded");
+  FP_REQUIRE(c->has_mesh, "fp_track: no mesh");
+  DeviceGuard dg(c->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t npix = (size_t)H * W;
+  FP_TRY(ensure_capacity(c, 1));
+  FP_TRY(prepare_frame(c, K, H, W, true));
+  FP_TRY(dev_alloc(c->epoch, c->track_pose, 64));
+  if (c->stage_npix < npix) {
+    if (c->stage_rgb) cudaFreeHost(c->stage_rgb);
+    if (c->stage_depth) cudaFreeHost(c->stage_depth);
+    c->stage_rgb = c->stage_depth = nullptr;
+    c->stage_npix = 0;
+    FP_CUDA_OK(cudaMallocHost(&c->stage_rgb, npix * 3));
+    FP_CUDA_OK(cudaMallocHost(&c->stage_depth, npix * 4));
+    c->stage_npix = npix;
+    ++c->epoch;  // the graph's copy nodes hold these addresses
+  }
+  if (!c->stage_pose) FP_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&c->stage_pose), 64));
+  if (pose_in_dev) {
+    FP_CUDA_OK(cudaMemcpyAsync(c->track_pose.p, pose_in_dev, 64, cudaMemcpyDeviceToDevice, st));
+  } else {
+    FP_REQUIRE(c->track_valid, "fp_track: no previous pose in this context: pass pose_in");
+  }
+  // the previous frame's graph has finished (fp_track synchronises), so the staging buffers are free
+  memcpy(c->stage_rgb, rgb_host, npix * 3);
+  memcpy(c->stage_depth, depth_host, npix * 4);
+  c->has_frame = false;
+  float* pa = reinterpret_cast<float*>(c->poses_a.p);
+  float* pb = reinterpret_cast<float*>(c->poses_b.p);
+  auto body = [&](cudaStream_t s2) -> int {
+    // estimater.py:250-268 in one launch sequence: upload, erode + bilateral, depth2xyzmap_batch(zfar=inf), K refiner passes
+    FP_CUDA_OK(cudaMemcpyAsync(c->rgb_raw.p, c->stage_rgb, npix * 3, cudaMemcpyHostToDevice, s2));
+    FP_CUDA_OK(cudaMemcpyAsync(c->depth_raw.p, c->stage_depth, npix * 4, cudaMemcpyHostToDevice, s2));
+    FP_TRY(set_frame_launches(c, reinterpret_cast<const unsigned char*>(c->rgb_raw.p),
+                              reinterpret_cast<const float*>(c->depth_raw.p), FP_FRAME_FILTER_DEPTH, INFINITY, s2));
+    FP_CUDA_OK(cudaMemcpyAsync(pa, c->track_pose.p, 64, cudaMemcpyDeviceToDevice, s2));
+    c->has_frame = true;
+    FP_TRY(refine_body(c, 1, iterations, s2));
+    const float* fin = (iterations % 2 == 0) ? pa : pb;
+    FP_CUDA_OK(cudaMemcpyAsync(c->track_pose.p, fin, 64, cudaMemcpyDeviceToDevice, s2));
+    FP_CUDA_OK(cudaMemcpyAsync(c->stage_pose, fin, 64, cudaMemcpyDeviceToHost, s2));
+    return 0;
+  };
+  FP_TRY(run_graphed(c, 2, 1, iterations, st, body));
+  c->has_frame = true;
+  c->track_valid = true;
+  if (pose_out_dev) FP_CUDA_OK(cudaMemcpyAsync(pose_out_dev, c->track_pose.p, 64, cudaMemcpyDeviceToDevice, st));
+  FP_CUDA_OK(cudaStreamSynchronize(st));
+  if (pose_out_host) memcpy(pose_out_host, c->stage_pose, 64);
+  return 0;
+  FP_API_END
 }
 
 int fp_op_depth_filter(const float* depth_dev, float* out_dev, int H, int W, int which, void* stream) {
+  FP_API_BEGIN
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   FP_REQUIRE(depth_dev && out_dev && H > 0 && W > 0, "fp_op_depth_filter: bad argument");
   if (which == 0) return erode_depth_launch(depth_dev, out_dev, H, W, 2, 0.001f, 0.8f, 100.f, st);
   return bilateral_depth_launch(depth_dev, out_dev, H, W, 2, 100.f, 2.f, 100000.f, st);
+  FP_API_END
 }
 
 int fp_op_pose_update(const float* poses_in, const float* trans, const float* rot, float* poses_out, int N,
                       float mesh_diameter, float rot_normalizer, void* stream) {
+  FP_API_BEGIN
   FP_REQUIRE(poses_in && trans && rot && poses_out, "fp_op_pose_update: null argument");
   return pose_update_launch(poses_in, trans, rot, poses_out, nullptr, nullptr, N, mesh_diameter / 2.0f, rot_normalizer,
                             reinterpret_cast<cudaStream_t>(stream));
+  FP_API_END
 }
 
 }  // extern "C"

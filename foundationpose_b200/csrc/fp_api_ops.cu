@@ -3,7 +3,10 @@
 #include "../../include/fpose.h"
 #include "fp_common.cuh"
 #include "fp_attn.cuh"
+#include "fp_crop.cuh"
 #include "fp_gemm.cuh"
+
+#include <vector>
 
 namespace fp {
 const char* get_last_error();
@@ -14,7 +17,7 @@ extern "C" {
 
 const char* fp_last_error(void) { return fp::get_last_error(); }
 
-unsigned long long fp_launch_count(void) { return fp::g_launch_count; }
+unsigned long long fp_launch_count(void) { return fp::launch_count(); }
 
 int fp_prof_enable(int on) {
   fp::g_prof_on = on != 0;
@@ -27,6 +30,58 @@ int fp_prof_collect(int kind, double* total_ms, double* total_work, int* launche
     return -1;
   }
   return fp::prof_collect(kind, total_ms, total_work, launches);
+}
+
+int fp_op_build_meshlets(int V, int F, const float* pos, const int* faces, int* info, int* face_of_tri_out) {
+  try {
+    if (!pos || !faces || !info || V <= 0 || F <= 0) {
+      fp::set_last_error("fp_op_build_meshlets: bad argument");
+      return -1;
+    }
+    for (int i = 0; i < 3 * F; ++i)
+      if (faces[i] < 0 || faces[i] >= V) {
+        fp::set_last_error("fp_op_build_meshlets: face index out of range");
+        return -1;
+      }
+    std::vector<float> nrm((size_t)V * 3, 0.f), att((size_t)V * 3, 0.f);
+    fp::MeshHost mh;
+    int rc = fp::build_mesh_host(V, F, pos, nrm.data(), att.data(), 3, faces, mh);
+    if (rc) return rc;
+    int max_t = 0, max_v = 0, total = 0;
+    for (const fp::Meshlet& m : mh.meshlets) {
+      max_t = m.n_tris > max_t ? m.n_tris : max_t;
+      max_v = m.n_verts > max_v ? m.n_verts : max_v;
+      total += m.n_tris;
+      for (int t = 0; t < m.n_tris; ++t) {
+        const uint2 tr = mh.ml_tris[m.tri_off + t];
+        for (int k = 0; k < 3; ++k) {
+          const int slot = (tr.x >> (8 * k)) & 255;
+          if (slot >= m.n_verts || mh.ml_verts[m.vert_off + slot] != faces[3 * tr.y + k]) {
+            fp::set_last_error("fp_op_build_meshlets: meshlet triangle does not map back to its face");
+            return -4;
+          }
+          // every vertex of the meshlet lies inside its bounding sphere
+          const float* q = pos + 3 * faces[3 * tr.y + k];
+          const float dx = q[0] - m.cx, dy = q[1] - m.cy, dz = q[2] - m.cz;
+          if (dx * dx + dy * dy + dz * dz > m.r * m.r * 1.0001f + 1e-12f) {
+            fp::set_last_error("fp_op_build_meshlets: vertex outside the meshlet's bounding sphere");
+            return -4;
+          }
+        }
+        if (face_of_tri_out) face_of_tri_out[m.tri_off + t] = (int)tr.y;
+      }
+    }
+    info[0] = (int)mh.meshlets.size();
+    info[1] = mh.closed;
+    info[2] = mh.front_sign;
+    info[3] = max_t;
+    info[4] = max_v;
+    info[5] = total;
+    return 0;
+  } catch (...) {
+    fp::set_last_error("fp_op_build_meshlets: exception");
+    return -3;
+  }
 }
 
 int fp_op_attention(const void* qkv, void* out, int B, int impl, void* stream) {
@@ -50,7 +105,8 @@ int fp_op_attention(const void* qkv, void* out, int B, int impl, void* stream) {
   ap.n_heads = 4;
   ap.scale = 0.08838834764831845f;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return impl == 0 ? fp::attn_legacy_launch(ap, st) : fp::attn_tc_launch(ap, st);
+  (void)impl;  // one implementation: the tcgen05 kernel
+  return fp::attn_tc_launch(ap, st);
 }
 
 int fp_op_gemm_layer(const fp_gemm_layer_t* l, void* stream) {

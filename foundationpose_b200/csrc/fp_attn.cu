@@ -1,11 +1,5 @@
 // fp_attn.cu — the non-GEMM parts of the transformer heads and the scorer tail.
 //
-//   attn_core_kernel     softmax(Q K^T / sqrt(128)) V for T = 400 tokens, 4 heads of 128
-//                        (nn.MultiheadAttention inside nn.TransformerEncoderLayer, refine_network.py:56-70;
-//                        score_network.py:53, :72).  Flash-style, one CTA per (sequence, head): K and V
-//                        of the head live in shared memory, each warp owns 16-query-row tiles.
-//                        Tensor-core path here is mma.sync m16n8k16 (2.7 % of the network FLOPs); the
-//                        projections around it run on the tcgen05 kernel (fp_gemm.cu).
 //   layernorm_kernel     row LayerNorm over 512 channels (norm1 of the encoder layer; the residual add is
 //                        fused in the producing GEMM's epilogue).
 //   head_final_kernel    norm2 -> mean over the 400 tokens -> Linear(512, 3)  (refine_network.py:89-90;
@@ -17,7 +11,6 @@
 //   pose_update_kernel   predict_pose_refine.py:195-231 + Utils.py:848-855 + pytorch3d so3_exp_map.
 #include "fp_attn.cuh"
 
-#include <mma.h>
 #include <stdlib.h>
 
 #include "fp_common.cuh"
@@ -25,186 +18,8 @@
 
 namespace fp {
 
-// ------------------------------------------------------------------------------------------------
-// attention core
-// ------------------------------------------------------------------------------------------------
-constexpr int kT = 400;            // tokens (20 x 20)
-constexpr int kDh = 128;           // head dim
-constexpr int kKvStride = 136;     // halfs per smem row (272 B): conflict-free ldmatrix
-constexpr int kKeyBlock = 80;      // keys per online-softmax step
-constexpr int kAttnWarps = 8;
-constexpr int kAttnSmem = 2 * kT * kKvStride * 2;
-
-__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(smem_u32(p)));
-}
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* p) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(smem_u32(p)));
-}
-__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src));
-}
-
-__global__ void __launch_bounds__(kAttnWarps * 32, 1) attn_core_kernel(const AttnParams p) {
-  extern __shared__ __align__(16) uint8_t attn_smem[];
-  __half* sK = reinterpret_cast<__half*>(attn_smem);
-  __half* sV = sK + kT * kKvStride;
-  const int b = blockIdx.x, h = blockIdx.y, g = blockIdx.z;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const __half* qkv = p.qkv + (size_t)b * kT * p.ld + (size_t)g * p.group_col_stride + h * kDh;
-  const __half* gq = qkv + p.q_off;
-  const __half* gk = qkv + p.k_off;
-  const __half* gv = qkv + p.v_off;
-
-  // stage K, V of this (sequence, head) in shared memory
-  for (int c = tid; c < kT * 16; c += kAttnWarps * 32) {
-    const int row = c >> 4, ch = c & 15;
-    cp_async16(sK + row * kKvStride + ch * 8, gk + (size_t)row * p.ld + ch * 8);
-    cp_async16(sV + row * kKvStride + ch * 8, gv + (size_t)row * p.ld + ch * 8);
-  }
-  asm volatile("cp.async.commit_group;");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-
-  const int gq_row = lane >> 2, tq = lane & 3;
-  const float sl2 = p.scale * 1.4426950408889634f;  // softmax scale folded into exp2
-  __half* outp = p.out + (size_t)g * p.out_group_stride + (size_t)b * kT * p.ld_out + h * kDh;
-
-  for (int rt = warp; rt < kT / 16; rt += kAttnWarps) {
-    const int row0 = rt * 16;
-    // Q fragments for the 8 k-steps
-    uint32_t qf[8][4];
-#pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
-      const __half* q0 = gq + (size_t)(row0 + gq_row) * p.ld + kk * 16 + tq * 2;
-      const __half* q1 = q0 + (size_t)8 * p.ld;
-      qf[kk][0] = __ldg(reinterpret_cast<const uint32_t*>(q0));
-      qf[kk][1] = __ldg(reinterpret_cast<const uint32_t*>(q1));
-      qf[kk][2] = __ldg(reinterpret_cast<const uint32_t*>(q0 + 8));
-      qf[kk][3] = __ldg(reinterpret_cast<const uint32_t*>(q1 + 8));
-    }
-    float o[16][4];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-
-    for (int kb = 0; kb < kT; kb += kKeyBlock) {
-      float s[kKeyBlock / 8][4];
-#pragma unroll
-      for (int i = 0; i < kKeyBlock / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-#pragma unroll
-        for (int nt = 0; nt < kKeyBlock / 16; ++nt) {
-          uint32_t kf[4];
-          const int key = kb + nt * 16 + (lane & 7) + ((lane >> 4) << 3);
-          const int col = kk * 16 + (((lane >> 3) & 1) << 3);
-          ldmatrix_x4(kf, sK + key * kKvStride + col);
-          mma_16816(s[2 * nt], qf[kk], kf[0], kf[1]);
-          mma_16816(s[2 * nt + 1], qf[kk], kf[2], kf[3]);
-        }
-      }
-      // online softmax (rows gq_row and gq_row + 8)
-      float bm0 = -INFINITY, bm1 = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < kKeyBlock / 8; ++i) {
-        bm0 = fmaxf(bm0, fmaxf(s[i][0], s[i][1]));
-        bm1 = fmaxf(bm1, fmaxf(s[i][2], s[i][3]));
-      }
-      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
-      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
-      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
-      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
-      const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);
-      const float c0 = exp2f((m0 - nm0) * sl2), c1 = exp2f((m1 - nm1) * sl2);
-      m0 = nm0;
-      m1 = nm1;
-      float rs0 = 0.f, rs1 = 0.f;
-#pragma unroll
-      for (int i = 0; i < kKeyBlock / 8; ++i) {
-        s[i][0] = exp2f((s[i][0] - m0) * sl2);
-        s[i][1] = exp2f((s[i][1] - m0) * sl2);
-        s[i][2] = exp2f((s[i][2] - m1) * sl2);
-        s[i][3] = exp2f((s[i][3] - m1) * sl2);
-        rs0 += s[i][0] + s[i][1];
-        rs1 += s[i][2] + s[i][3];
-      }
-      l0 = l0 * c0 + rs0;
-      l1 = l1 * c1 + rs1;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        o[i][0] *= c0;
-        o[i][1] *= c0;
-        o[i][2] *= c1;
-        o[i][3] *= c1;
-      }
-      // O += P V
-#pragma unroll
-      for (int ks = 0; ks < kKeyBlock / 16; ++ks) {
-        uint32_t pf[4];
-        pf[0] = pack_half2(s[2 * ks][0], s[2 * ks][1]);
-        pf[1] = pack_half2(s[2 * ks][2], s[2 * ks][3]);
-        pf[2] = pack_half2(s[2 * ks + 1][0], s[2 * ks + 1][1]);
-        pf[3] = pack_half2(s[2 * ks + 1][2], s[2 * ks + 1][3]);
-        const int key = kb + ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
-#pragma unroll
-        for (int dt = 0; dt < 8; ++dt) {
-          uint32_t vf[4];
-          ldmatrix_x4_trans(vf, sV + key * kKvStride + dt * 16 + ((lane >> 4) << 3));
-          mma_16816(o[2 * dt], pf, vf[0], vf[1]);
-          mma_16816(o[2 * dt + 1], pf, vf[2], vf[3]);
-        }
-      }
-    }
-    // finish: row sums across the quad, normalise, store
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float il0 = 1.f / l0, il1 = 1.f / l1;
-    __half* o0 = outp + (size_t)(row0 + gq_row) * p.ld_out + tq * 2;
-    __half* o1 = o0 + (size_t)8 * p.ld_out;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      *reinterpret_cast<uint32_t*>(o0 + i * 8) = pack_half2(o[i][0] * il0, o[i][1] * il0);
-      *reinterpret_cast<uint32_t*>(o1 + i * 8) = pack_half2(o[i][2] * il1, o[i][3] * il1);
-    }
-  }
-}
-
-int attn_legacy_launch(const AttnParams& p, cudaStream_t stream) {
-  FP_REQUIRE(p.T == kT && p.n_heads == 4, "attention core is specialised for T=400, 4 heads of 128 (got T=%d)", p.T);
-  static bool attr_set = false;
-  if (!attr_set) {
-    FP_CUDA_OK(cudaFuncSetAttribute(attn_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    attr_set = true;
-  }
-  if (p.B == 0) return 0;
-  dim3 grid(p.B, p.n_heads, p.n_groups);
-  attn_core_kernel<<<grid, kAttnWarps * 32, kAttnSmem, stream>>>(p);
-  ++g_launch_count;
-  FP_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
-int attn_core_launch(const AttnParams& p, cudaStream_t stream) {
-  static int use_tc = -1;
-  if (use_tc < 0) {
-    const char* e = getenv("FPOSE_ATTN");
-    use_tc = (e && e[0] == 'l') ? 0 : 1;
-  }
-  return use_tc ? attn_tc_launch(p, stream) : attn_legacy_launch(p, stream);
-}
+// attention itself lives in fp_attn_tc.cu (tcgen05); this file keeps the SIMT pieces around it
+int attn_core_launch(const AttnParams& p, cudaStream_t stream) { return attn_tc_launch(p, stream); }
 
 // ------------------------------------------------------------------------------------------------
 // LayerNorm helpers: one warp per 512-channel row, 16 channels per lane
@@ -290,7 +105,7 @@ int layernorm_launch(const __half* x, __half* y, const float* gamma, const float
   if (rows == 0) return 0;
   const int blocks = min((rows + 7) / 8, 148 * 8);
   FP_CUDA_OK(launch_pdl(layernorm_kernel, dim3(blocks), dim3(256), 0, stream, 1, x, y, gamma, beta, rows, 1e-5f));
-  ++g_launch_count;
+  note_launches(1);
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -359,7 +174,7 @@ int head_final_launch(const __half* x, const float* gamma, const float* beta, co
   if (B == 0) return 0;
   FP_CUDA_OK(launch_pdl(head_final_kernel, dim3(B), dim3(kHeadWarps * 32), 0, stream, 1, x, gamma, beta, w, bias, out, T, out_dim,
                         1e-5f));
-  ++g_launch_count;
+  note_launches(1);
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -408,7 +223,7 @@ int token_mean_proj_launch(const __half* x, const __half* w, const float* bias, 
                            cudaStream_t stream) {
   if (B == 0) return 0;
   FP_CUDA_OK(launch_pdl(token_mean_proj_kernel, dim3(B), dim3(256), 0, stream, 1, x, w, bias, out, T));
-  ++g_launch_count;
+  note_launches(1);
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -553,7 +368,7 @@ int score_tail_launch(const ScoreTailParams& p, cudaStream_t stream) {
   cross_attn_kernel<<<p.L, 128, 4 * p.L * sizeof(float), stream>>>(p.qkv, p.attn, p.L, 0.08838834764831845f);
   rowwise_linear_kernel<<<dim3((p.L + kRowBlock - 1) / kRowBlock, 8), 256, 0, stream>>>(p.attn, p.w_out, p.b_out, p.proj, p.L, 512);
   score_linear_kernel<<<1, 1024, 0, stream>>>(p.proj, p.w_lin, p.b_lin, p.offset, p.scores, p.best, p.L);
-  g_launch_count += 4;
+  note_launches(4);
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -629,7 +444,7 @@ int pose_update_launch(const float* pose_in, const float* trans, const float* ro
   if (N == 0) return 0;
   FP_CUDA_OK(launch_pdl(pose_update_kernel, dim3((N + 127) / 128), dim3(128), 0, stream, 1, pose_in, trans, rot, pose_out,
                         trans_delta_out, rot_delta_out, N, trans_scale, rot_normalizer));
-  ++g_launch_count;
+  note_launches(1);
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -642,7 +457,7 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ x, __half* __restric
 int f32_to_f16_launch(const float* x, __half* y, size_t n, cudaStream_t stream) {
   if (n == 0) return 0;
   f32_to_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, y, n);
-  ++g_launch_count;
+  note_launches(1);
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }

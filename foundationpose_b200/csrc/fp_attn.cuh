@@ -18,10 +18,9 @@ struct AttnParams {
   int B, T, n_heads;
   float scale;  // 1/sqrt(head_dim)
 };
-// dispatches to the tcgen05 kernel (fp_attn_tc.cu) unless FPOSE_ATTN=legacy selects the mma.sync one
+// the tcgen05 kernel (fp_attn_tc.cu)
 int attn_core_launch(const AttnParams& p, cudaStream_t stream);
 int attn_tc_launch(const AttnParams& p, cudaStream_t stream);
-int attn_legacy_launch(const AttnParams& p, cudaStream_t stream);
 
 int layernorm_launch(const __half* x, __half* y, const float* gamma, const float* beta, int rows, cudaStream_t stream);
 int head_final_launch(const __half* x, const float* gamma, const float* beta, const float* w, const float* bias,

@@ -435,10 +435,10 @@ __global__ void __launch_bounds__(kThreadsTc, 1)
 int attn_tc_launch(const AttnParams& p, cudaStream_t stream) {
   FP_REQUIRE(p.T == T && p.n_heads == 4, "tcgen05 attention is specialised for T=400, 4 heads of 128");
   FP_REQUIRE(p.ld_out == 512, "tcgen05 attention writes [*, 512] rows");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_mask{0};  // per device: the attribute is device state
+  if (!device_bit_test(attr_mask)) {
     FP_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    attr_set = true;
+    device_bit_set(attr_mask);
   }
   if (p.B == 0) return 0;
   CUtensorMap mk, mq, mv, mo;
@@ -472,7 +472,7 @@ int attn_tc_launch(const AttnParams& p, cudaStream_t stream) {
   FP_REQUIRE(sms > 0, "no CUDA device");
   dim3 grid(total < sms ? total : sms);
   FP_CUDA_OK(launch_pdl(attn_tc_kernel, grid, dim3(kThreadsTc), kSmem, stream, 1, mk, mq, mv, mo, tp));
-  ++g_launch_count;
+  note_launches(1);
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }

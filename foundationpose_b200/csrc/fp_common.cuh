@@ -10,7 +10,30 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+
 namespace fp {
+
+// ----------------------------------------------------------------------------------------------
+// process-wide state that several fp_ctx (one per thread / GPU) may touch concurrently
+// ----------------------------------------------------------------------------------------------
+// kernels launched by this library (bench.py's gpu_launches); launches recorded into a CUDA graph are
+// counted when the graph is replayed, not while it is captured
+void note_launches(int n);
+unsigned long long launch_count();
+void set_capturing(bool on);  // thread-local
+// cudaFuncSetAttribute is per-device state: a bit per device ordinal
+inline bool device_bit_test(const std::atomic<unsigned long long>& m) {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (m.load(std::memory_order_acquire) >> (d & 63)) & 1ull;
+}
+inline void device_bit_set(std::atomic<unsigned long long>& m) {
+  int d = 0;
+  cudaGetDevice(&d);
+  m.fetch_or(1ull << (d & 63), std::memory_order_release);
+}
+int num_sms();  // of the current device
 
 // ----------------------------------------------------------------------------------------------
 // error plumbing (host)

@@ -1,17 +1,24 @@
-// fp_crop.cu — fused "pose -> 160x160 network inputs" producer: for every pose hypothesis, one CTA
-//   1. derives the crop window from the pose              (Utils.py:577-621 compute_crop_window_tf_batch, 'box_3d')
-//   2. rasterises the textured mesh straight into the crop (Utils.py:133-219 nvdiffrast_render with bbox2d,
-//      dr.rasterize / dr.interpolate / dr.texture; predict_pose_refine.py:44-53)
-//   3. resamples the observed frame into the same window  (predict_pose_refine.py:63,72 / predict_score.py:89-90,
-//      kornia warp_perspective -> F.grid_sample; h5_dataset.py:158-161 depth round trip for the scorer)
-//   4. normalises both crops                              (h5_dataset.py:79-127 refiner, :137-179 scorer)
-// and writes the two 6-channel crops as fp16 8-channel images with the 3-pixel zero border and the even/odd
-// column split the 7x7 stem convolution reads (fp_stem.cu, LK_CONV7_S2).  Nothing full-frame and nothing fp32 is materialised in HBM.
+// fp_crop.cu — tiled "pose -> 160x160 network inputs" producer.  ONE kernel; one CTA per (pose hypothesis, 32x32-pixel
+// tile of the crop); nothing full-frame, nothing fp32 and no intermediate of any kind is materialised in HBM:
+//   1. crop window from the pose                          (Utils.py:577-621 compute_crop_window_tf_batch, 'box_3d')
+//   2. binning: every MESHLET of the mesh (<= 64 triangles, fp_meshlet.cu) is tested against the tile with its
+//      bounding sphere and — closed meshes — its normal cone; survivors go to a shared-memory list
+//   3. raster: each warp takes meshlets off the list, transforms their <= 64 vertices into shared memory, sets up
+//      their triangles from there (two per lane) and depth-tests the covered pixels into a SHARED-MEMORY z-tile
+//      (32x32 64-bit keys: interpolated 1/Z | ~face id, one atomicMax per fragment)
+//                                                          (Utils.py:133-219 nvdiffrast_render with bbox2d: dr.rasterize)
+//   4. shade: every thread resolves four pixels of the tile: perspective-correct attributes of the winning triangle,
+//      bilinear wrap texture, Lambert term (dr.interpolate / dr.texture, Utils.py:183-215), the observed frame resampled
+//      into the same window (predict_pose_refine.py:63,72 / predict_score.py:89-90 kornia warp_perspective;
+//      h5_dataset.py:158-161 depth round trip for the scorer), normalisation of both (h5_dataset.py:79-127, :137-179)
+//   5. one coalesced 16-byte store per crop pixel: the fp16 8-channel images with the 3-pixel zero border and the
+//      even/odd column split the 7x7 stem convolution reads (fp_stem.cu, LK_CONV7_S2).
 //
-// Raster: integer/fp32 load-store work (no tensor cores).  Vertices are snapped to 1/256 pixel and
-// coverage is decided by exact 64-bit integer edge functions with a top-left tie rule (watertight);
-// depth test = largest interpolated 1/Z, ties -> lowest triangle id, resolved by one 64-bit atomicMax
-// per covered pixel on a z-buffer that lives entirely in shared memory (160*160*8 B = 200 KB).
+// Integer / fp32 load-store work (no tensor cores).  Coverage rule: vertices snapped to 1/256 pixel, exact integer edge
+// functions with a top-left tie rule (watertight), depth test on the interpolated 1/Z (largest wins, ties -> lowest
+// original face id).  Triangles crossing the near plane (Utils.py:161 znear = 0.001) are not dropped: they take a
+// homogeneous (clip-space) path — nvdiffrast computes its barycentrics in clip space — with the depth range test
+// znear < Z < zfar per pixel.
 #include "fp_crop.cuh"
 
 #include "fp_common.cuh"
@@ -19,37 +26,40 @@
 
 namespace fp {
 
-constexpr int S = 160;               // crop size (cfg.input_resize)
+constexpr int S = 160;    // crop size (cfg.input_resize)
+constexpr int TILE = 32;  // tile edge in pixels
+constexpr int TPR = S / TILE;
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kListCap = 1024;  // meshlet list entries per binning round
+#ifndef FP_CROP_MIN_CTAS
+#define FP_CROP_MIN_CTAS 3  // resident CTAs per SM the register allocation aims for (85 registers / thread)
+#endif
 
 struct Window {
-  float left, top, sx, sy;           // tf_to_crop = [[sx,0,-left*sx],[0,sy,-top*sy],[0,0,1]]
-  float umin, vmin, rsx, rsy;        // render window origin and raster scale (pixels of crop per image pixel)
+  float left, top, sx, sy;     // tf_to_crop = [[sx,0,-left*sx],[0,sy,-top*sy],[0,0,1]]
+  float umin, vmin, rsx, rsy;  // render window origin and raster scale (pixels of crop per image pixel)
 };
 
-// Utils.py:602-621 + :584-598, fp32 with the reference's operation order (no FMA contraction so the
-// rounded window edges are reproducible bit-for-bit by the oracle).
-__device__ __forceinline__ void crop_window(const float* __restrict__ pose, float fx, float fy, float cx,
-                                            float cy, float r3, Window& w) {
+// Utils.py:602-621 + :584-598, fp32 with the reference's operation order (no FMA contraction so the rounded window
+// edges are reproducible bit-for-bit by the oracle).  Called by lanes 0..4 of one warp: lane k projects point k.
+__device__ __forceinline__ void crop_window_warp(const float* __restrict__ pose, float fx, float fy, float cx, float cy,
+                                                 float r3, int lane, Window& w) {
   const float tx = pose[3], ty = pose[7], tz = pose[11];
-  float u[5], v[5];
+  const int k = lane < 5 ? lane : 0;
+  const float ox = (k == 1) ? r3 : (k == 2 ? -r3 : 0.f);
+  const float oy = (k == 3) ? r3 : (k == 4 ? -r3 : 0.f);
+  const float px = __fadd_rn(tx, ox), py = __fadd_rn(ty, oy), pz = tz;
+  const float x = __fadd_rn(__fmul_rn(fx, px), __fmul_rn(cx, pz));
+  const float y = __fadd_rn(__fmul_rn(fy, py), __fmul_rn(cy, pz));
+  const float u = __fdiv_rn(x, pz), v = __fdiv_rn(y, pz);
+  const float u0 = __shfl_sync(0xffffffffu, u, 0), v0 = __shfl_sync(0xffffffffu, v, 0);
+  float radius = fmaxf(fabsf(__fsub_rn(u, u0)), fabsf(__fsub_rn(v, v0)));
 #pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    const float ox = (k == 1) ? r3 : (k == 2 ? -r3 : 0.f);
-    const float oy = (k == 3) ? r3 : (k == 4 ? -r3 : 0.f);
-    const float px = __fadd_rn(tx, ox), py = __fadd_rn(ty, oy), pz = tz;
-    const float x = __fadd_rn(__fmul_rn(fx, px), __fmul_rn(cx, pz));
-    const float y = __fadd_rn(__fmul_rn(fy, py), __fmul_rn(cy, pz));
-    u[k] = __fdiv_rn(x, pz);
-    v[k] = __fdiv_rn(y, pz);
-  }
-  float radius = 0.f;
-#pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    radius = fmaxf(radius, fabsf(__fsub_rn(u[k], u[0])));
-    radius = fmaxf(radius, fabsf(__fsub_rn(v[k], v[0])));
-  }
-  const float left = rintf(__fsub_rn(u[0], radius)), right = rintf(__fadd_rn(u[0], radius));
-  const float top = rintf(__fsub_rn(v[0], radius)), bottom = rintf(__fadd_rn(v[0], radius));
+  for (int o = 4; o > 0; o >>= 1) radius = fmaxf(radius, __shfl_xor_sync(0xffffffffu, radius, o));
+  radius = __shfl_sync(0xffffffffu, radius, 0);  // lanes 0..7 hold max over lanes 0..7 (lanes 5..7 duplicate point 0)
+  const float left = rintf(__fsub_rn(u0, radius)), right = rintf(__fadd_rn(u0, radius));
+  const float top = rintf(__fsub_rn(v0, radius)), bottom = rintf(__fadd_rn(v0, radius));
   w.left = left;
   w.top = top;
   // Utils.py:594-595 `out_size[0] / (right - left)` is int / Tensor = Tensor.__rtruediv__ = reciprocal() * 160 in
@@ -71,10 +81,9 @@ struct VtxScreen {
   float X, Y, Z;  // camera-space position
 };
 
-__device__ __forceinline__ void xform_vertex(const float* __restrict__ P /*pose 4x4 row-major, smem*/,
-                                             const float* __restrict__ vp, const Window& w, float fx, float fy,
-                                             float cx, float cy, VtxScreen& o) {
-  const float x = __ldg(vp), y = __ldg(vp + 1), z = __ldg(vp + 2);
+__device__ __forceinline__ void xform_vertex(const float* __restrict__ P /*pose 4x4 row-major, smem*/, float x, float y,
+                                             float z, const Window& w, float fx, float fy, float cx, float cy,
+                                             VtxScreen& o) {
   o.X = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P[0], x), __fmul_rn(P[1], y)), __fmul_rn(P[2], z)), P[3]);
   o.Y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P[4], x), __fmul_rn(P[5], y)), __fmul_rn(P[6], z)), P[7]);
   o.Z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P[8], x), __fmul_rn(P[9], y)), __fmul_rn(P[10], z)), P[11]);
@@ -89,14 +98,20 @@ __device__ __forceinline__ void xform_vertex(const float* __restrict__ P /*pose 
   o.yi = __float2int_rn(__fmul_rn(py, 256.f));
 }
 
+// what the raster phase keeps per vertex in shared memory
+struct __align__(16) VtxS {
+  int xi, yi;
+  float iz, Z;
+};
+
+// ---- exact coverage: 64-bit edge functions (any triangle) ------------------------------------------------------
 struct TriSetup {
   long long area2;
   int x0, y0, x1, y1, x2, y2;  // after orientation fix (area2 > 0)
   int swapped;                 // vertices 1 and 2 were exchanged
 };
-
-__device__ __forceinline__ bool tri_setup(const VtxScreen& a, const VtxScreen& b, const VtxScreen& c, TriSetup& t) {
-  t.x0 = a.xi; t.y0 = a.yi; t.x1 = b.xi; t.y1 = b.yi; t.x2 = c.xi; t.y2 = c.yi;
+__device__ __forceinline__ bool tri_setup(int ax, int ay, int bx, int by, int cx, int cy, TriSetup& t) {
+  t.x0 = ax; t.y0 = ay; t.x1 = bx; t.y1 = by; t.x2 = cx; t.y2 = cy;
   t.swapped = 0;
   long long area2 = (long long)(t.x1 - t.x0) * (t.y2 - t.y0) - (long long)(t.y1 - t.y0) * (t.x2 - t.x0);
   if (area2 == 0) return false;
@@ -109,8 +124,6 @@ __device__ __forceinline__ bool tri_setup(const VtxScreen& a, const VtxScreen& b
   t.area2 = area2;
   return true;
 }
-
-// edge function of edge (xa,ya)->(xb,yb) at pixel centre (px,py); all in 1/256 px
 __device__ __forceinline__ long long edge_fn(int xa, int ya, int xb, int yb, int px, int py) {
   return (long long)(xb - xa) * (py - ya) - (long long)(yb - ya) * (px - xa);
 }
@@ -119,7 +132,6 @@ __device__ __forceinline__ long long edge_fn(int xa, int ya, int xb, int yb, int
 __device__ __forceinline__ bool edge_ok(long long e, int dx, int dy) {
   return e > 0 || (e == 0 && (dy > 0 || (dy == 0 && dx > 0)));
 }
-
 // barycentric weights (screen space) of the *original* vertex order a, b, c; false if outside
 __device__ __forceinline__ bool tri_cover(const TriSetup& t, int px, int py, float& b0, float& b1, float& b2) {
   const long long e0 = edge_fn(t.x1, t.y1, t.x2, t.y2, px, py);  // weight of vertex 0
@@ -137,124 +149,14 @@ __device__ __forceinline__ bool tri_cover(const TriSetup& t, int px, int py, flo
   return true;
 }
 
-__device__ __forceinline__ float inv_depth(float b0, float b1, float b2, float iz0, float iz1, float iz2) {
-  return __fadd_rn(__fadd_rn(__fmul_rn(b0, iz0), __fmul_rn(b1, iz1)), __fmul_rn(b2, iz2));
-}
-
-// kornia.warp_perspective(..., align_corners=False) coordinate chain (SURVEY.md §8c K1): destination
-// pixel index d, affine map x = d * inv_scale + offset into a source of `size` pixels, then the
-// (size-1)-normalisation followed by grid_sample's align_corners=False un-normalisation.
-__device__ __forceinline__ float kornia_src_coord(float x_src, int size) {
-  const float xn = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, x_src), (float)(size - 1)), 1.f);
-  return __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(xn, 1.f), (float)size), 1.f), 0.5f);
-}
-
-__device__ __forceinline__ void normalise_xyz(float x, float y, float z, const float* t, float inv_radius, float tau,
-                                              float& ox, float& oy, float& oz) {
-  // h5_dataset.py:93-99 / :151-156
-  const bool inv = z < tau;
-  ox = (x - t[0]) * inv_radius;
-  oy = (y - t[1]) * inv_radius;
-  oz = (z - t[2]) * inv_radius;
-  if (inv || fabsf(ox) >= 2.f) ox = 0.f;
-  if (inv || fabsf(oy) >= 2.f) oy = 0.f;
-  if (inv || fabsf(oz) >= 2.f) oz = 0.f;
-}
-
-// ------------------------------------------------------------------------------------------------
-// pass 0: one thread per (hypothesis, vertex): camera transform, projection into the crop raster,
-// 1/256-px snap, per-vertex diffuse term.  16 + 16 bytes per vertex, written once, read ~6x (L2).
-// ------------------------------------------------------------------------------------------------
-constexpr int kTabWords = 6 * S;  // per hypothesis: colf, rowf (float), coln, rown, colz, rowz (int)
-
-struct __align__(16) VtxA {  // what the z-buffer pass needs
-  int xi, yi;
-  float iz, Z;
-};
-struct __align__(16) VtxB {  // what shading additionally needs
-  float X, Y, dif, pad;
-};
-
-__global__ void __launch_bounds__(256) vertex_kernel(const CropParams p) {
-  __shared__ float sP[16];
-  __shared__ Window sW;
-  pdl_trigger();
-  pdl_wait();  // poses come from the previous iteration's pose update; vtx / tab buffers are still read by its shade
-  const int n = blockIdx.y;
-  if (threadIdx.x < 16) sP[threadIdx.x] = p.poses[(size_t)n * 16 + threadIdx.x];
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    Window w;
-    crop_window(sP, p.fx, p.fy, p.cx, p.cy, p.r3, w);
-    sW = w;
-    if (blockIdx.x == 0) {
-      float* wb = p.win_buf + (size_t)n * 8;
-      wb[0] = w.left; wb[1] = w.top; wb[2] = w.sx; wb[3] = w.sy;
-      wb[4] = w.umin; wb[5] = w.vmin; wb[6] = w.rsx; wb[7] = w.rsy;
-      if (p.win_out) {
-        p.win_out[n * 4 + 0] = w.left;
-        p.win_out[n * 4 + 1] = w.top;
-        p.win_out[n * 4 + 2] = w.sx;
-        p.win_out[n * 4 + 3] = w.sy;
-      }
-    }
-  }
-  __syncthreads();
-  if (blockIdx.x == 0) {
-    // per-axis tables of the observed-crop resampling (every quantity is separable in x and y): S columns, S rows
-    for (int tI = threadIdx.x; tI < 2 * S; tI += blockDim.x) {
-      const bool is_row = tI >= S;
-      const int d = is_row ? tI - S : tI;
-      const float sc = is_row ? sW.sy : sW.sx, org = is_row ? sW.top : sW.left;
-      const int size = is_row ? p.H : p.W;
-      const float xs = __fadd_rn(__fdiv_rn((float)d, sc), org);
-      const float ix = kornia_src_coord(xs, size);
-      int un = (int)rintf(ix);
-      if (un < 0 || un >= size) un = -1;
-      int uz = -1;
-      if (un >= 0) {
-        // scorer: depth crop -> full-res (nearest) -> back-project -> crop (nearest), h5_dataset.py:158-161
-        const float xc = __fadd_rn(__fmul_rn(sc, (float)un), __fmul_rn(-org, sc));
-        const int jc = (int)rintf(kornia_src_coord(xc, S));
-        if (jc >= 0 && jc < S) {
-          const float xs2 = __fadd_rn(__fdiv_rn((float)jc, sc), org);
-          const int u2 = (int)rintf(kornia_src_coord(xs2, size));
-          if (u2 >= 0 && u2 < size) uz = u2;
-        }
-      }
-      float* tb = p.tab_buf + (size_t)n * kTabWords;
-      tb[(is_row ? 1 : 0) * S + d] = ix;
-      reinterpret_cast<int*>(tb)[(2 + (is_row ? 1 : 0)) * S + d] = un;
-      reinterpret_cast<int*>(tb)[(4 + (is_row ? 1 : 0)) * S + d] = uz;
-    }
-  }
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= p.V) return;
-  VtxScreen o;
-  xform_vertex(sP, p.vpos + 3 * v, sW, p.fx, p.fy, p.cx, p.cy, o);
-  // diffuse = clip(normalize(R n) . (0,0,-1), 0, 1)   (Utils.py:203-207)
-  const float nx = __ldg(p.vnrm + 3 * v), ny = __ldg(p.vnrm + 3 * v + 1), nz = __ldg(p.vnrm + 3 * v + 2);
-  const float cxn = sP[0] * nx + sP[1] * ny + sP[2] * nz;
-  const float cyn = sP[4] * nx + sP[5] * ny + sP[6] * nz;
-  const float czn = sP[8] * nx + sP[9] * ny + sP[10] * nz;
-  const float len = fmaxf(sqrtf(cxn * cxn + cyn * cyn + czn * czn), 1e-12f);
-  VtxA a;
-  a.xi = o.xi; a.yi = o.yi; a.iz = o.iz; a.Z = o.Z;
-  VtxB b;
-  b.X = o.X; b.Y = o.Y; b.dif = fminf(fmaxf(-czn / len, 0.f), 1.f); b.pad = 0.f;
-  p.vtx_a[(size_t)n * p.V + v] = a;
-  p.vtx_b[(size_t)n * p.V + v] = b;
-}
-
-// 32-bit edge functions relative to vertex 0 when the triangle is small enough (all deltas < 2^15, i.e.
-// < 128 px: products < 2^30); the integers are the same as the 64-bit ones, so coverage is unchanged.
+// ---- the same integers in 32 bits when the triangle is small enough (all deltas < 2^15, i.e. < 128 px: products
+// < 2^30), relative to vertex 0: coverage is unchanged ------------------------------------------------------------
 struct TriSetup32 {
   int area2;
-  int x0, y0;               // vertex 0 (absolute, 1/256 px)
-  int ax, ay, bx, by;       // oriented vertices 1 and 2 relative to vertex 0
+  int x0, y0;          // vertex 0 (absolute, 1/256 px)
+  int ax, ay, bx, by;  // oriented vertices 1 and 2 relative to vertex 0
   int swapped;
 };
-
 __device__ __forceinline__ bool tri_small(int x0, int y0, int x1, int y1, int x2, int y2) {
   const int m = max(max(abs(x1 - x0), abs(y1 - y0)), max(abs(x2 - x0), abs(y2 - y0)));
   return m < 16384;
@@ -294,127 +196,414 @@ __device__ __forceinline__ bool tri_cover32(const TriSetup32& t, int px, int py,
   return true;
 }
 
-// rare path: triangles spanning >= 128 px use the 64-bit edge functions (same integers, same coverage)
-__device__ __noinline__ void raster_big_tri(const VtxA a, const VtxA b, const VtxA c, int f, int j0, int j1, int r0,
-                                            int r1, unsigned long long* zbuf) {
-  VtxScreen sa, sb, sc;
-  sa.xi = a.xi; sa.yi = a.yi; sb.xi = b.xi; sb.yi = b.yi; sc.xi = c.xi; sc.yi = c.yi;
-  TriSetup t;
-  if (!tri_setup(sa, sb, sc, t)) return;
-  for (int r = r0; r <= r1; ++r)
-    for (int j = j0; j <= j1; ++j) {
-      float b0, b1, b2;
-      if (!tri_cover(t, j * 256 + 128, r * 256 + 128, b0, b1, b2)) continue;
-      const float iz = inv_depth(b0, b1, b2, a.iz, b.iz, c.iz);
-      const unsigned long long key =
-          ((unsigned long long)__float_as_uint(iz) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)f);
-      atomicMax(&zbuf[r * S + j], key);
-    }
+__device__ __forceinline__ float inv_depth(float b0, float b1, float b2, float iz0, float iz1, float iz2) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(b0, iz0), __fmul_rn(b1, iz1)), __fmul_rn(b2, iz2));
 }
-__device__ __noinline__ void bary_big_tri(const VtxA a, const VtxA b, const VtxA c, int px, int py, float* bw) {
-  VtxScreen sa, sb, sc;
-  sa.xi = a.xi; sa.yi = a.yi; sb.xi = b.xi; sb.yi = b.yi; sc.xi = c.xi; sc.yi = c.yi;
-  TriSetup t;
-  tri_setup(sa, sb, sc, t);
-  float b0 = 0.f, b1 = 0.f, b2 = 0.f;
-  tri_cover(t, px, py, b0, b1, b2);
-  bw[0] = b0; bw[1] = b1; bw[2] = b2;
+__device__ __forceinline__ unsigned long long depth_key(float iz, unsigned face) {
+  return ((unsigned long long)__float_as_uint(iz) << 32) | (unsigned long long)(0xFFFFFFFFu - face);
 }
 
-// ------------------------------------------------------------------------------------------------
-// pass 1: one thread per (hypothesis, triangle): coverage + depth test into the per-hypothesis z-buffer
-// (64-bit keys in global memory = L2: 200 KB per hypothesis), so the work spreads over the whole GPU for
-// any batch size (one pose in track_one, ~32 per GPU when sharded, 252 in register).
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) raster_kernel(const CropParams p) {
-  pdl_trigger();
-  pdl_wait();
-  const int n = blockIdx.y;
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= p.F) return;
-  const VtxA* va = p.vtx_a + (size_t)n * p.V;
-  unsigned long long* zbuf = p.zbuf + (size_t)n * S * S;
-  const int i0 = __ldg(p.faces + 3 * f), i1 = __ldg(p.faces + 3 * f + 1), i2 = __ldg(p.faces + 3 * f + 2);
-  const VtxA a = va[i0], b = va[i1], c = va[i2];
-  if (!(a.Z > p.znear && b.Z > p.znear && c.Z > p.znear)) return;  // no near-plane clipping
+// ---- homogeneous path for triangles that cross the near plane: solve [P0 P1 P2] w = d for the pixel ray d; w / sum(w)
+// are the perspective-correct barycentrics, sum(w) = 1 / Z.  fp32, same order in oracle/raster.py. -------------------
+struct HomTri {
+  float n0x, n0y, n0z, n1x, n1y, n1z, n2x, n2y, n2z;  // P1 x P2, P2 x P0, P0 x P1
+  float det;
+};
+__device__ __forceinline__ void hom_setup(const float* A, const float* B, const float* C, HomTri& h) {
+  h.n0x = __fsub_rn(__fmul_rn(B[1], C[2]), __fmul_rn(B[2], C[1]));
+  h.n0y = __fsub_rn(__fmul_rn(B[2], C[0]), __fmul_rn(B[0], C[2]));
+  h.n0z = __fsub_rn(__fmul_rn(B[0], C[1]), __fmul_rn(B[1], C[0]));
+  h.n1x = __fsub_rn(__fmul_rn(C[1], A[2]), __fmul_rn(C[2], A[1]));
+  h.n1y = __fsub_rn(__fmul_rn(C[2], A[0]), __fmul_rn(C[0], A[2]));
+  h.n1z = __fsub_rn(__fmul_rn(C[0], A[1]), __fmul_rn(C[1], A[0]));
+  h.n2x = __fsub_rn(__fmul_rn(A[1], B[2]), __fmul_rn(A[2], B[1]));
+  h.n2y = __fsub_rn(__fmul_rn(A[2], B[0]), __fmul_rn(A[0], B[2]));
+  h.n2z = __fsub_rn(__fmul_rn(A[0], B[1]), __fmul_rn(A[1], B[0]));
+  h.det = __fadd_rn(__fadd_rn(__fmul_rn(A[0], h.n0x), __fmul_rn(A[1], h.n0y)), __fmul_rn(A[2], h.n0z));
+}
+// pixel ray d = (dx, dy, 1); returns false outside / outside the depth range; l* = perspective-correct weights
+__device__ __forceinline__ bool hom_cover(const HomTri& h, float dx, float dy, float znear, float zfar, float& l0,
+                                          float& l1, float& l2, float& iz) {
+  if (h.det == 0.f) return false;
+  const float w0 = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(h.n0x, dx), __fmul_rn(h.n0y, dy)), h.n0z), h.det);
+  const float w1 = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(h.n1x, dx), __fmul_rn(h.n1y, dy)), h.n1z), h.det);
+  const float w2 = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(h.n2x, dx), __fmul_rn(h.n2y, dy)), h.n2z), h.det);
+  if (!(w0 >= 0.f && w1 >= 0.f && w2 >= 0.f)) return false;
+  iz = __fadd_rn(__fadd_rn(w0, w1), w2);
+  if (!(iz > 0.f)) return false;
+  const float z = __frcp_rn(iz);
+  if (!(z > znear && z < zfar)) return false;
+  l0 = __fmul_rn(w0, z);
+  l1 = __fmul_rn(w1, z);
+  l2 = __fmul_rn(w2, z);
+  return true;
+}
+
+// kornia.warp_perspective(..., align_corners=False) coordinate chain (SURVEY.md §8c K1): destination
+// pixel index d, affine map x = d * inv_scale + offset into a source of `size` pixels, then the
+// (size-1)-normalisation followed by grid_sample's align_corners=False un-normalisation.
+__device__ __forceinline__ float kornia_src_coord(float x_src, int size) {
+  const float xn = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, x_src), (float)(size - 1)), 1.f);
+  return __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(xn, 1.f), (float)size), 1.f), 0.5f);
+}
+
+__device__ __forceinline__ void normalise_xyz(float x, float y, float z, const float* t, float inv_radius, float tau,
+                                              float& ox, float& oy, float& oz) {
+  // h5_dataset.py:93-99 / :151-156
+  const bool inv = z < tau;
+  ox = (x - t[0]) * inv_radius;
+  oy = (y - t[1]) * inv_radius;
+  oz = (z - t[2]) * inv_radius;
+  if (inv || fabsf(ox) >= 2.f) ox = 0.f;
+  if (inv || fabsf(oy) >= 2.f) oy = 0.f;
+  if (inv || fabsf(oz) >= 2.f) oz = 0.f;
+}
+
+struct TileSmem {
+  unsigned long long zt[TILE * TILE];  // depth keys of the tile (0 = empty)
+  VtxS sv[kWarps][kMeshletVerts];      // per-warp transformed vertices of the meshlet in flight
+  float P[16];
+  Window win;
+  float colf[TILE], rowf[TILE];  // kornia source coordinates of the observed-crop resampling (separable)
+  int coln[TILE], rown[TILE];    // nearest source column / row (-1 = outside)
+  int colz[TILE], rowz[TILE];    // scorer depth round trip: source column / row of the depth sample
+  int list[kListCap];
+  int n_list, next;
+  int stat[4];
+};
+
+// one triangle of a meshlet, all three vertices in front of the near plane: coverage inside the tile + depth test
+__device__ __forceinline__ void raster_tri(const VtxS& a, const VtxS& b, const VtxS& c, unsigned face, int front_sign,
+                                           int tx0, int ty0, float iz_far, unsigned long long* zt, int& n_frag) {
   const int minx = min(a.xi, min(b.xi, c.xi)), maxx = max(a.xi, max(b.xi, c.xi));
   const int miny = min(a.yi, min(b.yi, c.yi)), maxy = max(a.yi, max(b.yi, c.yi));
-  const int j0 = max((minx + 127) >> 8, 0), j1 = min((maxx - 128) >> 8, S - 1);
-  const int r0 = max((miny + 127) >> 8, 0), r1 = min((maxy - 128) >> 8, S - 1);
+  const int j0 = max((minx + 127) >> 8, tx0), j1 = min((maxx - 128) >> 8, tx0 + TILE - 1);
+  const int r0 = max((miny + 127) >> 8, ty0), r1 = min((maxy - 128) >> 8, ty0 + TILE - 1);
   if (j0 > j1 || r0 > r1) return;
-  if (!tri_small(a.xi, a.yi, b.xi, b.yi, c.xi, c.yi)) {
-    raster_big_tri(a, b, c, f, j0, j1, r0, r1, zbuf);
-    return;
+  if (tri_small(a.xi, a.yi, b.xi, b.yi, c.xi, c.yi)) {
+    TriSetup32 t;
+    if (!tri_setup32(a.xi, a.yi, b.xi, b.yi, c.xi, c.yi, t)) return;
+    // closed mesh: a back-facing triangle is always behind a front-facing one that covers the same pixel centre
+    if (front_sign != 0 && (t.swapped ? 1 : -1) * front_sign > 0) return;
+    for (int r = r0; r <= r1; ++r)
+      for (int j = j0; j <= j1; ++j) {
+        float b0, b1, b2;
+        if (!tri_cover32(t, j * 256 + 128, r * 256 + 128, b0, b1, b2)) continue;
+        const float iz = inv_depth(b0, b1, b2, a.iz, b.iz, c.iz);
+        if (!(iz > iz_far)) continue;
+        atomicMax(&zt[(r - ty0) * TILE + (j - tx0)], depth_key(iz, face));
+        ++n_frag;
+      }
+  } else {
+    TriSetup t;
+    if (!tri_setup(a.xi, a.yi, b.xi, b.yi, c.xi, c.yi, t)) return;
+    if (front_sign != 0 && (t.swapped ? 1 : -1) * front_sign > 0) return;
+    for (int r = r0; r <= r1; ++r)
+      for (int j = j0; j <= j1; ++j) {
+        float b0, b1, b2;
+        if (!tri_cover(t, j * 256 + 128, r * 256 + 128, b0, b1, b2)) continue;
+        const float iz = inv_depth(b0, b1, b2, a.iz, b.iz, c.iz);
+        if (!(iz > iz_far)) continue;
+        atomicMax(&zt[(r - ty0) * TILE + (j - tx0)], depth_key(iz, face));
+        ++n_frag;
+      }
   }
-  TriSetup32 t32;
-  if (!tri_setup32(a.xi, a.yi, b.xi, b.yi, c.xi, c.yi, t32)) return;
-  for (int r = r0; r <= r1; ++r)
-    for (int j = j0; j <= j1; ++j) {
-      float b0, b1, b2;
-      if (!tri_cover32(t32, j * 256 + 128, r * 256 + 128, b0, b1, b2)) continue;
-      const float iz = inv_depth(b0, b1, b2, a.iz, b.iz, c.iz);
-      const unsigned long long key =
-          ((unsigned long long)__float_as_uint(iz) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)f);
-      atomicMax(&zbuf[r * S + j], key);
-    }
 }
 
-// ------------------------------------------------------------------------------------------------
-// pass 2: one thread per (hypothesis, crop pixel): shade the winning triangle (A), resample the observed
-// frame (B), normalise both, write the two fp16 NHWC(8) pixels.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) shade_kernel(const CropParams p) {
-  __shared__ float sP[16];
-  pdl_trigger();
-  pdl_wait();
+// `swapped` of the setup structs: the ORIGINAL signed area was negative.  front_sign = sign of the original signed
+// area of a front-facing triangle, so a triangle is back-facing iff sign(original area) * front_sign < 0, i.e.
+// (swapped ? -1 : 1) * front_sign < 0  <=>  (swapped ? 1 : -1) * front_sign > 0.
+
+__device__ __forceinline__ float pixel_ray(float idx_plus_half, float origin, float rscale, float c, float f) {
+  // crop pixel centre -> image coordinate -> normalised camera ray component
+  const float u = __fadd_rn(origin, __fdiv_rn(idx_plus_half, rscale));
+  return __fdiv_rn(__fsub_rn(u, c), f);
+}
+
+template <bool kStats>
+__global__ void __launch_bounds__(kThreads, FP_CROP_MIN_CTAS) crop_tile_kernel(const CropParams p) {
+  __shared__ TileSmem sm;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = blockIdx.y;
-  if (threadIdx.x < 16) sP[threadIdx.x] = p.poses[(size_t)n * 16 + threadIdx.x];
+  const int tile = blockIdx.x;
+  const int ty0 = (tile / TPR) * TILE, tx0 = (tile % TPR) * TILE;
+  const MeshDev& M = p.mesh;
+
+  for (int i = tid; i < TILE * TILE; i += kThreads) sm.zt[i] = 0ull;
+  if (tid == 0) {
+    sm.n_list = 0;
+    sm.next = 0;
+    sm.stat[0] = sm.stat[1] = sm.stat[2] = sm.stat[3] = 0;
+  }
+  pdl_trigger();
+  pdl_wait();  // the poses come from the previous iteration's pose update; the crop buffer is read by its stem conv
+  if (tid < 16) sm.P[tid] = p.poses[(size_t)n * 16 + tid];
   __syncthreads();
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= S * S) return;
-  const float* tb = p.tab_buf + (size_t)n * kTabWords;
-  const int* tbi = reinterpret_cast<const int*>(tb);
-  const VtxA* va = p.vtx_a + (size_t)n * p.V;
-  const VtxB* vb = p.vtx_b + (size_t)n * p.V;
+  if (warp == 0) {
+    Window w;
+    crop_window_warp(sm.P, p.fx, p.fy, p.cx, p.cy, p.r3, lane, w);
+    if (lane == 0) {
+      sm.win = w;
+      if (p.win_out && tile == 0) {
+        p.win_out[n * 4 + 0] = w.left;
+        p.win_out[n * 4 + 1] = w.top;
+        p.win_out[n * 4 + 2] = w.sx;
+        p.win_out[n * 4 + 3] = w.sy;
+      }
+    }
+  }
+  __syncthreads();
+  const Window W = sm.win;
+
+  // ---- per-axis tables of the observed-crop resampling for this tile's 32 columns and 32 rows
+  if (tid < 2 * TILE) {
+    const bool is_row = tid >= TILE;
+    const int k = is_row ? tid - TILE : tid;
+    const int d = (is_row ? ty0 : tx0) + k;
+    const float sc = is_row ? W.sy : W.sx, org = is_row ? W.top : W.left;
+    const int size = is_row ? p.H : p.W;
+    const float xs = __fadd_rn(__fdiv_rn((float)d, sc), org);
+    const float ix = kornia_src_coord(xs, size);
+    int un = (int)rintf(ix);
+    if (un < 0 || un >= size) un = -1;
+    int uz = -1;
+    if (un >= 0) {
+      // scorer: depth crop -> full-res (nearest) -> back-project -> crop (nearest), h5_dataset.py:158-161
+      const float xc = __fadd_rn(__fmul_rn(sc, (float)un), __fmul_rn(-org, sc));
+      const int jc = (int)rintf(kornia_src_coord(xc, S));
+      if (jc >= 0 && jc < S) {
+        const float xs2 = __fadd_rn(__fdiv_rn((float)jc, sc), org);
+        const int u2 = (int)rintf(kornia_src_coord(xs2, size));
+        if (u2 >= 0 && u2 < size) uz = u2;
+      }
+    }
+    (is_row ? sm.rowf : sm.colf)[k] = ix;
+    (is_row ? sm.rown : sm.coln)[k] = un;
+    (is_row ? sm.rowz : sm.colz)[k] = uz;
+  }
+
+  // camera position in object space (for the normal cones): o = -R^T t
+  const float ox = -(sm.P[0] * sm.P[3] + sm.P[4] * sm.P[7] + sm.P[8] * sm.P[11]);
+  const float oy = -(sm.P[1] * sm.P[3] + sm.P[5] * sm.P[7] + sm.P[9] * sm.P[11]);
+  const float oz = -(sm.P[2] * sm.P[3] + sm.P[6] * sm.P[7] + sm.P[10] * sm.P[11]);
+  const float iz_far = 1.f / p.zfar;
+  int n_vis = 0, n_tri = 0, n_frag = 0, n_mixed = 0;
+  // back faces may only be skipped when the camera centre is outside the solid (bounding sphere: conservative)
+  int front_sign = M.front_sign;
+  {
+    const float bx = ox - M.bs_x, by = oy - M.bs_y, bz = oz - M.bs_z;
+    if (bx * bx + by * by + bz * bz <= M.bs_r * M.bs_r) front_sign = 0;
+  }
+
+  for (int base = 0; base < M.n_meshlets; base += kListCap) {
+    // ---- binning: meshlet bounding sphere vs this tile, normal cone vs the camera
+    const int lim = min(M.n_meshlets, base + kListCap);
+    for (int m = base + tid; m < lim; m += kThreads) {
+      const float4 sph = __ldg(reinterpret_cast<const float4*>(M.meshlets + m));
+      const float X = sm.P[0] * sph.x + sm.P[1] * sph.y + sm.P[2] * sph.z + sm.P[3];
+      const float Y = sm.P[4] * sph.x + sm.P[5] * sph.y + sm.P[6] * sph.z + sm.P[7];
+      const float Z = sm.P[8] * sph.x + sm.P[9] * sph.y + sm.P[10] * sph.z + sm.P[11];
+      const float r = sph.w;
+      bool keep = true;
+      if (Z + r <= p.znear) {
+        keep = false;  // entirely behind the near plane
+      } else if (Z - r > p.znear) {
+        // |delta u| <= fx r (1 + |X| / Z) / (Z - r) for any point of the sphere; crop raster pixels; 1 px of slack
+        const float izc = 1.f / Z, izn = 1.f / (Z - r);
+        const float pu = (p.fx * X * izc + p.cx - W.umin) * W.rsx, pv = (p.fy * Y * izc + p.cy - W.vmin) * W.rsy;
+        const float ru = p.fx * W.rsx * r * (1.f + fabsf(X) * izc) * izn + 1.f;
+        const float rv = p.fy * W.rsy * r * (1.f + fabsf(Y) * izc) * izn + 1.f;
+        keep = pu + ru >= (float)tx0 && pu - ru <= (float)(tx0 + TILE) && pv + rv >= (float)ty0 &&
+               pv - rv <= (float)(ty0 + TILE);
+      }
+      if (keep && front_sign != 0) {
+        const float4 cone = __ldg(reinterpret_cast<const float4*>(M.meshlets + m) + 1);
+        if (cone.w >= 0.f) {
+          // every face normal n_f has dot(axis, n_f) >= cutoff; the meshlet is entirely back-facing if
+          // max over the cone and the sphere of dot(n, cam - p) < 0:  d cos(theta - alpha) + r < 0
+          const float vx = ox - sph.x, vy = oy - sph.y, vz = oz - sph.z;
+          const float d = sqrtf(vx * vx + vy * vy + vz * vz);
+          if (d > r) {
+            // cone of the OUTWARD normals: for an inside-out mesh (front_sign = +1) the stored face normals point inwards
+            const float ct = fminf(fmaxf((float)(-front_sign) * (cone.x * vx + cone.y * vy + cone.z * vz) / d, -1.f), 1.f);
+            const float st = sqrtf(fmaxf(1.f - ct * ct, 0.f));
+            const float ca = fminf(cone.w, 1.f), sa = sqrtf(fmaxf(1.f - ca * ca, 0.f));
+            // 0.03 of slack on the cosine: snapping to 1/256 px may flip triangles within ~1 degree of edge-on
+            if (ct * ca + st * sa < -r / d - 0.03f) keep = false;
+          }
+        }
+      }
+      if (keep) sm.list[atomicAdd(&sm.n_list, 1)] = m;
+    }
+    __syncthreads();
+    const int n_list = sm.n_list;
+
+    // ---- raster: warps pull meshlets off the list
+    VtxS* sv = sm.sv[warp];
+    for (;;) {
+      int li = 0;
+      if (lane == 0) li = atomicAdd(&sm.next, 1);
+      li = __shfl_sync(0xffffffffu, li, 0);
+      if (li >= n_list) break;
+      const int m = sm.list[li];
+      const int4 hdr = __ldg(reinterpret_cast<const int4*>(M.meshlets + m) + 2);  // vert_off, n_verts, tri_off, n_tris
+      ++n_vis;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int s = lane + 32 * h;
+        if (s < hdr.y) {
+          const int gid = __ldg(M.ml_verts + hdr.x + s);
+          const float4 q = __ldg(M.vpos + gid);
+          VtxScreen o;
+          xform_vertex(sm.P, q.x, q.y, q.z, W, p.fx, p.fy, p.cx, p.cy, o);
+          VtxS v;
+          v.xi = o.xi; v.yi = o.yi; v.iz = o.iz; v.Z = o.Z;
+          sv[s] = v;
+        }
+      }
+      __syncwarp();
+      unsigned mixed_mask[2] = {0u, 0u};
+      uint2 trec[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int t = lane + 32 * h;
+        bool mixed = false;
+        if (t < hdr.w) {
+          trec[h] = __ldg(M.ml_tris + hdr.z + t);
+          const VtxS a = sv[trec[h].x & 255], b = sv[(trec[h].x >> 8) & 255], c = sv[(trec[h].x >> 16) & 255];
+          const int nfront = (a.Z > p.znear) + (b.Z > p.znear) + (c.Z > p.znear);
+          if (nfront == 3) {
+            ++n_tri;
+            raster_tri(a, b, c, trec[h].y, front_sign, tx0, ty0, iz_far, sm.zt, n_frag);
+          } else if (nfront > 0) {
+            mixed = true;
+          }
+        }
+        mixed_mask[h] = __ballot_sync(0xffffffffu, mixed);
+      }
+      // triangles crossing the near plane (rare): the whole warp scans the tile for one such triangle at a time
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        unsigned mm = mixed_mask[h];
+        while (mm) {
+          const int src = __ffs(mm) - 1;
+          mm &= mm - 1;
+          ++n_mixed;
+          const unsigned packed = __shfl_sync(0xffffffffu, trec[h].x, src);
+          const unsigned face = __shfl_sync(0xffffffffu, trec[h].y, src);
+          float Pc[3][3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int gid = __ldg(M.ml_verts + hdr.x + ((packed >> (8 * k)) & 255));
+            const float4 q = __ldg(M.vpos + gid);
+            VtxScreen o;
+            xform_vertex(sm.P, q.x, q.y, q.z, W, p.fx, p.fy, p.cx, p.cy, o);
+            Pc[k][0] = o.X; Pc[k][1] = o.Y; Pc[k][2] = o.Z;
+          }
+          HomTri ht;
+          hom_setup(Pc[0], Pc[1], Pc[2], ht);
+          const float dx = pixel_ray((float)(tx0 + lane) + 0.5f, W.umin, W.rsx, p.cx, p.fx);
+          for (int r = 0; r < TILE; ++r) {
+            const float dy = pixel_ray((float)(ty0 + r) + 0.5f, W.vmin, W.rsy, p.cy, p.fy);
+            float l0, l1, l2, iz;
+            if (hom_cover(ht, dx, dy, p.znear, p.zfar, l0, l1, l2, iz)) {
+              atomicMax(&sm.zt[r * TILE + lane], depth_key(iz, face));
+              ++n_frag;
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      sm.n_list = 0;
+      sm.next = 0;
+    }
+    __syncthreads();
+  }
+  if (kStats && p.stats) {
+    atomicAdd(&sm.stat[0], lane == 0 ? n_vis : 0);
+    atomicAdd(&sm.stat[1], n_tri);
+    atomicAdd(&sm.stat[2], n_frag);
+    atomicAdd(&sm.stat[3], lane == 0 ? n_mixed : 0);
+    __syncthreads();
+    if (tid < 4) atomicAdd(p.stats + tid, sm.stat[tid]);
+  }
+
+  // ---- shade: thread = column `lane` of rows warp*4 .. warp*4+3 of the tile
   const float inv_radius = p.inv_radius;
-  const float tvec[3] = {sP[3], sP[7], sP[11]};
+  const float tvec[3] = {sm.P[3], sm.P[7], sm.P[11]};
   const float tau = p.mode == 0 ? 0.001f : 0.1f;
   const size_t img_stride = (size_t)(S + 6) * (S + 8) * 8;
   __half* outA = p.crops + (size_t)n * img_stride;
   __half* outB = p.crops + (size_t)(p.b_img0 + n) * img_stride;
-  {
-    const int r = pix / S, j = pix - r * S;
+  const int j = tx0 + lane;
+  // observed-crop column quantities are shared by the thread's four rows
+  const float ixc = sm.colf[lane];
+  const int unc = sm.coln[lane], uzc = sm.colz[lane];
+#pragma unroll 1
+  for (int k = 0; k < TILE / kWarps; ++k) {
+    const int rl = warp * (TILE / kWarps) + k;
+    const int r = ty0 + rl;
     // ---- A: rendered crop
     float ar = 0.f, ag = 0.f, ab = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
-    const unsigned long long key = p.zbuf[(size_t)n * S * S + pix];
+    const unsigned long long key = sm.zt[rl * TILE + lane];
     if (key != 0ull) {
-      p.zbuf[(size_t)n * S * S + pix] = 0ull;  // leave the z-buffer clean for the next launch (no separate clear pass)
       const int f = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
-      const int i0 = __ldg(p.faces + 3 * f), i1 = __ldg(p.faces + 3 * f + 1), i2 = __ldg(p.faces + 3 * f + 2);
-      const VtxA a = va[i0], b = va[i1], c = va[i2];
-      const VtxB a2 = vb[i0], b2v = vb[i1], c2 = vb[i2];
-      float b0, b1, b2;
-      if (tri_small(a.xi, a.yi, b.xi, b.yi, c.xi, c.yi)) {
-        TriSetup32 t32;
-        tri_setup32(a.xi, a.yi, b.xi, b.yi, c.xi, c.yi, t32);
-        tri_cover32(t32, j * 256 + 128, r * 256 + 128, b0, b1, b2);
-      } else {
-        float bw[3];
-        bary_big_tri(a, b, c, j * 256 + 128, r * 256 + 128, bw);
-        b0 = bw[0]; b1 = bw[1]; b2 = bw[2];
+      const int4 fi = __ldg(M.faces + f);
+      const int vid[3] = {fi.x, fi.y, fi.z};
+      VtxScreen vs[3];
+      float dif[3];
+      float4 att[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float4 pp = __ldg(M.vpos + vid[q]);
+        const float4 nn = __ldg(M.vnrm + vid[q]);
+        att[q] = __ldg(M.vatt + vid[q]);
+        xform_vertex(sm.P, pp.x, pp.y, pp.z, W, p.fx, p.fy, p.cx, p.cy, vs[q]);
+        // diffuse = clip(normalize(R n) . (0,0,-1), 0, 1)   (Utils.py:203-207)
+        const float cxn = sm.P[0] * nn.x + sm.P[1] * nn.y + sm.P[2] * nn.z;
+        const float cyn = sm.P[4] * nn.x + sm.P[5] * nn.y + sm.P[6] * nn.z;
+        const float czn = sm.P[8] * nn.x + sm.P[9] * nn.y + sm.P[10] * nn.z;
+        const float len = fmaxf(sqrtf(cxn * cxn + cyn * cyn + czn * czn), 1e-12f);
+        dif[q] = fminf(fmaxf(-czn / len, 0.f), 1.f);
       }
-      const float iz = inv_depth(b0, b1, b2, a.iz, b.iz, c.iz);
-      // perspective-correct weights (nvdiffrast: barycentrics computed in clip space)
-      const float z = 1.f / iz;
-      const float w0 = b0 * a.iz * z, w1 = b1 * b.iz * z, w2 = b2 * c.iz * z;
-      const float X = w0 * a2.X + w1 * b2v.X + w2 * c2.X;
-      const float Y = w0 * a2.Y + w1 * b2v.Y + w2 * c2.Y;
-      const float Z = w0 * a.Z + w1 * b.Z + w2 * c.Z;
-      const float diffuse = w0 * a2.dif + w1 * b2v.dif + w2 * c2.dif;
+      float w0, w1, w2;  // perspective-correct weights (nvdiffrast: barycentrics computed in clip space)
+      if (vs[0].Z > p.znear && vs[1].Z > p.znear && vs[2].Z > p.znear) {
+        float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+        if (tri_small(vs[0].xi, vs[0].yi, vs[1].xi, vs[1].yi, vs[2].xi, vs[2].yi)) {
+          TriSetup32 t;
+          tri_setup32(vs[0].xi, vs[0].yi, vs[1].xi, vs[1].yi, vs[2].xi, vs[2].yi, t);
+          tri_cover32(t, j * 256 + 128, r * 256 + 128, b0, b1, b2);
+        } else {
+          TriSetup t;
+          tri_setup(vs[0].xi, vs[0].yi, vs[1].xi, vs[1].yi, vs[2].xi, vs[2].yi, t);
+          tri_cover(t, j * 256 + 128, r * 256 + 128, b0, b1, b2);
+        }
+        const float iz = inv_depth(b0, b1, b2, vs[0].iz, vs[1].iz, vs[2].iz);
+        const float z = 1.f / iz;
+        w0 = b0 * vs[0].iz * z;
+        w1 = b1 * vs[1].iz * z;
+        w2 = b2 * vs[2].iz * z;
+      } else {
+        const float A3[3] = {vs[0].X, vs[0].Y, vs[0].Z}, B3[3] = {vs[1].X, vs[1].Y, vs[1].Z}, C3[3] = {vs[2].X, vs[2].Y, vs[2].Z};
+        HomTri ht;
+        hom_setup(A3, B3, C3, ht);
+        const float dx = pixel_ray((float)j + 0.5f, W.umin, W.rsx, p.cx, p.fx);
+        const float dy = pixel_ray((float)r + 0.5f, W.vmin, W.rsy, p.cy, p.fy);
+        float iz;
+        w0 = w1 = w2 = 0.f;
+        hom_cover(ht, dx, dy, p.znear, p.zfar, w0, w1, w2, iz);
+      }
+      const float X = w0 * vs[0].X + w1 * vs[1].X + w2 * vs[2].X;
+      const float Y = w0 * vs[0].Y + w1 * vs[1].Y + w2 * vs[2].Y;
+      const float Z = w0 * vs[0].Z + w1 * vs[1].Z + w2 * vs[2].Z;
+      const float diffuse = w0 * dif[0] + w1 * dif[1] + w2 * dif[2];
       float cr, cg, cb;
-      if (p.tex) {
-        const float tu = w0 * __ldg(p.vuv + 2 * i0) + w1 * __ldg(p.vuv + 2 * i1) + w2 * __ldg(p.vuv + 2 * i2);
-        const float tv = w0 * __ldg(p.vuv + 2 * i0 + 1) + w1 * __ldg(p.vuv + 2 * i1 + 1) + w2 * __ldg(p.vuv + 2 * i2 + 1);
+      if (p.has_tex) {
+        const float tu = w0 * att[0].x + w1 * att[1].x + w2 * att[2].x;
+        const float tv = w0 * att[0].y + w1 * att[1].y + w2 * att[2].y;
         // dr.texture(filter_mode='linear', boundary 'wrap'): texel centres at +0.5
         const float xx = tu * p.Wt - 0.5f, yy = tv * p.Ht - 0.5f;
         const float xf = floorf(xx), yf = floorf(yy);
@@ -431,9 +620,9 @@ __global__ void __launch_bounds__(256) shade_kernel(const CropParams p) {
         cg = (w00 * t00.y + w01 * t01.y + w10 * t10.y + w11 * t11.y) * k255;
         cb = (w00 * t00.z + w01 * t01.z + w10 * t10.z + w11 * t11.z) * k255;
       } else {
-        cr = w0 * __ldg(p.vcol + 3 * i0) + w1 * __ldg(p.vcol + 3 * i1) + w2 * __ldg(p.vcol + 3 * i2);
-        cg = w0 * __ldg(p.vcol + 3 * i0 + 1) + w1 * __ldg(p.vcol + 3 * i1 + 1) + w2 * __ldg(p.vcol + 3 * i2 + 1);
-        cb = w0 * __ldg(p.vcol + 3 * i0 + 2) + w1 * __ldg(p.vcol + 3 * i1 + 2) + w2 * __ldg(p.vcol + 3 * i2 + 2);
+        cr = w0 * att[0].x + w1 * att[1].x + w2 * att[2].x;
+        cg = w0 * att[0].y + w1 * att[1].y + w2 * att[2].y;
+        cb = w0 * att[0].z + w1 * att[1].z + w2 * att[2].z;
       }
       // color*w_ambient + diffuse*color*w_diffuse, clip(0,1)   (Utils.py:211-213)
       ar = fminf(fmaxf(cr * 0.8f + diffuse * cr * 0.5f, 0.f), 1.f);
@@ -444,11 +633,11 @@ __global__ void __launch_bounds__(256) shade_kernel(const CropParams p) {
     // ---- B: observed crop
     float br = 0.f, bg = 0.f, bb = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
     {
-      const float ix = __ldg(tb + j), iy = __ldg(tb + S + r);
+      const float iy = sm.rowf[rl];
       // bilinear rgb, zeros padding
-      const float fx0 = floorf(ix), fy0 = floorf(iy);
+      const float fx0 = floorf(ixc), fy0 = floorf(iy);
       const int x0 = (int)fx0, y0 = (int)fy0;
-      const float wx1 = ix - fx0, wy1 = iy - fy0;
+      const float wx1 = ixc - fx0, wy1 = iy - fy0;
 #pragma unroll
       for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
@@ -466,21 +655,21 @@ __global__ void __launch_bounds__(256) shade_kernel(const CropParams p) {
       bg *= (1.f / 255.f);
       bb *= (1.f / 255.f);
       // nearest geometry
-      const int un = __ldg(tbi + 2 * S + j), vn = __ldg(tbi + 3 * S + r);
+      const int vn = sm.rown[rl];
       float X = 0.f, Y = 0.f, Z = 0.f;
-      if (un >= 0 && vn >= 0) {
+      if (unc >= 0 && vn >= 0) {
         if (p.mode == 0) {
           // refiner: xyz_map (depth2xyzmap, Utils.py:399-438) sampled nearest
-          const float* q = p.xyz_map + ((size_t)vn * p.W + un) * 3;
-          X = __ldg(q);
-          Y = __ldg(q + 1);
-          Z = __ldg(q + 2);
+          const float4 q = __ldg(p.xyz_map + (size_t)vn * p.W + unc);
+          X = q.x;
+          Y = q.y;
+          Z = q.z;
         } else {
-          const int u2 = __ldg(tbi + 4 * S + j), v2 = __ldg(tbi + 5 * S + r);
+          const int v2 = sm.rowz[rl];
           float zz = 0.f;
-          if (u2 >= 0 && v2 >= 0) zz = __ldg(p.depth + (size_t)v2 * p.W + u2);
+          if (uzc >= 0 && v2 >= 0) zz = __ldg(p.depth + (size_t)v2 * p.W + uzc);
           if (zz >= 0.001f) {  // depth2xyzmap_batch(zfar=inf): invalid z<0.001 -> 0
-            X = ((float)un - p.cx) * zz / p.fx;
+            X = ((float)unc - p.cx) * zz / p.fx;
             Y = ((float)vn - p.cy) * zz / p.fy;
             Z = zz;
           }
@@ -489,12 +678,13 @@ __global__ void __launch_bounds__(256) shade_kernel(const CropParams p) {
       normalise_xyz(X, Y, Z, tvec, inv_radius, tau, bx, by, bz);
     }
     // even / odd padded columns live in separate half-rows ("EO" layout, fp_stem.cu): pixel (row, col) ->
-    // [row][col & 1][col >> 1][8]
+    // [row][col & 1][col >> 1][8]; a warp (32 consecutive columns of one row) writes two 256-byte runs per image
     const int pc = j + 3;
     const size_t off = (((size_t)(r + 3) * 2 + (pc & 1)) * ((S + 8) / 2) + (pc >> 1)) * 8;
     *reinterpret_cast<uint4*>(outA + off) = make_uint4(pack_half2(ar, ag), pack_half2(ab, ax), pack_half2(ay, az), 0u);
     *reinterpret_cast<uint4*>(outB + off) = make_uint4(pack_half2(br, bg), pack_half2(bb, bx), pack_half2(by, bz), 0u);
     if (p.dbg) {
+      const int pix = r * S + j;
       float* d = p.dbg + (((size_t)n * 2 + 0) * S * S + pix) * 6;
       d[0] = ar; d[1] = ag; d[2] = ab; d[3] = ax; d[4] = ay; d[5] = az;
       d = p.dbg + (((size_t)n * 2 + 1) * S * S + pix) * 6;
@@ -505,14 +695,16 @@ __global__ void __launch_bounds__(256) shade_kernel(const CropParams p) {
 
 int crop_launch(const CropParams& p, cudaStream_t stream) {
   if (p.N == 0) return 0;
-  // algorithmic bytes: the two 6-channel fp16 crops each hypothesis produces (BASELINE.md §2)
+  // algorithmic bytes: the two 6-channel fp16 crops each hypothesis produces (SURVEY.md §8d)
   prof_mark_begin(1, (double)p.N * 2.0 * 6.0 * S * S * 2.0, stream);
-  // the z-buffer is all-zero here: allocated zeroed, and shade_kernel clears every cell it consumes
-  FP_CUDA_OK(launch_pdl(vertex_kernel, dim3((p.V + 255) / 256, p.N), dim3(256), 0, stream, 1, p));
-  FP_CUDA_OK(launch_pdl(raster_kernel, dim3((p.F + 255) / 256, p.N), dim3(256), 0, stream, 1, p));
-  FP_CUDA_OK(launch_pdl(shade_kernel, dim3((S * S + 255) / 256, p.N), dim3(256), 0, stream, 1, p));
+  const dim3 grid(TPR * TPR, p.N);
+  if (p.stats) {
+    FP_CUDA_OK(launch_pdl(crop_tile_kernel<true>, grid, dim3(kThreads), 0, stream, 1, p));
+  } else {
+    FP_CUDA_OK(launch_pdl(crop_tile_kernel<false>, grid, dim3(kThreads), 0, stream, 1, p));
+  }
   prof_mark_end(stream);
-  g_launch_count += 3;
+  note_launches(1);
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -525,7 +717,7 @@ __global__ void rgb_to_rgba_kernel(const unsigned char* __restrict__ rgb, uchar4
   if (i < npix) out[i] = make_uchar4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 255);
 }
 
-__global__ void depth_to_xyz_kernel(const float* __restrict__ depth, float* __restrict__ xyz, int H, int W, float fx,
+__global__ void depth_to_xyz_kernel(const float* __restrict__ depth, float4* __restrict__ xyz, int H, int W, float fx,
                                     float fy, float cx, float cy, float zfar) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= H * W) return;
@@ -537,22 +729,20 @@ __global__ void depth_to_xyz_kernel(const float* __restrict__ depth, float* __re
     Y = ((float)v - cy) * z / fy;
     Z = z;
   }
-  xyz[3 * i] = X;
-  xyz[3 * i + 1] = Y;
-  xyz[3 * i + 2] = Z;
+  xyz[i] = make_float4(X, Y, Z, 0.f);
 }
 
 int rgb_to_rgba_launch(const unsigned char* rgb, uchar4* out, int npix, cudaStream_t stream) {
   rgb_to_rgba_kernel<<<(npix + 255) / 256, 256, 0, stream>>>(rgb, out, npix);
-  ++g_launch_count;
+  note_launches(1);
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-int depth_to_xyz_launch(const float* depth, float* xyz, int H, int W, float fx, float fy, float cx, float cy,
+int depth_to_xyz_launch(const float* depth, float4* xyz, int H, int W, float fx, float fy, float cx, float cy,
                         float zfar, cudaStream_t stream) {
   depth_to_xyz_kernel<<<(H * W + 255) / 256, 256, 0, stream>>>(depth, xyz, H, W, fx, fy, cx, cy, zfar);
-  ++g_launch_count;
+  note_launches(1);
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }

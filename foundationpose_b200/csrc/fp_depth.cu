@@ -76,7 +76,7 @@ int erode_depth_launch(const float* depth, float* out, int H, int W, int radius,
                        float zfar, cudaStream_t stream) {
   dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8);
   erode_depth_kernel<<<grid, block, 0, stream>>>(depth, out, H, W, radius, diff_thres, ratio_thres, zfar);
-  ++g_launch_count;
+  note_launches(1);
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -85,7 +85,7 @@ int bilateral_depth_launch(const float* depth, float* out, int H, int W, int rad
                            float sigmaR, cudaStream_t stream) {
   dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8);
   bilateral_depth_kernel<<<grid, block, 0, stream>>>(depth, out, H, W, radius, zfar, sigmaD, sigmaR);
-  ++g_launch_count;
+  note_launches(1);
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -222,7 +222,7 @@ int start_poses_launch(const float* depth, const unsigned char* mask, int H, int
   FP_CUDA_OK(cudaMemsetAsync(stats, 0, 6 * sizeof(unsigned int), stream));
   mask_stats_kernel<<<148, 256, 0, stream>>>(depth, mask, H, W, stats);
   start_poses_kernel<<<1, 1024, 0, stream>>>(depth, mask, H, W, fx, fy, cx, cy, rot_grid, N, stats, poses_out, info);
-  g_launch_count += 2;
+  note_launches(2);
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -37,8 +37,16 @@
 
 namespace fp {
 
-unsigned long long g_launch_count = 0;
-bool g_prof_on = false;
+static std::atomic<unsigned long long> g_launch_count{0};
+static thread_local bool t_capturing = false;
+void note_launches(int n) {
+  if (!t_capturing) g_launch_count.fetch_add((unsigned long long)n, std::memory_order_relaxed);
+}
+unsigned long long launch_count() { return g_launch_count.load(std::memory_order_relaxed); }
+void set_capturing(bool on) { t_capturing = on; }
+
+std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;
 
 struct ProfRec {
   cudaEvent_t e0, e1;
@@ -55,15 +63,19 @@ void prof_mark_begin(int kind, double work, cudaStream_t stream) {
   cudaEventCreate(&r.e0);
   cudaEventCreate(&r.e1);
   cudaEventRecord(r.e0, stream);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof_recs.push_back(r);
 }
 void prof_mark_end(cudaStream_t stream) {
-  if (!g_prof_on || g_prof_recs.empty()) return;
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (g_prof_recs.empty()) return;
   cudaEventRecord(g_prof_recs.back().e1, stream);
 }
 // sums and clears the records of `kind`; synchronises the device
 int prof_collect(int kind, double* total_ms, double* total_work, int* launches) {
   FP_CUDA_OK(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   double ms = 0, work = 0;
   int n = 0;
   std::vector<ProfRec> keep;
@@ -1088,11 +1100,11 @@ template <int BN, int CG, int SLABS, bool PATCH = false>
 static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mr,
                      const GemmParams& p, cudaStream_t stream) {
   using Cfg = TileCfg<BN, CG, SLABS, PATCH>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_mask{0};  // per device: the attribute is device state
+  if (!device_bit_test(attr_mask)) {
     FP_CUDA_OK(cudaFuncSetAttribute(gemm_tile_kernel<BN, CG, SLABS, PATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::kSmemBytes));
-    attr_set = true;
+    device_bit_set(attr_mask);
   }
   if (g_num_sms == 0) {
     int dev = 0;
@@ -1107,7 +1119,7 @@ static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtenso
   FP_CUDA_OK(launch_pdl(gemm_tile_kernel<BN, CG, SLABS, PATCH>, dim3(grid), dim3(kTileThreads), Cfg::kSmemBytes, stream, CG, ma, mb,
                         mo, mr, p));
   prof_mark_end(stream);
-  ++g_launch_count;
+  note_launches(1);
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -1115,10 +1127,10 @@ static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtenso
 
 static int launch_swap(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mo, const CUtensorMap& mr,
                        const GemmParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_mask{0};  // per device: the attribute is device state
+  if (!device_bit_test(attr_mask)) {
     FP_CUDA_OK(cudaFuncSetAttribute(gemm_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSwapSmem));
-    attr_set = true;
+    device_bit_set(attr_mask);
   }
   if (g_num_sms == 0) {
     int dev = 0;
@@ -1131,17 +1143,17 @@ static int launch_swap(const CUtensorMap& ma, const CUtensorMap& mw, const CUten
   prof_mark_begin(0, p.alg_flops, stream);
   FP_CUDA_OK(launch_pdl(gemm_swap_kernel, dim3(grid), dim3(kTileThreads), kSwapSmem, stream, 1, ma, mw, mo, mr, p));
   prof_mark_end(stream);
-  ++g_launch_count;
+  note_launches(1);
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 static int launch_swap_patch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mo, const CUtensorMap& mr,
                              const GemmParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_mask{0};  // per device: the attribute is device state
+  if (!device_bit_test(attr_mask)) {
     FP_CUDA_OK(cudaFuncSetAttribute(gemm_swap_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSwapPatchSmem));
-    attr_set = true;
+    device_bit_set(attr_mask);
   }
   const int sms = num_sms();
   FP_REQUIRE(sms > 0, "no CUDA device");
@@ -1150,7 +1162,7 @@ static int launch_swap_patch(const CUtensorMap& ma, const CUtensorMap& mw, const
   prof_mark_begin(0, p.alg_flops, stream);
   FP_CUDA_OK(launch_pdl(gemm_swap_patch_kernel, dim3(grid), dim3(kTileThreads), kSwapPatchSmem, stream, 1, ma, mw, mo, mr, p));
   prof_mark_end(stream);
-  ++g_launch_count;
+  note_launches(1);
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }

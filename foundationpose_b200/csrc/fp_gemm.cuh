@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace fp {
 
 enum LayerKind : int {
@@ -38,14 +40,12 @@ struct GemmLayer {
 // Enqueue one layer on `stream`.  Returns 0 or a negative error code (fp_last_error() has text).
 int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream);
 
-// Number of kernel launches issued so far by this library (all kernels), for bench.py.
-extern unsigned long long g_launch_count;
 
 // Optional per-launch device timing (CUDA events on the launching stream) of the two kernels the
 // roofline is reported for: kind 0 = gemm_tile_kernel (work = algorithmic FLOPs), kind 1 = crop_kernel
 // (work = algorithmic output bytes).  Off by default; bench.py turns it on for a dedicated pass.
 void prof_mark_begin(int kind, double work, cudaStream_t stream);
 void prof_mark_end(cudaStream_t stream);
-extern bool g_prof_on;
+extern std::atomic<bool> g_prof_on;
 
 }  // namespace fp

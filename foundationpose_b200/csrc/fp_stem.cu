@@ -273,10 +273,10 @@ int stem_conv_launch(const GemmLayer& L, cudaStream_t stream) {
   p.total_tiles = p.tiles_w * p.tiles_h * L.n_img;
   p.bias = L.bias;
   p.relu = L.relu;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_mask{0};  // per device: the attribute is device state
+  if (!device_bit_test(attr_mask)) {
     FP_CUDA_OK(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem));
-    attr_set = true;
+    device_bit_set(attr_mask);
   }
   const int sms = num_sms();
   FP_REQUIRE(sms > 0, "no CUDA device");
@@ -285,7 +285,7 @@ int stem_conv_launch(const GemmLayer& L, cudaStream_t stream) {
   FP_CUDA_OK(launch_pdl(stem_conv_kernel, dim3(grid), dim3(kThreadsStem), kStemSmem, stream, 1, mi, mo,
                         reinterpret_cast<const __half*>(L.w), p));
   prof_mark_end(stream);
-  ++g_launch_count;
+  note_launches(1);
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }

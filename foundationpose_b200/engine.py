@@ -23,11 +23,15 @@ def _proto():
     vp, i, f = C.c_void_p, C.c_int, C.c_float
     lib.fp_create.argtypes = [C.POINTER(vp)]
     lib.fp_destroy.argtypes = [vp]
-    lib.fp_set_config.argtypes = [vp, f, f]
+    lib.fp_set_config.argtypes = [vp, i, f, f]
+    lib.fp_mesh_info.argtypes = [vp, C.POINTER(i)]
+    lib.fp_crop_stats.argtypes = [vp, vp, i, i, C.POINTER(i), vp]
+    lib.fp_track.argtypes = [vp, vp, vp, C.POINTER(f), i, i, vp, i, vp, vp, vp]
     lib.fp_load_network.argtypes = [vp, i, C.POINTER(_FpTensor), i]
     lib.fp_set_mesh.argtypes = [vp, i, i, vp, vp, vp, vp, vp, vp, i, i, f]
     lib.fp_set_frame.argtypes = [vp, vp, vp, C.POINTER(f), i, i, i, f, vp]
     lib.fp_get_depth.argtypes = [vp, vp, vp, vp]
+    lib.fp_set_xyz_map.argtypes = [vp, vp, vp]
     lib.fp_make_crops.argtypes = [vp, vp, i, i, vp, vp, vp, vp]
     lib.fp_start_poses.argtypes = [vp, vp, i, vp, i, vp, vp, vp]
     lib.fp_refine.argtypes = [vp, vp, i, i, vp, vp, vp, vp]
@@ -40,7 +44,7 @@ def _proto():
     lib.fp_op_tokens.argtypes = [vp, i, vp, i, vp, vp]
     lib.fp_op_depth_filter.argtypes = [vp, vp, i, i, i, vp]
     lib.fp_op_pose_update.argtypes = [vp, vp, vp, vp, i, f, f, vp]
-    for name in ("fp_create", "fp_destroy", "fp_set_config", "fp_load_network", "fp_set_mesh", "fp_set_frame",
+    for name in ("fp_create", "fp_destroy", "fp_set_config", "fp_mesh_info", "fp_crop_stats", "fp_track", "fp_set_xyz_map", "fp_load_network", "fp_set_mesh", "fp_set_frame",
                  "fp_get_depth", "fp_make_crops", "fp_start_poses", "fp_refine", "fp_score", "fp_score_features", "fp_score_tail",
                  "fp_register", "fp_op_refine_net", "fp_op_score_feats", "fp_op_tokens", "fp_op_depth_filter",
                  "fp_op_pose_update"):
@@ -134,6 +138,7 @@ class Engine:
         h = C.c_void_p()
         _lib.check(lib.fp_create(C.byref(h)), "fp_create")
         self._h = h
+        self.device_index = torch.cuda.current_device()
         self.diameter = None
         self.frame_hw = None
 
@@ -149,8 +154,10 @@ class Engine:
             pass
 
     # ---- setup
-    def set_config(self, crop_ratio=1.2, rot_normalizer=0.3490658503988659):
-        _lib.check(lib.fp_set_config(self._h, float(crop_ratio), float(rot_normalizer)), "fp_set_config")
+    def set_config(self, kind, crop_ratio=1.2, rot_normalizer=0.3490658503988659):
+        """Per-predictor config (each reference predictor reads its own config.yml): kind 'refine' | 'score'."""
+        which = 0 if kind == "refine" else 1
+        _lib.check(lib.fp_set_config(self._h, which, float(crop_ratio), float(rot_normalizer)), "fp_set_config")
 
     def load_network(self, kind, state_dict):
         packed = pack_network(state_dict, kind)
@@ -179,6 +186,38 @@ class Engine:
         _lib.check(lib.fp_set_mesh(self._h, len(pos), len(fc), cp(pos), cp(nrm), cp(uvp), cp(colp), cp(fc), cp(texp), Ht, Wt,
                                    float(diameter)), "fp_set_mesh")
         self.diameter = float(diameter)
+        self.mesh_key = (len(pos), len(fc), float(diameter))
+
+    def mesh_info(self):
+        """dict(meshlets, closed, front_sign, V, F) of the mesh in the context (fp_mesh_info)."""
+        info = (C.c_int * 5)()
+        _lib.check(lib.fp_mesh_info(self._h, info), "fp_mesh_info")
+        return dict(meshlets=info[0], closed=bool(info[1]), front_sign=info[2], V=info[3], F=info[4])
+
+    def crop_stats(self, poses, mode=0):
+        """Work counters of one crop pass: dict(meshlet_visits, triangles, fragments, near_plane_triangles)."""
+        poses = self._poses(poses)
+        st = (C.c_int * 4)()
+        _lib.check(lib.fp_crop_stats(self._h, _p(poses), len(poses), mode, st, _stream()), "fp_crop_stats")
+        return dict(meshlet_visits=st[0], triangles=st[1], fragments=st[2], near_plane_triangles=st[3])
+
+    def track(self, rgb, depth, K, pose_in, iterations, pose_out=None):
+        """fp_track: one CUDA-graph launch per frame (upload + depth filters + xyz map + refiner passes + read-back).
+        rgb uint8 (H,W,3) / depth float32 (H,W) HOST arrays; pose_in (4,4) CUDA tensor or None (continue).
+        Returns (pose_out CUDA (4,4), pose host (4,4) float32 numpy)."""
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        depth = np.ascontiguousarray(depth, dtype=np.float32)
+        H, W = depth.shape
+        Kf = (C.c_float * 9)(*[float(x) for x in np.asarray(K, dtype=np.float64).reshape(-1)])
+        if pose_in is not None:
+            pose_in = pose_in.reshape(4, 4).contiguous().float()
+        if pose_out is None:
+            pose_out = torch.empty(4, 4, dtype=torch.float32, device="cuda")
+        host = np.empty((4, 4), dtype=np.float32)
+        _lib.check(lib.fp_track(self._h, C.c_void_p(rgb.ctypes.data), C.c_void_p(depth.ctypes.data), Kf, H, W, _p(pose_in),
+                                int(iterations), _p(pose_out), C.c_void_p(host.ctypes.data), _stream()), "fp_track")
+        self.frame_hw = (H, W)
+        return pose_out, host
 
     def set_frame(self, rgb, depth, K, filter_depth=True, zfar=float("inf")):
         """rgb uint8 (H,W,3), depth float32 (H,W): numpy / CPU tensors (pinned for async H2D) or CUDA tensors."""
@@ -204,6 +243,14 @@ class Engine:
         _lib.check(lib.fp_set_frame(self._h, rp, dp, Kf, H, W, flags, float(zfar), _stream()), "fp_set_frame")
         self.frame_hw = (H, W)
 
+    def set_xyz_map(self, xyz_map):
+        """Caller-supplied xyz map (H,W,3) float32 — numpy / CPU tensor / CUDA tensor — instead of the derived one."""
+        x = xyz_map if torch.is_tensor(xyz_map) else torch.from_numpy(np.ascontiguousarray(xyz_map, dtype=np.float32))
+        x = x.float().contiguous()
+        assert tuple(x.shape) == (*self.frame_hw, 3), "xyz_map must be (H, W, 3)"
+        self._xyz_keep = x
+        _lib.check(lib.fp_set_xyz_map(self._h, _p(x), _stream()), "fp_set_xyz_map")
+
     def get_depth(self):
         H, W = self.frame_hw
         d = torch.empty(H, W, dtype=torch.float32, device="cuda")
@@ -217,12 +264,12 @@ class Engine:
         Returns poses (N,4,4) and info (4,) = (tx, ty, tz, n_valid), both CUDA tensors."""
         rot_grid = rot_grid.contiguous()
         N = len(rot_grid)
-        if torch.is_tensor(mask) and mask.is_cuda:
-            m = mask.to(torch.uint8).contiguous()
-            on_dev = 1
-        else:
-            m = torch.as_tensor(np.ascontiguousarray(mask)).to(torch.uint8).contiguous() if not torch.is_tensor(mask) else mask.to(torch.uint8).contiguous()
-            on_dev = 0
+        # the reference tests `mask > 0` (estimater.py:138, :183): binarise before the uint8 cast so that fractional
+        # float masks and values >= 256 behave the same
+        if not torch.is_tensor(mask):
+            mask = torch.as_tensor(np.ascontiguousarray(mask))
+        m = (mask if mask.dtype == torch.bool else (mask > 0)).to(torch.uint8).contiguous()
+        on_dev = 1 if m.is_cuda else 0
         self._mask_keep = m
         poses = torch.empty(N, 4, 4, dtype=torch.float32, device="cuda")
         info = torch.empty(4, dtype=torch.float32, device="cuda")

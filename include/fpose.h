@@ -73,7 +73,7 @@ int fp_op_gemm_layer(const fp_gemm_layer_t* layer, void* stream);
 
 /* softmax(Q K^T / sqrt(128)) V of nn.MultiheadAttention (refine_network.py:56-70, score_network.py:53):
  * qkv fp16 [B*400][1536] (q | k | v, 4 heads of 128 each), out fp16 [B*400][512].
- * impl 1 = tcgen05 kernel (product path), 0 = the mma.sync kernel kept for A/B checks. */
+ * `impl` is ignored (kept for ABI stability): there is one implementation, the tcgen05 kernel. */
 int fp_op_attention(const void* qkv, void* out, int B, int impl, void* stream);
 
 
@@ -88,8 +88,10 @@ typedef struct fp_ctx fp_ctx;
 int fp_create(fp_ctx** ctx);
 int fp_destroy(fp_ctx* ctx);
 
-/* crop_ratio (predict_pose_refine.py:117-118) and rot_normalizer (cfg['rot_normalizer'], :221). */
-int fp_set_config(fp_ctx* ctx, float crop_ratio, float rot_normalizer);
+/* Per-predictor configuration, as each reference predictor reads its own config.yml: which = 0 the refiner's
+ * crop_ratio (predict_pose_refine.py:117-118) and rot_normalizer (cfg['rot_normalizer'], :221); which = 1 the
+ * scorer's crop_ratio (predict_score.py:137-138; rot_normalizer ignored). */
+int fp_set_config(fp_ctx* ctx, int which, float crop_ratio, float rot_normalizer);
 
 /* One named host tensor of a packed network (see foundationpose_b200/engine.py for the packing:
  * BatchNorm folded, conv weights K-major fp16).  dtype: 0 = float32, 1 = float16. */
@@ -109,6 +111,9 @@ int fp_load_network(fp_ctx* ctx, int which, const fp_tensor_t* tensors, int n);
  * vertex-coloured meshes).  diameter = estimater.py:54. */
 int fp_set_mesh(fp_ctx* ctx, int V, int F, const float* pos, const float* nrm, const float* uv, const float* vcol,
                 const int* faces, const unsigned char* tex_rgb, int Ht, int Wt, float diameter);
+/* What fp_set_mesh derived (test hook): info[5] = {meshlets, mesh is closed and consistently oriented (0/1),
+ * front-face winding sign used for back-face culling (0 = both sides are rendered, as nvdiffrast does), V, F}. */
+int fp_mesh_info(fp_ctx* ctx, int* info);
 
 #define FP_FRAME_ON_DEVICE 1    /* rgb/depth are device pointers (default: host, copied on `stream`) */
 #define FP_FRAME_FILTER_DEPTH 2 /* erode_depth + bilateral_filter_depth (estimater.py:173-174, :257-258) */
@@ -117,6 +122,9 @@ int fp_set_mesh(fp_ctx* ctx, int V, int F, const float* pos, const float* nrm, c
  * INFINITY for register()).  Asynchronous on `stream`. */
 int fp_set_frame(fp_ctx* ctx, const unsigned char* rgb, const float* depth, const float* K, int H, int W, int flags,
                  float zfar, void* stream);
+/* Replaces the xyz map derived by fp_set_frame with the caller's own (PoseRefinePredictor.predict's `xyz_map`
+ * argument, predict_pose_refine.py:150,177): float32 [H][W][3], host or device pointer. */
+int fp_set_xyz_map(fp_ctx* ctx, const float* xyz, void* stream);
 /* Copies the filtered depth [H][W] and/or the xyz map [H][W][3] to device buffers (test hook). */
 int fp_get_depth(fp_ctx* ctx, float* depth_out_dev, float* xyz_out_dev, void* stream);
 
@@ -135,6 +143,9 @@ int fp_start_poses(fp_ctx* ctx, const unsigned char* mask, int mask_on_device, c
  * ([N][4] = left, top, sx, sy of tf_to_crop). */
 int fp_make_crops(fp_ctx* ctx, const float* poses, int N, int mode, void* crops_out, float* dbg_out, float* win_out,
                   void* stream);
+/* Work counters of one crop pass (profiling hook; synchronises): stats_out_host[4] = {meshlet visits, triangles set
+ * up, fragments depth-tested, triangles that took the near-plane path}. */
+int fp_crop_stats(fp_ctx* ctx, const float* poses, int N, int mode, int* stats_out_host, void* stream);
 
 /* PoseRefinePredictor.predict (predict_pose_refine.py:149-239) without the host round trips: poses
  * in/out are DEVICE [N][16]; last_trans [N][3] / last_rot [N][9] (optional) receive
@@ -157,10 +168,23 @@ int fp_score_tail(fp_ctx* ctx, const float* feats, int L, float* scores_out, int
 int fp_register(fp_ctx* ctx, const float* poses_host, int N, int iterations, float* poses_out_host,
                 float* scores_out_host, int* best_out_host, void* stream);
 
+/* FoundationPose.track_one (estimater.py:250-268) as ONE CUDA-graph launch per frame: upload of the frame (HOST rgb
+ * uint8 [H][W][3], depth float32 [H][W]; staged through pinned memory owned by the context), erode_depth +
+ * bilateral_filter_depth, depth2xyzmap_batch(zfar = inf), `iterations` refiner passes on ONE pose, pose read-back.
+ * pose_in_dev: DEVICE [16] ob_in_cam of the centred mesh (pose_last), or NULL = continue from the pose this context's
+ * previous fp_track produced.  pose_out_dev (DEVICE [16]) / pose_out_host (HOST [16]) are optional.  Synchronises. */
+int fp_track(fp_ctx* ctx, const unsigned char* rgb_host, const float* depth_host, const float* K, int H, int W,
+             const float* pose_in_dev, int iterations, float* pose_out_dev, float* pose_out_host, void* stream);
+
 /* parity-test hooks on pre-built crops (fp16 [2N][166][2][84][8], device) */
 int fp_op_refine_net(fp_ctx* ctx, const void* crops, int N, float* trans_out, float* rot_out, void* stream);
 int fp_op_score_feats(fp_ctx* ctx, const void* crops, int N, float* feats_out, void* stream);
 int fp_op_tokens(fp_ctx* ctx, int which, const void* crops, int N, void* tokens_out, void* stream);
+/* Host-only hook (no GPU needed) on the mesh preparation fp_set_mesh performs: meshlets of <= 64 triangles / <= 64
+ * vertices + closedness / orientation analysis.  info[6] = {meshlets, closed (0/1), front-face winding sign (0 = none),
+ * max triangles per meshlet, max vertices per meshlet, total triangles}; face_of_tri_out (optional, [F]) receives the
+ * original face id of every meshlet triangle.  Verifies internally that every meshlet triangle maps back to its face. */
+int fp_op_build_meshlets(int V, int F, const float* pos, const int* faces, int* info, int* face_of_tri_out);
 /* which: 0 = erode_depth (Utils.py:359-395), 1 = bilateral_filter_depth (Utils.py:304-356) */
 int fp_op_depth_filter(const float* depth_dev, float* out_dev, int H, int W, int which, void* stream);
 /* egocentric_delta_pose_to_pose with the refiner's output decoding (predict_pose_refine.py:195-231) */

@@ -116,8 +116,7 @@ def test_score_tail_252(engine):
     assert int(best.item()) == int(ref.argmax())
 
 
-@pytest.mark.parametrize("impl", [0, 1])
-def test_attention_core(impl):
+def test_attention_core(impl=1):
     """softmax(QK^T/sqrt(128))V for 400 tokens x 4 heads vs torch fp32 on the same fp16 q, k, v."""
     from foundationpose_b200 import ops
 
