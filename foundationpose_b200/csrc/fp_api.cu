@@ -114,6 +114,7 @@ struct fp_ctx {
   bool use_graphs = true;
   bool cull_backfaces = true;  // FPOSE_NO_CULL=1: render both sides even for closed meshes (A/B checks)
   bool track_valid = false;
+  int crop_tile = 0;
   fp::DevBuf lt_buf, lr_buf, feat_buf, pose_stage;
   fp::DevBuf mask_buf, mask_stats, crop_stats;
   // fp_track: pinned host staging (frame in, pose out) so that the whole frame is ONE graph launch
@@ -370,6 +371,7 @@ static int make_crops(fp_ctx* c, const float* poses, int N, int mode, float* dbg
   p.dbg = dbg;
   p.win_out = win;
   p.stats = stats;
+  p.tile_override = c->crop_tile;
   return crop_launch(p, st);
 }
 
@@ -692,6 +694,15 @@ int fp_set_mesh(fp_ctx* c, int V, int F, const float* pos, const float* nrm, con
   for (int i = 0; i < 4; ++i) c->mesh_bs[i] = mh.bs[i];
   c->diameter = diameter;
   c->has_mesh = true;
+  ++c->epoch;
+  return 0;
+  FP_API_END
+}
+
+int fp_set_crop_tile(fp_ctx* c, int tile) {
+  FP_API_BEGIN
+  FP_REQUIRE(c && (tile == 0 || tile == 16 || tile == 32 || tile == 80), "fp_set_crop_tile: tile must be 0 (automatic), 16, 32 or 80");
+  c->crop_tile = tile;
   ++c->epoch;
   return 0;
   FP_API_END

@@ -32,7 +32,8 @@ int fp_prof_collect(int kind, double* total_ms, double* total_work, int* launche
   return fp::prof_collect(kind, total_ms, total_work, launches);
 }
 
-int fp_op_build_meshlets(int V, int F, const float* pos, const int* faces, int* info, int* face_of_tri_out) {
+int fp_op_build_meshlets(int V, int F, const float* pos, const int* faces, int* info, int* face_of_tri_out,
+                         float* meshlets_out) {
   try {
     if (!pos || !faces || !info || V <= 0 || F <= 0) {
       fp::set_last_error("fp_op_build_meshlets: bad argument");
@@ -71,6 +72,12 @@ int fp_op_build_meshlets(int V, int F, const float* pos, const int* faces, int* 
         if (face_of_tri_out) face_of_tri_out[m.tri_off + t] = (int)tr.y;
       }
     }
+    if (meshlets_out)
+      for (size_t i = 0; i < mh.meshlets.size(); ++i) {
+        const fp::Meshlet& m = mh.meshlets[i];
+        const float rec[8] = {m.cx, m.cy, m.cz, m.r, m.ax, m.ay, m.az, m.cutoff};
+        for (int k = 0; k < 8; ++k) meshlets_out[8 * i + k] = rec[k];
+      }
     info[0] = (int)mh.meshlets.size();
     info[1] = mh.closed;
     info[2] = mh.front_sign;

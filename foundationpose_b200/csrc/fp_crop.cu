@@ -21,14 +21,17 @@
 // znear < Z < zfar per pixel.
 #include "fp_crop.cuh"
 
+#include <stdlib.h>
+
 #include "fp_common.cuh"
 #include "fp_gemm.cuh"
 
 namespace fp {
 
 constexpr int S = 160;    // crop size (cfg.input_resize)
-constexpr int TILE = 32;  // tile edge in pixels
-constexpr int TPR = S / TILE;
+// Tile edge in pixels = template parameter TILE of the kernel: 80 (4 CTAs per hypothesis) for large batches — every
+// meshlet is set up by ~1.35 tiles instead of ~2 and the per-CTA prologue (window, tables, binning) is paid 4x, not 25x —
+// 32 for mid-size batches and 16 (100 CTAs per hypothesis) for track_one's single pose, where latency is what counts.
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kListCap = 1024;  // meshlet list entries per binning round
@@ -259,6 +262,7 @@ __device__ __forceinline__ void normalise_xyz(float x, float y, float z, const f
   if (inv || fabsf(oz) >= 2.f) oz = 0.f;
 }
 
+template <int TILE>
 struct TileSmem {
   unsigned long long zt[TILE * TILE];  // depth keys of the tile (0 = empty)
   VtxS sv[kWarps][kMeshletVerts];      // per-warp transformed vertices of the meshlet in flight
@@ -273,8 +277,15 @@ struct TileSmem {
 };
 
 // one triangle of a meshlet, all three vertices in front of the near plane: coverage inside the tile + depth test
+template <int TILE>
 __device__ __forceinline__ void raster_tri(const VtxS& a, const VtxS& b, const VtxS& c, unsigned face, int front_sign,
                                            int tx0, int ty0, float iz_far, unsigned long long* zt, int& n_frag) {
+  if (front_sign != 0) {
+    // closed mesh: a back-facing triangle is always behind a front-facing one that covers the same pixel centre.
+    // Same integer as the setup's area2 (the exact sign decides), computed first so that back faces leave early.
+    const long long area2 = (long long)(b.xi - a.xi) * (c.yi - a.yi) - (long long)(b.yi - a.yi) * (c.xi - a.xi);
+    if (area2 == 0 || (area2 > 0 ? 1 : -1) != front_sign) return;
+  }
   const int minx = min(a.xi, min(b.xi, c.xi)), maxx = max(a.xi, max(b.xi, c.xi));
   const int miny = min(a.yi, min(b.yi, c.yi)), maxy = max(a.yi, max(b.yi, c.yi));
   const int j0 = max((minx + 127) >> 8, tx0), j1 = min((maxx - 128) >> 8, tx0 + TILE - 1);
@@ -283,8 +294,6 @@ __device__ __forceinline__ void raster_tri(const VtxS& a, const VtxS& b, const V
   if (tri_small(a.xi, a.yi, b.xi, b.yi, c.xi, c.yi)) {
     TriSetup32 t;
     if (!tri_setup32(a.xi, a.yi, b.xi, b.yi, c.xi, c.yi, t)) return;
-    // closed mesh: a back-facing triangle is always behind a front-facing one that covers the same pixel centre
-    if (front_sign != 0 && (t.swapped ? 1 : -1) * front_sign > 0) return;
     for (int r = r0; r <= r1; ++r)
       for (int j = j0; j <= j1; ++j) {
         float b0, b1, b2;
@@ -297,7 +306,6 @@ __device__ __forceinline__ void raster_tri(const VtxS& a, const VtxS& b, const V
   } else {
     TriSetup t;
     if (!tri_setup(a.xi, a.yi, b.xi, b.yi, c.xi, c.yi, t)) return;
-    if (front_sign != 0 && (t.swapped ? 1 : -1) * front_sign > 0) return;
     for (int r = r0; r <= r1; ++r)
       for (int j = j0; j <= j1; ++j) {
         float b0, b1, b2;
@@ -310,19 +318,17 @@ __device__ __forceinline__ void raster_tri(const VtxS& a, const VtxS& b, const V
   }
 }
 
-// `swapped` of the setup structs: the ORIGINAL signed area was negative.  front_sign = sign of the original signed
-// area of a front-facing triangle, so a triangle is back-facing iff sign(original area) * front_sign < 0, i.e.
-// (swapped ? -1 : 1) * front_sign < 0  <=>  (swapped ? 1 : -1) * front_sign > 0.
-
 __device__ __forceinline__ float pixel_ray(float idx_plus_half, float origin, float rscale, float c, float f) {
   // crop pixel centre -> image coordinate -> normalised camera ray component
   const float u = __fadd_rn(origin, __fdiv_rn(idx_plus_half, rscale));
   return __fdiv_rn(__fsub_rn(u, c), f);
 }
 
-template <bool kStats>
+template <int TILE, bool kStats>
 __global__ void __launch_bounds__(kThreads, FP_CROP_MIN_CTAS) crop_tile_kernel(const CropParams p) {
-  __shared__ TileSmem sm;
+  constexpr int TPR = S / TILE;
+  extern __shared__ __align__(16) unsigned char crop_smem_raw[];
+  TileSmem<TILE>& sm = *reinterpret_cast<TileSmem<TILE>*>(crop_smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = blockIdx.y;
   const int tile = blockIdx.x;
@@ -356,6 +362,7 @@ __global__ void __launch_bounds__(kThreads, FP_CROP_MIN_CTAS) crop_tile_kernel(c
   const Window W = sm.win;
 
   // ---- per-axis tables of the observed-crop resampling for this tile's 32 columns and 32 rows
+  static_assert(2 * TILE <= kThreads, "one thread per table entry");
   if (tid < 2 * TILE) {
     const bool is_row = tid >= TILE;
     const int k = is_row ? tid - TILE : tid;
@@ -474,7 +481,7 @@ __global__ void __launch_bounds__(kThreads, FP_CROP_MIN_CTAS) crop_tile_kernel(c
           const int nfront = (a.Z > p.znear) + (b.Z > p.znear) + (c.Z > p.znear);
           if (nfront == 3) {
             ++n_tri;
-            raster_tri(a, b, c, trec[h].y, front_sign, tx0, ty0, iz_far, sm.zt, n_frag);
+            raster_tri<TILE>(a, b, c, trec[h].y, front_sign, tx0, ty0, iz_far, sm.zt, n_frag);
           } else if (nfront > 0) {
             mixed = true;
           }
@@ -502,12 +509,13 @@ __global__ void __launch_bounds__(kThreads, FP_CROP_MIN_CTAS) crop_tile_kernel(c
           }
           HomTri ht;
           hom_setup(Pc[0], Pc[1], Pc[2], ht);
-          const float dx = pixel_ray((float)(tx0 + lane) + 0.5f, W.umin, W.rsx, p.cx, p.fx);
-          for (int r = 0; r < TILE; ++r) {
+          for (int px = lane; px < TILE * TILE; px += 32) {
+            const int r = px / TILE, jl = px - r * TILE;
+            const float dx = pixel_ray((float)(tx0 + jl) + 0.5f, W.umin, W.rsx, p.cx, p.fx);
             const float dy = pixel_ray((float)(ty0 + r) + 0.5f, W.vmin, W.rsy, p.cy, p.fy);
             float l0, l1, l2, iz;
             if (hom_cover(ht, dx, dy, p.znear, p.zfar, l0, l1, l2, iz)) {
-              atomicMax(&sm.zt[r * TILE + lane], depth_key(iz, face));
+              atomicMax(&sm.zt[px], depth_key(iz, face));
               ++n_frag;
             }
           }
@@ -531,24 +539,24 @@ __global__ void __launch_bounds__(kThreads, FP_CROP_MIN_CTAS) crop_tile_kernel(c
     if (tid < 4) atomicAdd(p.stats + tid, sm.stat[tid]);
   }
 
-  // ---- shade: thread = column `lane` of rows warp*4 .. warp*4+3 of the tile
+  // ---- shade: a warp resolves 8 x 4-pixel blocks (coverage is coherent in 2-D: fewer warps straddle the silhouette
+  // than with 32 x 1 rows, and those are the ones that pay for both the covered and the background path)
   const float inv_radius = p.inv_radius;
   const float tvec[3] = {sm.P[3], sm.P[7], sm.P[11]};
   const float tau = p.mode == 0 ? 0.001f : 0.1f;
   const size_t img_stride = (size_t)(S + 6) * (S + 8) * 8;
   __half* outA = p.crops + (size_t)n * img_stride;
   __half* outB = p.crops + (size_t)(p.b_img0 + n) * img_stride;
-  const int j = tx0 + lane;
-  // observed-crop column quantities are shared by the thread's four rows
-  const float ixc = sm.colf[lane];
-  const int unc = sm.coln[lane], uzc = sm.colz[lane];
+  constexpr int kBlocksX = TILE / 8, kBlocks = kBlocksX * (TILE / 4);
 #pragma unroll 1
-  for (int k = 0; k < TILE / kWarps; ++k) {
-    const int rl = warp * (TILE / kWarps) + k;
-    const int r = ty0 + rl;
+  for (int blk = warp; blk < kBlocks; blk += kWarps) {
+    const int jl = (blk % kBlocksX) * 8 + (lane & 7), rl = (blk / kBlocksX) * 4 + (lane >> 3);
+    const int j = tx0 + jl, r = ty0 + rl;
+    const float ixc = sm.colf[jl];
+    const int unc = sm.coln[jl], uzc = sm.colz[jl];
     // ---- A: rendered crop
     float ar = 0.f, ag = 0.f, ab = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
-    const unsigned long long key = sm.zt[rl * TILE + lane];
+    const unsigned long long key = sm.zt[rl * TILE + jl];
     if (key != 0ull) {
       const int f = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
       const int4 fi = __ldg(M.faces + f);
@@ -678,7 +686,7 @@ __global__ void __launch_bounds__(kThreads, FP_CROP_MIN_CTAS) crop_tile_kernel(c
       normalise_xyz(X, Y, Z, tvec, inv_radius, tau, bx, by, bz);
     }
     // even / odd padded columns live in separate half-rows ("EO" layout, fp_stem.cu): pixel (row, col) ->
-    // [row][col & 1][col >> 1][8]; a warp (32 consecutive columns of one row) writes two 256-byte runs per image
+    // [row][col & 1][col >> 1][8]; a warp (8 columns x 4 rows) writes two 64-byte runs per row and image
     const int pc = j + 3;
     const size_t off = (((size_t)(r + 3) * 2 + (pc & 1)) * ((S + 8) / 2) + (pc >> 1)) * 8;
     *reinterpret_cast<uint4*>(outA + off) = make_uint4(pack_half2(ar, ag), pack_half2(ab, ax), pack_half2(ay, az), 0u);
@@ -693,16 +701,45 @@ __global__ void __launch_bounds__(kThreads, FP_CROP_MIN_CTAS) crop_tile_kernel(c
   }
 }
 
+static int g_crop_tile_override = [] {
+  const char* e = getenv("FPOSE_CROP_TILE");  // 16 / 32 / 80: force one tile size (A/B measurements)
+  const int v = e ? atoi(e) : 0;
+  return (v == 16 || v == 32 || v == 80) ? v : 0;
+}();
+
+#define FP_TRY_RC(expr)  \
+  do {                   \
+    int _rc = (expr);    \
+    if (_rc) return _rc; \
+  } while (0)
+
+template <int TILE>
+static int launch_tile(const CropParams& p, cudaStream_t stream) {
+  constexpr int TPR = S / TILE;
+  const size_t smem = sizeof(TileSmem<TILE>);
+  static std::atomic<unsigned long long> attr_mask{0};  // per device
+  if (!device_bit_test(attr_mask)) {
+    FP_CUDA_OK(cudaFuncSetAttribute(crop_tile_kernel<TILE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FP_CUDA_OK(cudaFuncSetAttribute(crop_tile_kernel<TILE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    device_bit_set(attr_mask);
+  }
+  const dim3 grid(TPR * TPR, p.N);
+  if (p.stats) {
+    FP_CUDA_OK(launch_pdl(crop_tile_kernel<TILE, true>, grid, dim3(kThreads), smem, stream, 1, p));
+  } else {
+    FP_CUDA_OK(launch_pdl(crop_tile_kernel<TILE, false>, grid, dim3(kThreads), smem, stream, 1, p));
+  }
+  return 0;
+}
+
 int crop_launch(const CropParams& p, cudaStream_t stream) {
   if (p.N == 0) return 0;
   // algorithmic bytes: the two 6-channel fp16 crops each hypothesis produces
   prof_mark_begin(1, (double)p.N * 2.0 * 6.0 * S * S * 2.0, stream);
-  const dim3 grid(TPR * TPR, p.N);
-  if (p.stats) {
-    FP_CUDA_OK(launch_pdl(crop_tile_kernel<true>, grid, dim3(kThreads), 0, stream, 1, p));
-  } else {
-    FP_CUDA_OK(launch_pdl(crop_tile_kernel<false>, grid, dim3(kThreads), 0, stream, 1, p));
-  }
+  int tile = p.N >= 64 ? 80 : (p.N >= 4 ? 32 : 16);
+  if (g_crop_tile_override) tile = g_crop_tile_override;
+  if (p.tile_override == 16 || p.tile_override == 32 || p.tile_override == 80) tile = p.tile_override;
+  FP_TRY_RC(tile == 80 ? launch_tile<80>(p, stream) : (tile == 32 ? launch_tile<32>(p, stream) : launch_tile<16>(p, stream)));
   prof_mark_end(stream);
   note_launches(1);
   FP_CUDA_OK(cudaGetLastError());

@@ -60,6 +60,7 @@ struct CropParams {
   int b_img0;      // first B image (N rounded up to the conv tile's image count, see fp_api.cu)
   float* dbg;      // optional [N][2][160][160][6] fp32 copy of the normalised crops
   float* win_out;  // optional [N][4] = (left, top, sx, sy)
+  int tile_override;  // 0 = pick by batch size; 16 / 32 / 80 = force (fp_set_crop_tile, A/B tests)
   int* stats;      // optional [4]: meshlet visits, triangles set up, fragments, mixed (near-plane) triangles
 };
 

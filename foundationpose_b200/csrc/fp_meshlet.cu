@@ -4,8 +4,9 @@
 //     of the position-welded mesh occurs exactly once and its reverse exactly once); the sign of the enclosed volume
 //     tells which screen-space winding is front-facing.  nvdiffrast (Utils.py:182) renders both sides, so an open mesh
 //     keeps both sides here too;
-//   * builds meshlets: faces are sorted by (normal octant, Morton code of the centroid) and chunked greedily into
-//     groups of <= 64 triangles / <= 64 unique vertices, each with a bounding sphere and a normal cone.
+//   * builds meshlets by region growing over the face adjacency (nearest-centroid, normal-coherent growth from a seed
+//     face): connected, compact patches of <= 64 triangles / <= 64 unique vertices, each with a bounding sphere and a
+//     normal cone.
 // Pure host code (no kernels); compiled with the rest of the library.
 #include <math.h>
 #include <stdint.h>
@@ -120,7 +121,7 @@ int build_mesh_host(int V, int F, const float* pos, const float* nrm, const floa
   // NEGATIVE signed screen area (x1-x0)(y2-y0) - (y1-y0)(x2-x0); inside-out meshes (negative volume) flip that
   out.front_sign = !closed || vol6 == 0.0 ? 0 : (vol6 > 0.0 ? -1 : 1);
 
-  // ---- sort faces: (normal octant, Morton code of the centroid)
+  // ---- face centroids / unit normals, Morton order of the centroids (seed order for disconnected pieces)
   V3 lo = {1e300, 1e300, 1e300}, hi = {-1e300, -1e300, -1e300};
   for (int v = 0; v < V; ++v) {
     const V3 p = P(v);
@@ -137,24 +138,56 @@ int build_mesh_host(int V, int F, const float* pos, const float* nrm, const floa
     out.bs[2] = (float)c.z;
     out.bs[3] = (float)(r * 1.0001 + 1e-9);
   }
-  std::vector<V3> fn(F);
+  std::vector<V3> fn(F), fc(F);
   std::vector<uint64_t> key(F);
   for (int f = 0; f < F; ++f) {
     const V3 a = P(faces[3 * f]), b = P(faces[3 * f + 1]), c = P(faces[3 * f + 2]);
     V3 n = cross(sub(b, a), sub(c, a));
     const double l = norm(n);
     fn[f] = l > 0 ? V3{n.x / l, n.y / l, n.z / l} : V3{0, 0, 0};
-    const V3 ctr = {(a.x + b.x + c.x) / 3, (a.y + b.y + c.y) / 3, (a.z + b.z + c.z) / 3};
-    const uint32_t qx = (uint32_t)std::min(1023.0, (ctr.x - lo.x) / ext * 1023.0);
-    const uint32_t qy = (uint32_t)std::min(1023.0, (ctr.y - lo.y) / ext * 1023.0);
-    const uint32_t qz = (uint32_t)std::min(1023.0, (ctr.z - lo.z) / ext * 1023.0);
-    const uint64_t morton = part1by2(qx) | (part1by2(qy) << 1) | (part1by2(qz) << 2);
-    const uint64_t oct = out.front_sign ? (uint64_t)((fn[f].x < 0) | ((fn[f].y < 0) << 1) | ((fn[f].z < 0) << 2)) : 0;
-    key[f] = (oct << 32) | morton;
+    fc[f] = {(a.x + b.x + c.x) / 3, (a.y + b.y + c.y) / 3, (a.z + b.z + c.z) / 3};
+    const uint32_t qx = (uint32_t)std::min(1023.0, (fc[f].x - lo.x) / ext * 1023.0);
+    const uint32_t qy = (uint32_t)std::min(1023.0, (fc[f].y - lo.y) / ext * 1023.0);
+    const uint32_t qz = (uint32_t)std::min(1023.0, (fc[f].z - lo.z) / ext * 1023.0);
+    key[f] = part1by2(qx) | (part1by2(qy) << 1) | (part1by2(qz) << 2);
   }
   std::vector<int> order(F);
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+
+  // ---- face adjacency over the welded edges (CSR); non-manifold edges link all their faces
+  std::vector<int> adj_off(F + 1, 0), adj;
+  {
+    std::vector<std::pair<uint64_t, int>> ef;
+    ef.reserve((size_t)F * 3);
+    for (int f = 0; f < F; ++f) {
+      const int i[3] = {canon[faces[3 * f]], canon[faces[3 * f + 1]], canon[faces[3 * f + 2]]};
+      for (int e = 0; e < 3; ++e) {
+        const int a = i[e], b = i[(e + 1) % 3];
+        if (a == b) continue;
+        ef.push_back({((uint64_t)(uint32_t)std::min(a, b) << 32) | (uint32_t)std::max(a, b), f});
+      }
+    }
+    std::sort(ef.begin(), ef.end());
+    std::vector<std::pair<int, int>> links;
+    for (size_t s0 = 0; s0 < ef.size();) {
+      size_t s1 = s0;
+      while (s1 < ef.size() && ef[s1].first == ef[s0].first) ++s1;
+      const size_t run = std::min<size_t>(s1 - s0, 8);  // cap pathological fans
+      for (size_t a = s0; a < s0 + run; ++a)
+        for (size_t b = a + 1; b < s0 + run; ++b)
+          if (ef[a].second != ef[b].second) {
+            links.push_back({ef[a].second, ef[b].second});
+            links.push_back({ef[b].second, ef[a].second});
+          }
+      s0 = s1;
+    }
+    for (auto& l : links) ++adj_off[l.first + 1];
+    for (int f = 0; f < F; ++f) adj_off[f + 1] += adj_off[f];
+    adj.resize(links.size());
+    std::vector<int> fill(adj_off.begin(), adj_off.end() - 1);
+    for (auto& l : links) adj[fill[l.first]++] = l.second;
+  }
 
   // ---- greedy chunking
   out.meshlets.clear();
@@ -211,32 +244,98 @@ int build_mesh_host(int V, int F, const float* pos, const float* nrm, const floa
     cur_faces.clear();
     cur_tris.clear();
   };
-  uint64_t cur_oct = ~0ull;
-  for (int k = 0; k < F; ++k) {
-    const int f = order[k];
-    const int i[3] = {faces[3 * f], faces[3 * f + 1], faces[3 * f + 2]};
-    const uint64_t oct = key[f] >> 32;
-    int fresh = 0;
-    for (int e = 0; e < 3; ++e) {
-      bool dup = false;
-      for (int e2 = 0; e2 < e; ++e2) dup = dup || i[e2] == i[e];
-      if (slot_of[i[e]] < 0 && !dup) ++fresh;
+  // ---- region growing: a meshlet starts at a seed face and repeatedly takes, from the faces adjacent to it, the
+  // one whose centroid is nearest to the meshlet's (penalised by how far its normal turns away from the meshlet's
+  // mean normal) until it holds 64 triangles or 64 vertices.  Compact, connected patches: small bounding spheres
+  // (fewer tiles per meshlet) and tight normal cones (more meshlets culled as back-facing).
+  std::vector<char> assigned(F, 0), in_frontier(F, 0);
+  std::vector<int> pending;  // faces that bordered a finished meshlet: preferred seeds (keeps neighbours together)
+  size_t cursor = 0;         // Morton-order fallback for disconnected components
+  int n_assigned = 0;
+  std::vector<int> frontier;
+  while (n_assigned < F) {
+    int seed = -1;
+    while (!pending.empty() && seed < 0) {
+      const int f = pending.back();
+      pending.pop_back();
+      if (!assigned[f]) seed = f;
     }
-    if (oct != cur_oct || (int)cur_faces.size() == kMeshletTris || (int)cur_verts.size() + fresh > kMeshletVerts) flush();
-    cur_oct = oct;
-    uint32_t packed = 0;
-    for (int e = 0; e < 3; ++e) {
-      if (slot_of[i[e]] < 0) {
-        slot_of[i[e]] = (int)cur_verts.size();
-        cur_verts.push_back(i[e]);
+    while (seed < 0) {
+      const int f = order[cursor++];
+      if (!assigned[f]) seed = f;
+    }
+    frontier.clear();
+    V3 csum = {0, 0, 0}, nsum = {0, 0, 0};
+    int next = seed;
+    while (next >= 0) {
+      const int f = next;
+      const int i[3] = {faces[3 * f], faces[3 * f + 1], faces[3 * f + 2]};
+      uint32_t packed = 0;
+      for (int e = 0; e < 3; ++e) {
+        if (slot_of[i[e]] < 0) {
+          slot_of[i[e]] = (int)cur_verts.size();
+          cur_verts.push_back(i[e]);
+        }
+        packed |= (uint32_t)slot_of[i[e]] << (8 * e);
       }
-      packed |= (uint32_t)slot_of[i[e]] << (8 * e);
+      cur_tris.push_back(make_uint2(packed, (unsigned)f));
+      cur_faces.push_back(f);
+      assigned[f] = 1;
+      ++n_assigned;
+      csum = {csum.x + fc[f].x, csum.y + fc[f].y, csum.z + fc[f].z};
+      nsum = {nsum.x + fn[f].x, nsum.y + fn[f].y, nsum.z + fn[f].z};
+      for (int a = adj_off[f]; a < adj_off[f + 1]; ++a) {
+        const int g = adj[a];
+        if (!assigned[g] && !in_frontier[g]) {
+          in_frontier[g] = 1;
+          frontier.push_back(g);
+        }
+      }
+      next = -1;
+      if ((int)cur_faces.size() == kMeshletTris) break;
+      const double inv = 1.0 / cur_faces.size();
+      const V3 ctr = {csum.x * inv, csum.y * inv, csum.z * inv};
+      const double nl = norm(nsum);
+      double best = 1e300;
+      size_t best_k = 0;
+      for (size_t k2 = 0; k2 < frontier.size(); ++k2) {
+        const int g = frontier[k2];
+        if (assigned[g]) continue;
+        int fresh = 0;
+        for (int e = 0; e < 3; ++e) {
+          const int v = faces[3 * g + e];
+          bool dup = false;
+          for (int e2 = 0; e2 < e; ++e2) dup = dup || faces[3 * g + e2] == v;
+          if (slot_of[v] < 0 && !dup) ++fresh;
+        }
+        if ((int)cur_verts.size() + fresh > kMeshletVerts) continue;
+        const V3 dv = sub(fc[g], ctr);
+        const double turn = nl > 1e-12 ? 1.0 - dot(fn[g], nsum) / nl : 0.0;  // 0 = parallel, 2 = opposite
+        // faces about to be orphaned (no / one unassigned neighbour left) go first: fewer left-over islands
+        int live = 0;
+        for (int a = adj_off[g]; a < adj_off[g + 1]; ++a) live += !assigned[adj[a]];
+        const double orphan = live == 0 ? 0.2 : (live == 1 ? 0.55 : 1.0);
+        const double score = dot(dv, dv) * (1.0 + 2.0 * turn) * orphan + 1e-30 * fresh;
+        if (score < best) {
+          best = score;
+          best_k = k2;
+          next = g;
+        }
+      }
+      if (next >= 0) {
+        frontier[best_k] = frontier.back();
+        frontier.pop_back();
+        in_frontier[next] = 0;
+      }
     }
-    cur_tris.push_back(make_uint2(packed, (unsigned)f));
-    cur_faces.push_back(f);
+    for (int g : frontier) {
+      in_frontier[g] = 0;
+      if (!assigned[g]) pending.push_back(g);
+    }
+    flush();
   }
-  flush();
   return 0;
+
 }
 
 }  // namespace fp

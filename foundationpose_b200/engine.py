@@ -25,6 +25,7 @@ def _proto():
     lib.fp_destroy.argtypes = [vp]
     lib.fp_set_config.argtypes = [vp, i, f, f]
     lib.fp_mesh_info.argtypes = [vp, C.POINTER(i)]
+    lib.fp_set_crop_tile.argtypes = [vp, i]
     lib.fp_crop_stats.argtypes = [vp, vp, i, i, C.POINTER(i), vp]
     lib.fp_track.argtypes = [vp, vp, vp, C.POINTER(f), i, i, vp, i, vp, vp, vp]
     lib.fp_load_network.argtypes = [vp, i, C.POINTER(_FpTensor), i]
@@ -44,7 +45,7 @@ def _proto():
     lib.fp_op_tokens.argtypes = [vp, i, vp, i, vp, vp]
     lib.fp_op_depth_filter.argtypes = [vp, vp, i, i, i, vp]
     lib.fp_op_pose_update.argtypes = [vp, vp, vp, vp, i, f, f, vp]
-    for name in ("fp_create", "fp_destroy", "fp_set_config", "fp_mesh_info", "fp_crop_stats", "fp_track", "fp_set_xyz_map", "fp_load_network", "fp_set_mesh", "fp_set_frame",
+    for name in ("fp_create", "fp_destroy", "fp_set_config", "fp_mesh_info", "fp_set_crop_tile", "fp_crop_stats", "fp_track", "fp_set_xyz_map", "fp_load_network", "fp_set_mesh", "fp_set_frame",
                  "fp_get_depth", "fp_make_crops", "fp_start_poses", "fp_refine", "fp_score", "fp_score_features", "fp_score_tail",
                  "fp_register", "fp_op_refine_net", "fp_op_score_feats", "fp_op_tokens", "fp_op_depth_filter",
                  "fp_op_pose_update"):
@@ -193,6 +194,10 @@ class Engine:
         info = (C.c_int * 5)()
         _lib.check(lib.fp_mesh_info(self._h, info), "fp_mesh_info")
         return dict(meshlets=info[0], closed=bool(info[1]), front_sign=info[2], V=info[3], F=info[4])
+
+    def set_crop_tile(self, tile=0):
+        """Force the crop producer's tile edge (16 / 32 / 80; 0 = automatic from the batch size)."""
+        _lib.check(lib.fp_set_crop_tile(self._h, int(tile)), "fp_set_crop_tile")
 
     def crop_stats(self, poses, mode=0):
         """Work counters of one crop pass: dict(meshlet_visits, triangles, fragments, near_plane_triangles)."""

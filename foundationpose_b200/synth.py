@@ -149,3 +149,77 @@ def default_scene(subdivisions=5, seed=0):
     pose[:3, 3] = [0.0, 0.0, 0.6]
     rgb, depth, mask = make_scene(mesh.visual.image, pose)
     return mesh, pose, DEFAULT_K.copy(), rgb, depth, mask
+
+
+def track_sequence(n_frames, pose0, seed=3, max_trans=0.005, max_rot_deg=2.0):
+    """Ground-truth poses of a synthetic tracking sequence: the object moves by at most
+    `max_trans` metres and `max_rot_deg` degrees per frame (a smooth random walk, rng(seed))."""
+    rng = np.random.default_rng(seed)
+    poses = [np.asarray(pose0, dtype=np.float64).copy()]
+    vel_t = rng.normal(size=3)
+    vel_r = rng.normal(size=3)
+    for _ in range(1, n_frames):
+        vel_t = 0.9 * vel_t + 0.4 * rng.normal(size=3)
+        vel_r = 0.9 * vel_r + 0.4 * rng.normal(size=3)
+        dt = vel_t / max(np.linalg.norm(vel_t), 1e-9) * max_trans * min(1.0, np.linalg.norm(vel_t) / 2.0)
+        ang = np.deg2rad(max_rot_deg) * min(1.0, np.linalg.norm(vel_r) / 2.0)
+        ax = vel_r / max(np.linalg.norm(vel_r), 1e-9)
+        Kx = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        dR = np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * (Kx @ Kx)
+        p = poses[-1].copy()
+        p[:3, :3] = dR @ p[:3, :3]
+        p[:3, 3] = p[:3, 3] + dt * np.array([1.0, 1.0, 0.5])
+        poses.append(p)
+    return np.stack(poses)
+
+
+def write_obj(mesh, path):
+    """Wavefront OBJ + MTL + PNG texture of a SimpleMesh (uv in the trimesh convention: v = 0 at the image bottom)."""
+    import os
+
+    import cv2
+
+    stem = os.path.splitext(os.path.basename(path))[0]
+    d = os.path.dirname(path)
+    os.makedirs(d, exist_ok=True)
+    with open(path, "w") as fh:
+        fh.write(f"mtllib {stem}.mtl\nusemtl material_0\n")
+        for p in mesh.vertices:
+            fh.write(f"v {p[0]:.9g} {p[1]:.9g} {p[2]:.9g}\n")
+        for n in mesh.vertex_normals:
+            fh.write(f"vn {n[0]:.9g} {n[1]:.9g} {n[2]:.9g}\n")
+        for t in mesh.visual.uv:
+            fh.write(f"vt {t[0]:.9g} {t[1]:.9g}\n")
+        for f in mesh.faces + 1:
+            fh.write("f " + " ".join(f"{i}/{i}/{i}" for i in f) + "\n")
+    with open(os.path.join(d, stem + ".mtl"), "w") as fh:
+        fh.write(f"newmtl material_0\nKa 1 1 1\nKd 1 1 1\nKs 0 0 0\nmap_Kd {stem}.png\n")
+    cv2.imwrite(os.path.join(d, stem + ".png"), mesh.visual.image[..., ::-1])
+
+
+def write_demo_scene(root, n_frames=5, subdivisions=3, seed=0):
+    """A scene directory in the layout of the reference's demo data (run_demo.py:18-19, datareader.py:57-152):
+    mesh/textured_simple.obj (+ .mtl + .png), cam_K.txt, rgb/*.png, depth/*.png (uint16 millimetres), masks/*.png and
+    annotated_poses/*.txt (ground truth).  Returns (mesh, gt_poses)."""
+    import os
+
+    import cv2
+
+    mesh = make_mesh(subdivisions)
+    pose0 = np.eye(4)
+    pose0[:3, :3] = random_rotation(seed)
+    pose0[:3, 3] = [0.02, -0.01, 0.6]
+    poses = track_sequence(n_frames, pose0)
+    write_obj(mesh, os.path.join(root, "mesh", "textured_simple.obj"))
+    for sub in ("rgb", "depth", "masks", "annotated_poses"):
+        os.makedirs(os.path.join(root, sub), exist_ok=True)
+    np.savetxt(os.path.join(root, "cam_K.txt"), DEFAULT_K)
+    for i, p in enumerate(poses):
+        rgb, depth, mask = make_scene(mesh.visual.image, p, seed=1 + i)
+        name = f"{i:06d}"
+        cv2.imwrite(os.path.join(root, "rgb", name + ".png"), rgb[..., ::-1])
+        cv2.imwrite(os.path.join(root, "depth", name + ".png"), np.clip(np.rint(depth * 1000.0), 0, 65535).astype(np.uint16))
+        if i == 0:
+            cv2.imwrite(os.path.join(root, "masks", name + ".png"), mask.astype(np.uint8) * 255)
+        np.savetxt(os.path.join(root, "annotated_poses", name + ".txt"), p)
+    return mesh, poses

@@ -143,6 +143,9 @@ int fp_start_poses(fp_ctx* ctx, const unsigned char* mask, int mask_on_device, c
  * ([N][4] = left, top, sx, sy of tf_to_crop). */
 int fp_make_crops(fp_ctx* ctx, const float* poses, int N, int mode, void* crops_out, float* dbg_out, float* win_out,
                   void* stream);
+/* Tile edge of the crop producer: 0 = chosen from the batch size (80 px for >= 64 hypotheses, 32 px, 16 px for < 4),
+ * or force 16 / 32 / 80 (A/B measurements and the tile-size invariance test: the crops do not depend on it). */
+int fp_set_crop_tile(fp_ctx* ctx, int tile);
 /* Work counters of one crop pass (profiling hook; synchronises): stats_out_host[4] = {meshlet visits, triangles set
  * up, fragments depth-tested, triangles that took the near-plane path}. */
 int fp_crop_stats(fp_ctx* ctx, const float* poses, int N, int mode, int* stats_out_host, void* stream);
@@ -184,7 +187,8 @@ int fp_op_tokens(fp_ctx* ctx, int which, const void* crops, int N, void* tokens_
  * vertices + closedness / orientation analysis.  info[6] = {meshlets, closed (0/1), front-face winding sign (0 = none),
  * max triangles per meshlet, max vertices per meshlet, total triangles}; face_of_tri_out (optional, [F]) receives the
  * original face id of every meshlet triangle.  Verifies internally that every meshlet triangle maps back to its face. */
-int fp_op_build_meshlets(int V, int F, const float* pos, const int* faces, int* info, int* face_of_tri_out);
+int fp_op_build_meshlets(int V, int F, const float* pos, const int* faces, int* info, int* face_of_tri_out,
+                         float* meshlets_out /* optional [ceil(F/1)][8]: sphere xyz r, cone axis xyz cutoff */);
 /* which: 0 = erode_depth (Utils.py:359-395), 1 = bilateral_filter_depth (Utils.py:304-356) */
 int fp_op_depth_filter(const float* depth_dev, float* out_dev, int H, int W, int which, void* stream);
 /* egocentric_delta_pose_to_pose with the refiner's output decoding (predict_pose_refine.py:195-231) */

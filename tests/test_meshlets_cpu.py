@@ -10,13 +10,13 @@ def _build(verts, faces):
     from foundationpose_b200 import _lib
 
     lib = _lib.lib
-    lib.fp_op_build_meshlets.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]
+    lib.fp_op_build_meshlets.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
     lib.fp_op_build_meshlets.restype = C.c_int
     pos = np.ascontiguousarray(verts, dtype=np.float32)
     fc = np.ascontiguousarray(faces, dtype=np.int32)
     info = (C.c_int * 6)()
     face_of = np.full(len(fc), -1, dtype=np.int32)
-    rc = lib.fp_op_build_meshlets(len(pos), len(fc), pos.ctypes.data, fc.ctypes.data, info, face_of.ctypes.data)
+    rc = lib.fp_op_build_meshlets(len(pos), len(fc), pos.ctypes.data, fc.ctypes.data, info, face_of.ctypes.data, None)
     assert rc == 0, _lib.lib.fp_last_error()
     return dict(meshlets=info[0], closed=info[1], front_sign=info[2], max_tris=info[3], max_verts=info[4], total=info[5]), face_of
 

@@ -99,7 +99,8 @@ def test_score_feats_and_tail(engine):
     # tail on identical (oracle) features: fp32 SIMT vs fp32 torch
     scores, best = e.score_tail(ref_feats.cuda())
     ref_logits = nets.score_tail(sd_s, ref_feats, 5).reshape(-1)
-    np.testing.assert_allclose(scores.cpu().numpy() - 100.0, ref_logits.numpy(), atol=2e-3, rtol=0)
+    # fp32 on both sides: the bar is relative to the magnitude of the logits (the stand-in read-out is scaled x60)
+    np.testing.assert_allclose(scores.cpu().numpy() - 100.0, ref_logits.numpy(), atol=2e-5 * float(ref_logits.abs().max()) + 2e-5, rtol=0)
     assert int(best.item()) == int(ref_logits.argmax())
 
 
@@ -112,7 +113,7 @@ def test_score_tail_252(engine):
     feats = torch.randn(252, 512, generator=g) * 2
     scores, best = e.score_tail(feats.cuda())
     ref = nets.score_tail(sd_s, feats, 252).reshape(-1)
-    np.testing.assert_allclose(scores.cpu().numpy() - 100.0, ref.numpy(), atol=3e-3, rtol=0)
+    np.testing.assert_allclose(scores.cpu().numpy() - 100.0, ref.numpy(), atol=2e-5 * float(ref.abs().max()) + 2e-5, rtol=0)
     assert int(best.item()) == int(ref.argmax())
 
 

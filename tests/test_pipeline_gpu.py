@@ -74,10 +74,13 @@ def test_score_matches_oracle(setup):
     got = scores.cpu().numpy()
     ref = ref_scores.numpy()
     print("scores", got, ref)
-    np.testing.assert_allclose(got, ref, atol=1e-2, rtol=0)
+    spread = float(ref.std())
+    err = got - ref
+    assert np.abs(err).max() <= 0.1 * spread, f"score error {np.abs(err).max():.3g} vs spread {spread:.3g}"
     top2 = np.sort(ref)[-2:]
-    if top2[1] - top2[0] > 2e-2:  # index parity is only defined when the oracle's margin exceeds the tolerance
-        assert int(best.item()) == ref_best
+    print(f"top-2 margin {top2[1] - top2[0]:.4f}, rank-relevant error {np.abs(err - err.mean()).max():.2e}")
+    assert top2[1] - top2[0] > 10 * np.abs(err - err.mean()).max(), "margin must dominate the score error"
+    assert int(best.item()) == ref_best
     assert int(best.item()) == int(np.argmax(got))
 
 

@@ -139,6 +139,30 @@ def test_culling_does_not_change_the_crops():
     assert n_px <= 4 * len(poses), f"{n_px} pixels differ between culled and unculled rendering (max {diff.max():.3g})"
 
 
+def test_tile_size_does_not_change_the_crops():
+    """16 / 32 / 80-pixel tiles (track_one, sharded, full batch) produce bit-identical crop buffers."""
+    from foundationpose_b200 import synth
+
+    mesh = synth.make_mesh(4)
+    pose = _base_pose()
+    poses = np.stack([pose] * 5).astype(np.float32)
+    for i in range(1, 5):
+        poses[i, :3, :3] = synth.random_rotation(60 + i)
+    poses[4, :3, 3] = [0.2, 0.12, 0.45]
+    e, mt, rgb, depth, d = _setup(mesh, pose, poses)
+    ref = None
+    for tile in (16, 32, 80):
+        e.set_crop_tile(tile)
+        for mode in (0, 1):
+            c, _, _ = e.make_crops(poses, mode=mode)
+            if tile == 16:
+                ref = ref or {}
+                ref[mode] = c.clone()
+            else:
+                assert torch.equal(c, ref[mode]), f"tile {tile}, mode {mode}: crops differ from the 16-pixel tiling"
+    e.set_crop_tile(0)
+
+
 def test_mesh_swap_between_graph_replays():
     """a larger mesh after a (kind, N, iters) graph exists must not allocate during capture."""
     from foundationpose_b200 import synth

@@ -33,8 +33,11 @@ def main():
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         peak = 6650.0
-    for n in (252, 32, 1):
+    tiles = [int(t) for t in os.environ.get("PROBE_TILES", "0").split(",")]
+    for n, tile in [(n, t) for n in (252, 32, 1) for t in tiles]:
         p = torch.from_numpy(poses[:n]).cuda()
+        e.set_crop_tile(tile)
+        print(f"--- N={n} tile={tile or 'auto'}")
         for mode in (0, 1):
             for _ in range(5):
                 e.make_crops(p, mode=mode, want_crops=False)
