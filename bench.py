@@ -8,6 +8,8 @@ reference architectures.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...      # the reference networks on the host CPU cores
+    python bench.py --impl torch-cuda ...     # GPU STAND-IN for the reference's CUDA build (not the reference arm):
+                                              # the oracle port of its networks on CUDA under fp16 autocast
 
 A step = one pass of the hot path over one frame.  `value` = hypotheses / step time with the frame,
 mesh and weights resident in HBM (device-timed with CUDA events, max over ranks); `e2e` = the same
@@ -93,19 +95,43 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def physical_cores_one_socket():
+    """Physical cores of socket 0 (from /proc/cpuinfo); falls back to os.cpu_count()."""
+    try:
+        cores, phys, cur = set(), None, {}
+        for line in open("/proc/cpuinfo"):
+            if ":" in line:
+                k, v = [x.strip() for x in line.split(":", 1)]
+                cur[k] = v
+            elif cur:
+                if cur.get("physical id", "0") == "0":
+                    cores.add(cur.get("core id", cur.get("processor")))
+                cur = {}
+        if cur and cur.get("physical id", "0") == "0":
+            cores.add(cur.get("core id", cur.get("processor")))
+        return max(1, len(cores))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def pick_cpu_threads(fn):
-    """torch's intra-op pool oversubscribes badly on many-core hosts for these small batches: try a few
-    thread counts on the probe workload and keep the fastest (the baseline gets its best configuration).
-    Returns (threads, seconds per call)."""
-    total = os.cpu_count() or 1
-    cands = sorted({c for c in (8, 16, 32, 64, total) if c <= total})
+    """torch's intra-op pool oversubscribes badly on many-core hosts for these small batches, and crossing sockets or
+    using SMT siblings makes it worse (round 1: 128 threads on the 8-GPU box gave the slowest result).  Fixed candidate
+    set capped at the physical cores of ONE socket; per candidate 2 warm-ups, then the median of 3 timed calls; the
+    fastest wins.  Returns (threads, seconds per call)."""
+    cap = min(physical_cores_one_socket(), os.cpu_count() or 1)
+    cands = sorted({c for c in (8, 16, 32, cap) if c <= cap}) or [cap]
     best = (None, float("inf"))
     for c in cands:
         torch.set_num_threads(c)
         fn()
-        t0 = time.perf_counter()
         fn()
-        dt = time.perf_counter() - t0
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        dt = sorted(ts)[1]
         if dt < best[1]:
             best = (c, dt)
     torch.set_num_threads(best[0])
@@ -134,7 +160,7 @@ def cpu_nets_rate(budget_s=20.0):
     nets.score_forward(sd_s, A, B, L=n)
     t_sc = (time.perf_counter() - t0) / n
     rate = 1.0 / (N_ITER * t_ref + t_sc)
-    return rate, cores, (f"RefineNet + ScoreNetMultiPair (oracle port, fp32 torch CPU, {cores} threads, best of 8/16/32/64/all) on {n} pre-built 160x160 crop pairs; "
+    return rate, cores, (f"RefineNet + ScoreNetMultiPair (oracle port, fp32 torch CPU, {cores} threads = best of 8/16/32/one socket's physical cores) on {n} pre-built 160x160 crop pairs; "
                          f"{t_ref * 1e3:.1f} ms/hyp-iter refine, {t_sc * 1e3:.1f} ms/hyp score; extrapolated to {N_ITER} iters + 1 score; raster/warp not included")
 
 
@@ -198,12 +224,100 @@ def run_reference(args, rank, world):
     })
 
 
+def load_traffic():
+    """DRAM bytes per launch of the roofline kernels, measured by `ncu --set full` and committed by
+    tools/ncu_summary.py as profiles/r02_ncu_traffic.json (kernel-name prefix -> dram read + write bytes of ONE launch)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return {}
+
+
+class TorchCudaStandin:
+    """GPU STAND-IN for the reference's nvdiffrast + PyTorch CUDA build, which cannot be installed here (SURVEY.md §8d
+    last row): the oracle port of the reference networks as plain torch ops on CUDA under fp16 autocast with
+    cudnn.benchmark = False / deterministic = True (what register()'s set_seed(0) leaves, Utils.py:222-229), fed with
+    crops from THIS repository's producer because nvdiffrast / kornia are absent.  Clearly a stand-in: it is never the
+    `--impl reference` arm."""
+
+    def __init__(self, eng, sd_r, sd_s, diameter):
+        from oracle import geometry, nets
+
+        self.eng, self.nets, self.geometry, self.d = eng, nets, geometry, diameter
+        self.sd_r = {k: v.cuda() for k, v in sd_r.items()}
+        self.sd_s = {k: v.cuda() for k, v in sd_s.items()}
+        torch.backends.cudnn.benchmark = False
+        torch.backends.cudnn.deterministic = True
+
+    def crops(self, poses, mode):
+        _, dbg, _ = self.eng.make_crops(poses, mode=mode, want_crops=False, want_dbg=True)
+        A = dbg[:, 0].permute(0, 3, 1, 2).contiguous()
+        B = dbg[:, 1].permute(0, 3, 1, 2).contiguous()
+        return A, B
+
+    def refine_once(self, poses, autocast=True):
+        A, B = self.crops(poses, 0)
+        with torch.autocast("cuda", dtype=torch.float16, enabled=autocast):
+            out = self.nets.refine_forward(self.sd_r, A, B)
+        return self.geometry.pose_update(poses, out["trans"].float(), out["rot"].float(), self.d, 0.3490658503988659)
+
+    def step(self, poses, iters, autocast=True):
+        for _ in range(iters):
+            poses, _, _ = self.refine_once(poses, autocast)
+        A, B = self.crops(poses, 1)
+        with torch.autocast("cuda", dtype=torch.float16, enabled=autocast):
+            logits = self.nets.score_forward(self.sd_s, A, B, L=len(A)).reshape(-1).float()
+        return poses, logits + 100
+
+
+def run_torch_cuda(args, rank, world):
+    """--impl torch-cuda: the stand-in alone, same metric / config, one JSON line with "impl": "torch-cuda"."""
+    if rank != 0:
+        return
+    from foundationpose_b200 import hypotheses, synth
+    from foundationpose_b200.engine import Engine
+    from foundationpose_b200.estimater import make_mesh_tensors
+    from foundationpose_b200.weights import random_state_dict
+
+    torch.cuda.set_device(0)
+    mesh, gt_pose, K, rgb, depth, mask = synth.default_scene(subdivisions=5, seed=0)
+    mt = make_mesh_tensors(mesh)
+    d = synth.mesh_diameter(mesh.vertices)
+    eng = Engine()
+    eng.set_mesh(mt["pos"], mt["normals"], mt["faces"], d, uv=mt["uv"], tex=mt["tex"])
+    eng.set_frame(torch.from_numpy(rgb).cuda(), torch.from_numpy(depth).cuda(), K, filter_depth=True)
+    center = hypotheses.guess_translation(eng.get_depth()[0].cpu().numpy(), mask, K)
+    poses0 = torch.from_numpy(hypotheses.make_rotation_grid()).float().cuda()
+    poses0[:, :3, 3] = torch.as_tensor(center, dtype=torch.float32, device="cuda")
+    st = TorchCudaStandin(eng, random_state_dict("refine", 0), random_state_dict("score", 0), d)
+    with torch.inference_mode():
+        for _ in range(max(1, min(args.warmup, 2))):
+            st.step(poses0, N_ITER)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            _, scores = st.step(poses0, N_ITER)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    emit({"impl": "torch-cuda", "metric": METRIC, "value": N_HYP / (ms * 1e-3), "unit": "hyp/s", "n_gpus": 1, "steps": args.steps,
+          "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
+          "data": "synthetic", "best_index": int(scores.argmax().item()),
+          "config": {"workload": "register: 252 hyp x 5 refine iters + score; GPU STAND-IN for the reference's CUDA build: oracle port of its "
+                                 "networks as torch ops on CUDA, fp16 autocast, cudnn.benchmark=False; crops from this repository's producer "
+                                 "(nvdiffrast / kornia are not installable here)"}})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--impl", default="native", choices=["native", "reference", "torch-cuda"])
+    ap.add_argument("--no-standin", action="store_true", help="skip the torch-cuda stand-in / parity legs of the native line")
+    ap.add_argument("--no-track", action="store_true", help="skip the track_one (BASELINE.json configs[2]) leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
@@ -215,6 +329,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.impl == "torch-cuda":
+        run_torch_cuda(args, rank, world)
         return
 
     import torch.distributed as dist
@@ -320,11 +437,84 @@ def main():
                 "achieved": tf_ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": tf_ach / peaks["tf_sustained"],
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); kernel timed inside a long step",
                 "launches_timed": g_n, "avg_launch_ms": g_ms / max(g_n, 1), "share_of_step": (g_ms / 2) / ms,
-                "traffic": 371.2e6,
-                "traffic_note": "dram read+write of ONE representative launch (256-channel 3x3 conv, gemm_tile_kernel<256,2,2,patch>) from profiles/r01f_prof5_conv256_patch_details.csv (ncu --set full); algorithmic bytes of that launch: 413 MB"}
-    roofline_raster = {"kernel": "crop producer: vertex_kernel + raster_kernel + shade_kernel (raster + warp + normalise)", "bound": "hbm", "achieved": gb_ach,
-                       "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gb_ach / peaks["hbm_gbs"], "launches_timed": c_n,
-                       "avg_launch_ms": c_ms / max(c_n, 1), "share_of_step": (c_ms / 2) / ms, "traffic": None}
+                "traffic": None}
+    traffic = load_traffic()  # measured by ncu --set full, committed under profiles/ (never a literal in this file)
+    tg = traffic.get("gemm_tile_kernel")
+    if tg:
+        roofline["traffic"] = tg["dram_bytes"]
+        roofline["traffic_note"] = (f"dram read+write of ONE launch of {tg['kernel']} ({tg.get('what', '')}) from {tg['source']}; "
+                                    f"algorithmic bytes of that launch: {tg.get('algorithmic_bytes')}")
+    roofline_raster = {"kernel": "crop producer: crop_tile_kernel<TILE> (meshlet binning + raster + shade + warp + normalise, one launch per pass)",
+                       "bound": "hbm", "achieved": gb_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gb_ach / peaks["hbm_gbs"],
+                       "launches_timed": c_n, "avg_launch_ms": c_ms / max(c_n, 1), "share_of_step": (c_ms / 2) / ms, "traffic": None}
+    tc = traffic.get("crop_tile_kernel")
+    if tc:
+        roofline_raster["traffic"] = tc["dram_bytes"]
+        roofline_raster["traffic_note"] = f"dram read+write of ONE launch at N = {tc.get('n_hyp')} from {tc['source']}; algorithmic bytes: {tc.get('algorithmic_bytes')}"
+        if tc.get("issue_active_pct") is not None:
+            roofline_raster["issue_active_pct"] = tc["issue_active_pct"]
+
+    # ---------------------------------------------------------------- ranking margin of this run (SURVEY.md §7 hard part v)
+    sc_sorted = torch.sort(scores.float(), descending=True).values
+    top2_margin = float((sc_sorted[0] - sc_sorted[1]).item())
+    score_spread = float(scores.float().std().item())
+
+    # ---------------------------------------------------------------- track_one leg (BASELINE.json configs[2]), rank 0, N = 1
+    track = None
+    if rank == 0 and world == 1 and not args.no_track:
+        seq = synth.track_sequence(20, gt_pose)
+        frames = [synth.make_scene(mesh.visual.image, p_, seed=1 + i)[:2] for i, p_ in enumerate(seq)]
+        est.register(K=K, rgb=frames[0][0], depth=frames[0][1], ob_mask=mask, iteration=N_ITER)
+        n_frames = 1000
+        for i in range(20):
+            est.track_one(rgb=frames[i % 20][0], depth=frames[i % 20][1], K=K, iteration=2)
+        lat = []
+        for i in range(n_frames):
+            k40 = i % 40
+            f_rgb, f_depth = frames[k40 if k40 < 20 else 39 - k40]  # forwards, then backwards: no jumps
+            t0 = time.perf_counter()
+            est.track_one(rgb=f_rgb, depth=f_depth, K=K, iteration=2)
+            lat.append((time.perf_counter() - t0) * 1e3)
+        lat = np.sort(np.asarray(lat))
+        track = {"ms_p50": float(lat[len(lat) // 2]), "ms_p99": float(lat[int(len(lat) * 0.99)]), "ms_mean": float(lat.mean()),
+                 "frames": n_frames, "refine_iters": 2, "hypotheses": 1,
+                 "api": "FoundationPose.track_one(rgb, depth, K, iteration=2) with host numpy frames (one CUDA-graph launch per frame: upload, "
+                        "depth filters, xyz map, 2 refiner passes, pose read-back); wall clock per call",
+                 "sequence": "20 distinct synthetic frames (object moving <= 5 mm / 2 deg per frame) played forwards and backwards 25 times"}
+
+    # ---------------------------------------------------------------- GPU stand-in + parity numbers (rank 0, N = 1)
+    standin = parity = None
+    if rank == 0 and world == 1 and not args.no_standin:
+        try:
+            eng.set_frame(torch.from_numpy(rgb).cuda(), torch.from_numpy(depth).cuda(), K, filter_depth=True)
+            st = TorchCudaStandin(eng, random_state_dict("refine", 0), random_state_dict("score", 0), est.diameter)
+            with torch.inference_mode():
+                st.step(poses0, N_ITER)
+                torch.cuda.synchronize()
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record()
+                for _ in range(3):
+                    _, st_scores = st.step(poses0, N_ITER)
+                s1.record()
+                torch.cuda.synchronize()
+                st_ms = s0.elapsed_time(s1) / 3
+                # parity of the first refine iteration's SE(3) deltas on the 252 start poses, same crops for all three
+                torch.backends.cuda.matmul.allow_tf32 = False
+                torch.backends.cudnn.allow_tf32 = False
+                _, t32, r32 = st.refine_once(poses0, autocast=False)
+                _, t16, r16 = st.refine_once(poses0, autocast=True)
+                _, tn, rn = eng.refine(poses0, 1)
+            standin = {"value": N_HYP / (st_ms * 1e-3), "unit": "hyp/s", "ms_per_step": st_ms, "best_index": int(st_scores.argmax().item()),
+                       "what": "GPU STAND-IN for the reference's nvdiffrast + PyTorch CUDA build (not installable here): oracle port of its "
+                               "networks as torch ops on CUDA, fp16 autocast, cudnn.benchmark=False, crops from this repository's producer; "
+                               "NOT the --impl reference arm"}
+            parity = {"what": "first refine iteration on the 252 start poses: max |delta| difference of the predicted SE(3) update "
+                              "(translation in metres / rotation-matrix entries); fp32 oracle = the reference networks as fp32 torch ops on the same crops",
+                      "native_vs_fp32_oracle": {"trans": float((tn - t32).abs().max()), "rot": float((rn - r32).abs().max())},
+                      "autocast_oracle_vs_fp32_oracle": {"trans": float((t16 - t32).abs().max()), "rot": float((r16 - r32).abs().max())},
+                      "native_vs_autocast_oracle": {"trans": float((tn - t16).abs().max()), "rot": float((rn - r16).abs().max())}}
+        except Exception as ex:
+            standin = {"value": None, "what": f"stand-in failed: {ex}"}
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
@@ -354,7 +544,15 @@ def main():
             "roofline": roofline,
             "roofline_raster": roofline_raster,
             "best_index": int(best.item()),
+            "top2_margin": top2_margin,
+            "score_spread": score_spread,
         }
+        if track is not None:
+            line["track_one"] = track
+        if standin is not None:
+            line["gpu_standin"] = standin
+        if parity is not None:
+            line["parity"] = parity
         if cpu is not None:
             line["cpu_baseline"] = cpu
         emit(line)

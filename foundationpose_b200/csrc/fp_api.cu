@@ -1060,3 +1060,219 @@ int fp_op_pose_update(const float* poses_in, const float* trans, const float* ro
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// fp_group: ONE process (one host thread) driving several GPUs — the reference's process model (run_demo.py is one
+// script).  One fp_ctx per device, each with its own stream; register() shards the hypothesis list contiguously,
+// every device filters the frame, derives the start poses and refines / featurises its slice; the only exchange is
+// the per-hypothesis feature rows (+ refined poses), written by each device DIRECTLY into device 0's gather buffer
+// over NVLink peer memory (cudaMemcpyAsync device-to-device on the producing device's stream: no host staging, no
+// collective library); device 0 waits on one event per peer and runs the cross-hypothesis tail once.
+// ------------------------------------------------------------------------------------------------
+struct fp_group {
+  std::vector<fp_ctx*> ctx;
+  std::vector<cudaStream_t> stream;
+  std::vector<cudaEvent_t> done;
+  std::vector<fp::DevBuf> grid, start, info, refined;  // per device: rot grid [N][16], start poses, info[4], refined slice
+  fp::DevBuf feats_all, poses_all, scores, best;       // on device 0
+  void* pin_rgb = nullptr;
+  void* pin_depth = nullptr;
+  void* pin_mask = nullptr;
+  void* pin_grid = nullptr;
+  size_t pin_npix = 0, pin_grid_n = 0;
+  unsigned long long epoch = 0;
+};
+
+extern "C" {
+
+int fp_group_destroy(fp_group* g) {
+  FP_API_BEGIN
+  if (!g) return 0;
+  for (size_t i = 0; i < g->ctx.size(); ++i) {
+    DeviceGuard dg(g->ctx[i]->device);
+    cudaDeviceSynchronize();
+    for (fp::DevBuf* b : {&g->grid[i], &g->start[i], &g->info[i], &g->refined[i]})
+      if (b->p) cudaFree(b->p);
+    if (i == 0)
+      for (fp::DevBuf* b : {&g->feats_all, &g->poses_all, &g->scores, &g->best})
+        if (b->p) cudaFree(b->p);
+    if (g->stream[i]) cudaStreamDestroy(g->stream[i]);
+    if (g->done[i]) cudaEventDestroy(g->done[i]);
+    fp_destroy(g->ctx[i]);
+  }
+  for (void* p : {g->pin_rgb, g->pin_depth, g->pin_mask, g->pin_grid})
+    if (p) cudaFreeHost(p);
+  delete g;
+  return 0;
+  FP_API_END
+}
+
+int fp_group_create(int ndev, const int* dev_ids, fp_group** out) {
+  FP_API_BEGIN
+  FP_REQUIRE(out && ndev > 0, "fp_group_create: bad argument");
+  int visible = 0;
+  FP_CUDA_OK(cudaGetDeviceCount(&visible));
+  fp_group* g = new fp_group();
+  int prev = 0;
+  cudaGetDevice(&prev);
+  for (int i = 0; i < ndev; ++i) {
+    const int dev = dev_ids ? dev_ids[i] : i;
+    if (dev < 0 || dev >= visible) {
+      fp_group_destroy(g);
+      set_last_error("fp_group_create: device %d not visible (%d devices)", dev, visible);
+      cudaSetDevice(prev);
+      return -1;
+    }
+    cudaSetDevice(dev);
+    fp_ctx* c = nullptr;
+    const int rc = fp_create(&c);
+    if (rc) {
+      fp_group_destroy(g);
+      cudaSetDevice(prev);
+      return rc;
+    }
+    cudaStream_t s = nullptr;
+    cudaEvent_t e = nullptr;
+    cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    g->ctx.push_back(c);
+    g->stream.push_back(s);
+    g->done.push_back(e);
+    g->grid.emplace_back();
+    g->start.emplace_back();
+    g->info.emplace_back();
+    g->refined.emplace_back();
+    if (i > 0) {
+      // peers write their feature rows into device 0's buffer: map device 0's memory into this device
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, dev, g->ctx[0]->device);
+      if (can) {
+        const cudaError_t pe = cudaDeviceEnablePeerAccess(g->ctx[0]->device, 0);
+        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) {
+          set_last_error("fp_group_create: cudaDeviceEnablePeerAccess(%d -> %d): %s", dev, g->ctx[0]->device, cudaGetErrorString(pe));
+          fp_group_destroy(g);
+          cudaSetDevice(prev);
+          return -2;
+        }
+        cudaGetLastError();
+      }
+    }
+  }
+  cudaSetDevice(prev);
+  *out = g;
+  return 0;
+  FP_API_END
+}
+
+int fp_group_size(fp_group* g) { return g ? (int)g->ctx.size() : 0; }
+
+fp_ctx* fp_group_ctx(fp_group* g, int i) { return (g && i >= 0 && i < (int)g->ctx.size()) ? g->ctx[i] : nullptr; }
+
+int fp_group_load_network(fp_group* g, int which, const fp_tensor_t* tensors, int n) {
+  FP_API_BEGIN
+  FP_REQUIRE(g, "fp_group_load_network: null group");
+  for (fp_ctx* c : g->ctx) FP_TRY(fp_load_network(c, which, tensors, n));
+  return 0;
+  FP_API_END
+}
+
+int fp_group_set_config(fp_group* g, int which, float crop_ratio, float rot_normalizer) {
+  FP_API_BEGIN
+  FP_REQUIRE(g, "fp_group_set_config: null group");
+  for (fp_ctx* c : g->ctx) FP_TRY(fp_set_config(c, which, crop_ratio, rot_normalizer));
+  return 0;
+  FP_API_END
+}
+
+int fp_group_set_mesh(fp_group* g, int V, int F, const float* pos, const float* nrm, const float* uv, const float* vcol,
+                      const int* faces, const unsigned char* tex_rgb, int Ht, int Wt, float diameter) {
+  FP_API_BEGIN
+  FP_REQUIRE(g, "fp_group_set_mesh: null group");
+  for (fp_ctx* c : g->ctx) FP_TRY(fp_set_mesh(c, V, F, pos, nrm, uv, vcol, faces, tex_rgb, Ht, Wt, diameter));
+  return 0;
+  FP_API_END
+}
+
+int fp_group_register(fp_group* g, const unsigned char* rgb_host, const float* depth_host, const float* K, int H, int W,
+                      const unsigned char* mask_host, const float* rot_grid_host, int N, int iterations,
+                      float* poses_out_host, float* scores_out_host, int* best_out_host, float* info_out_host) {
+  FP_API_BEGIN
+  FP_REQUIRE(g && rgb_host && depth_host && K && mask_host && rot_grid_host && poses_out_host && scores_out_host &&
+                 best_out_host && N > 0 && H > 0 && W > 0,
+             "fp_group_register: bad argument");
+  const int G = (int)g->ctx.size();
+  const size_t npix = (size_t)H * W;
+  // pinned staging, filled once, read by every device
+  if (g->pin_npix < npix) {
+    for (void** p : {&g->pin_rgb, &g->pin_depth, &g->pin_mask}) {
+      if (*p) cudaFreeHost(*p);
+      *p = nullptr;
+    }
+    g->pin_npix = 0;
+    FP_CUDA_OK(cudaHostAlloc(&g->pin_rgb, npix * 3, cudaHostAllocPortable));
+    FP_CUDA_OK(cudaHostAlloc(&g->pin_depth, npix * 4, cudaHostAllocPortable));
+    FP_CUDA_OK(cudaHostAlloc(&g->pin_mask, npix, cudaHostAllocPortable));
+    g->pin_npix = npix;
+  }
+  if (g->pin_grid_n < (size_t)N) {
+    if (g->pin_grid) cudaFreeHost(g->pin_grid);
+    g->pin_grid = nullptr;
+    g->pin_grid_n = 0;
+    FP_CUDA_OK(cudaHostAlloc(&g->pin_grid, (size_t)N * 64, cudaHostAllocPortable));
+    g->pin_grid_n = N;
+  }
+  memcpy(g->pin_rgb, rgb_host, npix * 3);
+  memcpy(g->pin_depth, depth_host, npix * 4);
+  memcpy(g->pin_mask, mask_host, npix);
+  memcpy(g->pin_grid, rot_grid_host, (size_t)N * 64);
+  fp_ctx* c0 = g->ctx[0];
+  {
+    DeviceGuard dg(c0->device);
+    FP_TRY(dev_alloc(g->epoch, g->feats_all, (size_t)N * 2048));
+    FP_TRY(dev_alloc(g->epoch, g->poses_all, (size_t)N * 64));
+    FP_TRY(dev_alloc(g->epoch, g->scores, (size_t)N * 4));
+    FP_TRY(dev_alloc(g->epoch, g->best, 16));
+  }
+  const int base = N / G, rem = N % G;
+  for (int i = 0; i < G; ++i) {
+    fp_ctx* c = g->ctx[i];
+    DeviceGuard dg(c->device);
+    cudaStream_t st = g->stream[i];
+    const int lo = i * base + (i < rem ? i : rem), n = base + (i < rem ? 1 : 0);
+    FP_TRY(dev_alloc(g->epoch, g->grid[i], (size_t)N * 64));
+    FP_TRY(dev_alloc(g->epoch, g->start[i], (size_t)N * 64));
+    FP_TRY(dev_alloc(g->epoch, g->info[i], 16));
+    FP_TRY(dev_alloc(g->epoch, g->refined[i], (size_t)(n > 0 ? n : 1) * 64));
+    FP_TRY(fp_set_frame(c, reinterpret_cast<const unsigned char*>(g->pin_rgb), reinterpret_cast<const float*>(g->pin_depth),
+                        K, H, W, FP_FRAME_FILTER_DEPTH, INFINITY, st));
+    FP_CUDA_OK(cudaMemcpyAsync(g->grid[i].p, g->pin_grid, (size_t)N * 64, cudaMemcpyHostToDevice, st));
+    FP_TRY(fp_start_poses(c, reinterpret_cast<const unsigned char*>(g->pin_mask), 0, reinterpret_cast<const float*>(g->grid[i].p),
+                          N, reinterpret_cast<float*>(g->start[i].p), reinterpret_cast<float*>(g->info[i].p), st));
+    if (n > 0) {
+      float* refined = reinterpret_cast<float*>(g->refined[i].p);
+      FP_TRY(fp_refine(c, reinterpret_cast<const float*>(g->start[i].p) + (size_t)lo * 16, n, iterations, refined, nullptr,
+                       nullptr, st));
+      // the gather: feature rows and refined poses land in device 0's buffers, straight over peer memory
+      FP_TRY(fp_score_features(c, refined, n, reinterpret_cast<float*>(g->feats_all.p) + (size_t)lo * 512, st));
+      FP_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<float*>(g->poses_all.p) + (size_t)lo * 16, refined, (size_t)n * 64,
+                                 cudaMemcpyDefault, st));
+    }
+    FP_CUDA_OK(cudaEventRecord(g->done[i], st));
+  }
+  {
+    DeviceGuard dg(c0->device);
+    cudaStream_t s0 = g->stream[0];
+    for (int i = 1; i < G; ++i) FP_CUDA_OK(cudaStreamWaitEvent(s0, g->done[i], 0));
+    FP_TRY(fp_score_tail(c0, reinterpret_cast<const float*>(g->feats_all.p), N, reinterpret_cast<float*>(g->scores.p),
+                         reinterpret_cast<int*>(g->best.p), s0));
+    FP_CUDA_OK(cudaMemcpyAsync(poses_out_host, g->poses_all.p, (size_t)N * 64, cudaMemcpyDeviceToHost, s0));
+    FP_CUDA_OK(cudaMemcpyAsync(scores_out_host, g->scores.p, (size_t)N * 4, cudaMemcpyDeviceToHost, s0));
+    FP_CUDA_OK(cudaMemcpyAsync(best_out_host, g->best.p, 4, cudaMemcpyDeviceToHost, s0));
+    if (info_out_host) FP_CUDA_OK(cudaMemcpyAsync(info_out_host, g->info[0].p, 16, cudaMemcpyDeviceToHost, s0));
+    FP_CUDA_OK(cudaStreamSynchronize(s0));
+  }
+  return 0;
+  FP_API_END
+}
+
+}  // extern "C"

@@ -268,7 +268,8 @@ struct TileSmem {
   VtxS sv[kWarps][kMeshletVerts];      // per-warp transformed vertices of the meshlet in flight
   float P[16];
   Window win;
-  float colf[TILE], rowf[TILE];  // kornia source coordinates of the observed-crop resampling (separable)
+  float colf[TILE], rowf[TILE];  // bilinear weight of the right / lower tap of the observed-crop resampling (separable)
+  int colx[TILE], rowy[TILE];    // right / lower tap index; bit 30 / 31 set when the left (upper) / right (lower) tap is outside
   int coln[TILE], rown[TILE];    // nearest source column / row (-1 = outside)
   int colz[TILE], rowz[TILE];    // scorer depth round trip: source column / row of the depth sample
   int list[kListCap];
@@ -294,15 +295,33 @@ __device__ __forceinline__ void raster_tri(const VtxS& a, const VtxS& b, const V
   if (tri_small(a.xi, a.yi, b.xi, b.yi, c.xi, c.yi)) {
     TriSetup32 t;
     if (!tri_setup32(a.xi, a.yi, b.xi, b.yi, c.xi, c.yi, t)) return;
-    for (int r = r0; r <= r1; ++r)
-      for (int j = j0; j <= j1; ++j) {
-        float b0, b1, b2;
-        if (!tri_cover32(t, j * 256 + 128, r * 256 + 128, b0, b1, b2)) continue;
-        const float iz = inv_depth(b0, b1, b2, a.iz, b.iz, c.iz);
+    // Incremental form of tri_cover32: the three edge functions, each biased by its tie flag (an integer e passes
+    // the top-left rule iff e + tie > 0), stepped by one pixel = 256 sub-pixel units.  Same integers, same coverage;
+    // ~10 instructions per tested pixel centre instead of ~35.
+    const int dx0 = t.bx - t.ax, dy0 = t.by - t.ay;
+    const int tie0 = (dy0 > 0 || (dy0 == 0 && dx0 > 0)) ? 1 : 0;
+    const int tie1 = (-t.by > 0 || (t.by == 0 && -t.bx > 0)) ? 1 : 0;
+    const int tie2 = (t.ay > 0 || (t.ay == 0 && t.ax > 0)) ? 1 : 0;
+    const int qx0 = j0 * 256 + 128 - t.x0, qy0 = r0 * 256 + 128 - t.y0;
+    int E0r = dx0 * (qy0 - t.ay) - dy0 * (qx0 - t.ax) + tie0;
+    int E1r = (-t.bx) * (qy0 - t.by) + t.by * (qx0 - t.bx) + tie1;
+    const int sum = t.area2 + tie0 + tie1 + tie2;
+    const int sx0 = -dy0 * 256, sy0 = dx0 * 256, sx1 = t.by * 256, sy1 = -t.bx * 256;
+    const float fa = __int2float_rn(t.area2);
+    for (int r = r0; r <= r1; ++r, E0r += sy0, E1r += sy1) {
+      int E0 = E0r, E1 = E1r;
+      for (int j = j0; j <= j1; ++j, E0 += sx0, E1 += sx1) {
+        if (min(min(E0, E1), sum - E0 - E1) <= 0) continue;
+        const int e0 = E0 - tie0, e1 = E1 - tie1, e2 = t.area2 - e0 - e1;
+        const float b0 = __fdiv_rn(__int2float_rn(e0), fa);
+        const float w1 = __fdiv_rn(__int2float_rn(e1), fa);
+        const float w2 = __fdiv_rn(__int2float_rn(e2), fa);
+        const float iz = inv_depth(b0, t.swapped ? w2 : w1, t.swapped ? w1 : w2, a.iz, b.iz, c.iz);
         if (!(iz > iz_far)) continue;
         atomicMax(&zt[(r - ty0) * TILE + (j - tx0)], depth_key(iz, face));
         ++n_frag;
       }
+    }
   } else {
     TriSetup t;
     if (!tri_setup(a.xi, a.yi, b.xi, b.yi, c.xi, c.yi, t)) return;
@@ -384,7 +403,17 @@ __global__ void __launch_bounds__(kThreads, FP_CROP_MIN_CTAS) crop_tile_kernel(c
         if (u2 >= 0 && u2 < size) uz = u2;
       }
     }
-    (is_row ? sm.rowf : sm.colf)[k] = ix;
+    {
+      // bilinear taps (zeros padding): index of the first tap, weight of the second, out-of-range flags
+      const float f0 = floorf(ix);
+      const int i0 = (int)fminf(fmaxf(f0, -2.f), (float)size);
+      const unsigned out0 = (i0 < 0 || i0 >= size) ? 0x40000000u : 0u;
+      const unsigned out1 = (i0 + 1 < 0 || i0 + 1 >= size) ? 0x80000000u : 0u;
+      (is_row ? sm.rowf : sm.colf)[k] = ix - f0;
+      // stored index = the SECOND tap, clamped into the image; the first tap is one before it (or the same pixel
+      // when the second one fell off the far edge)
+      (is_row ? sm.rowy : sm.colx)[k] = (int)((unsigned)(max(min(i0 + 1, size - 1), 0)) | out0 | out1);
+    }
     (is_row ? sm.rown : sm.coln)[k] = un;
     (is_row ? sm.rowz : sm.colz)[k] = uz;
   }
@@ -552,7 +581,8 @@ __global__ void __launch_bounds__(kThreads, FP_CROP_MIN_CTAS) crop_tile_kernel(c
   for (int blk = warp; blk < kBlocks; blk += kWarps) {
     const int jl = (blk % kBlocksX) * 8 + (lane & 7), rl = (blk / kBlocksX) * 4 + (lane >> 3);
     const int j = tx0 + jl, r = ty0 + rl;
-    const float ixc = sm.colf[jl];
+    const float wx1 = sm.colf[jl];
+    const int cxi = sm.colx[jl];
     const int unc = sm.coln[jl], uzc = sm.colz[jl];
     // ---- A: rendered crop
     float ar = 0.f, ag = 0.f, ab = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
@@ -612,13 +642,18 @@ __global__ void __launch_bounds__(kThreads, FP_CROP_MIN_CTAS) crop_tile_kernel(c
       if (p.has_tex) {
         const float tu = w0 * att[0].x + w1 * att[1].x + w2 * att[2].x;
         const float tv = w0 * att[0].y + w1 * att[1].y + w2 * att[2].y;
-        // dr.texture(filter_mode='linear', boundary 'wrap'): texel centres at +0.5
+        // dr.texture(filter_mode='linear', boundary 'wrap'): texel centres at +0.5.  Interpolated uv of a mesh lie in
+        // (-1, 2): the wrap is two conditional adds; anything further out takes the general modulo.
         const float xx = tu * p.Wt - 0.5f, yy = tv * p.Ht - 0.5f;
         const float xf = floorf(xx), yf = floorf(yy);
         const float ax1 = xx - xf, ay1 = yy - yf;
-        int x0 = (int)xf % p.Wt, y0 = (int)yf % p.Ht;
+        int x0 = (int)xf, y0 = (int)yf;
+        if ((unsigned)(x0 + p.Wt) >= (unsigned)(3 * p.Wt)) x0 %= p.Wt;
+        if ((unsigned)(y0 + p.Ht) >= (unsigned)(3 * p.Ht)) y0 %= p.Ht;
         if (x0 < 0) x0 += p.Wt;
         if (y0 < 0) y0 += p.Ht;
+        if (x0 >= p.Wt) x0 -= p.Wt;
+        if (y0 >= p.Ht) y0 -= p.Ht;
         const int x1 = (x0 + 1 == p.Wt) ? 0 : x0 + 1, y1 = (y0 + 1 == p.Ht) ? 0 : y0 + 1;
         const uchar4 t00 = __ldg(p.tex + (size_t)y0 * p.Wt + x0), t01 = __ldg(p.tex + (size_t)y0 * p.Wt + x1);
         const uchar4 t10 = __ldg(p.tex + (size_t)y1 * p.Wt + x0), t11 = __ldg(p.tex + (size_t)y1 * p.Wt + x1);
@@ -641,24 +676,20 @@ __global__ void __launch_bounds__(kThreads, FP_CROP_MIN_CTAS) crop_tile_kernel(c
     // ---- B: observed crop
     float br = 0.f, bg = 0.f, bb = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
     {
-      const float iy = sm.rowf[rl];
-      // bilinear rgb, zeros padding
-      const float fx0 = floorf(ixc), fy0 = floorf(iy);
-      const int x0 = (int)fx0, y0 = (int)fy0;
-      const float wx1 = ixc - fx0, wy1 = iy - fy0;
-#pragma unroll
-      for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-          const int xq = x0 + dx, yq = y0 + dy;
-          if (xq >= 0 && xq < p.W && yq >= 0 && yq < p.H) {
-            const float wgt = (dx ? wx1 : 1.f - wx1) * (dy ? wy1 : 1.f - wy1);
-            const uchar4 c4 = __ldg(p.rgb + (size_t)yq * p.W + xq);
-            br += wgt * c4.x;
-            bg += wgt * c4.y;
-            bb += wgt * c4.z;
-          }
-        }
+      // bilinear rgb, zeros padding: tap indices / weights / validity come from the per-axis tables
+      const float wy1 = sm.rowf[rl];
+      const int ryi = sm.rowy[rl];
+      const int x1 = cxi & 0x3fffffff, y1 = ryi & 0x3fffffff;
+      const int x0 = (cxi & 0x80000000) ? x1 : max(x1 - 1, 0), y0 = (ryi & 0x80000000) ? y1 : max(y1 - 1, 0);
+      const float wx[2] = {(cxi & 0x40000000) ? 0.f : 1.f - wx1, (cxi & 0x80000000) ? 0.f : wx1};
+      const float wy[2] = {(ryi & 0x40000000) ? 0.f : 1.f - wy1, (ryi & 0x80000000) ? 0.f : wy1};
+      const uchar4* row0 = p.rgb + (size_t)y0 * p.W;
+      const uchar4* row1 = p.rgb + (size_t)y1 * p.W;
+      const uchar4 t00 = __ldg(row0 + x0), t01 = __ldg(row0 + x1), t10 = __ldg(row1 + x0), t11 = __ldg(row1 + x1);
+      const float w00 = wx[0] * wy[0], w01 = wx[1] * wy[0], w10 = wx[0] * wy[1], w11 = wx[1] * wy[1];
+      br = w00 * t00.x + w01 * t01.x + w10 * t10.x + w11 * t11.x;
+      bg = w00 * t00.y + w01 * t01.y + w10 * t10.y + w11 * t11.y;
+      bb = w00 * t00.z + w01 * t01.z + w10 * t10.z + w11 * t11.z;
       br *= (1.f / 255.f);
       bg *= (1.f / 255.f);
       bb *= (1.f / 255.f);

@@ -243,9 +243,24 @@ class Engine:
             depth = depth.contiguous()
             assert rgb.dtype == torch.uint8 and depth.dtype == torch.float32
             H, W = depth.shape
+            if not rgb.is_pinned():
+                # pageable host memory makes cudaMemcpyAsync synchronous and staged by the driver: stage through a
+                # pinned buffer owned by the engine (the previous frame's copy has been consumed: same stream)
+                pin = getattr(self, "_pin", None)
+                if pin is None or pin[0].shape != rgb.shape or pin[1].shape != depth.shape:
+                    torch.cuda.current_stream().synchronize()
+                    pin = self._pin = (torch.empty(rgb.shape, dtype=torch.uint8).pin_memory(), torch.empty(depth.shape, dtype=torch.float32).pin_memory(),
+                                       torch.cuda.Event())
+                else:
+                    pin[2].synchronize()
+                pin[0].copy_(rgb)
+                pin[1].copy_(depth)
+                rgb, depth = pin[0], pin[1]
             rp, dp = _p(rgb), _p(depth)
         self._frame_keep = (rgb, depth)
         _lib.check(lib.fp_set_frame(self._h, rp, dp, Kf, H, W, flags, float(zfar), _stream()), "fp_set_frame")
+        if getattr(self, "_pin", None) is not None and rgb is self._pin[0]:
+            self._pin[2].record()  # the staging buffers may be overwritten once this point of the stream has passed
         self.frame_hw = (H, W)
 
     def set_xyz_map(self, xyz_map):

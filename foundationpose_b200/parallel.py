@@ -22,25 +22,36 @@ def shard_counts(n, world):
     return [shard_bounds(n, world, r)[1] - shard_bounds(n, world, r)[0] for r in range(world)]
 
 
+_gather_ws = {}
+
+
 def gather_rows(local, n_total, group=None):
     """All-gather row blocks of unequal height: local (n_local, C) -> (n_total, C) on every rank,
-    rows in rank order.  One collective; shards are padded to the largest height."""
+    rows in rank order.  One collective; shards are padded to the largest height.  The send / receive / output
+    buffers and the compaction index are allocated once per (shape, world) and reused: no allocation, no torch.cat
+    and no host-side loop on the per-frame path."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         assert local.shape[0] == n_total
         return local
     world = dist.get_world_size(group)
-    counts = shard_counts(n_total, world)
-    assert local.shape[0] == counts[dist.get_rank(group)], "local shard does not match shard_bounds()"
-    mx = max(counts)
+    rank = dist.get_rank(group)
     C = local.shape[1]
-    send = local.new_zeros(mx, C)
-    send[: local.shape[0]] = local
-    recv = local.new_empty(world * mx, C)
-    dist.all_gather_into_tensor(recv, send, group=group)
-    recv = recv.reshape(world, mx, C)
-    if all(c == mx for c in counts):
-        return recv.reshape(world * mx, C)
-    return torch.cat([recv[r, : counts[r]] for r in range(world)], 0)
+    key = (n_total, C, world, rank, local.dtype, local.device)
+    ws = _gather_ws.get(key)
+    if ws is None:
+        counts = shard_counts(n_total, world)
+        mx = max(counts)
+        idx = None
+        if not all(c == mx for c in counts):
+            idx = torch.cat([torch.arange(r * mx, r * mx + counts[r]) for r in range(world)]).to(local.device)
+        ws = _gather_ws[key] = dict(counts=counts, mx=mx, send=local.new_zeros(mx, C), recv=local.new_empty(world * mx, C), idx=idx,
+                                    out=local.new_empty(n_total, C))
+    assert local.shape[0] == ws["counts"][rank], "local shard does not match shard_bounds()"
+    ws["send"][: local.shape[0]].copy_(local)
+    dist.all_gather_into_tensor(ws["recv"], ws["send"], group=group)
+    if ws["idx"] is None:
+        return ws["recv"]
+    return torch.index_select(ws["recv"], 0, ws["idx"], out=ws["out"])
 
 
 class ShardedRegister:
@@ -52,6 +63,7 @@ class ShardedRegister:
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._packed = {}
 
     def run(self, poses_all, iterations):
         """poses_all: (N,4,4) identical on every rank (host or device).  Returns refined poses (N,4,4),
@@ -65,7 +77,11 @@ class ShardedRegister:
         if hi > lo:
             refined, _, _ = e.refine(local, iterations)
             feats = e.score_features(refined)
-            packed = torch.cat([feats, refined.reshape(-1, 16)], 1)
+            packed = self._packed.get(hi - lo)
+            if packed is None:
+                packed = self._packed[hi - lo] = torch.empty(hi - lo, 528, dtype=torch.float32, device="cuda")
+            packed[:, :512].copy_(feats)
+            packed[:, 512:].copy_(refined.reshape(-1, 16))
         else:
             packed = torch.empty(0, 528, dtype=torch.float32, device="cuda")
         allp = gather_rows(packed, N, self.group)

@@ -105,6 +105,13 @@ def random_state_dict(kind, seed=0, c_in=6, use_bn=True):
                 sd[f"{head}.0.{ln}.weight"] = 0.8 + 0.4 * torch.rand(512, generator=g)
                 sd[f"{head}.0.{ln}.bias"] = torch.randn(512, generator=g) * 0.1
             _linear(g, sd, f"{head}.1", out_dim, 512, gain=0.05)
+            # A trained refiner is contractive: near the answer its update shrinks.  A plain random read-out moves every
+            # hypothesis by centimetres / several degrees per pass whatever it sees, so rounding differences between two
+            # correct implementations grow ~2x per pass (measured: 3.5e-4 after one pass -> 5e-3 after five) and decide
+            # which hypothesis the scorer picks.  The stand-in's read-out is therefore scaled to millimetre / sub-degree
+            # updates (x0.1): the render-and-compare loop stays exercised, the run-to-run result becomes reproducible.
+            sd[f"{head}.1.weight"] *= 0.1
+            sd[f"{head}.1.bias"] *= 0.1
     elif kind == "score":
         _encoders(g, sd, "encoderA", "encoderAB", c_in, use_bn)
         _mha(g, sd, "att")
@@ -113,9 +120,9 @@ def random_state_dict(kind, seed=0, c_in=6, use_bn=True):
         # 252 scores collapse to one value +- 6e-4 and "the selected index" is decided by rounding noise.  The stand-in
         # tail therefore has its own generator (the encoder / `att` weights above are untouched by it), sharper
         # query/key projections (x3) and a larger read-out (x60), picked — tools/make_golden_register.py reports the
-        # numbers — so that on the 252-hypothesis golden scene the scores spread (std 0.17) and the winner leads the
-        # runner-up by 2.6 sigma (0.45), ~60x the score error of an fp16 feature path.
-        g2 = torch.Generator(device="cpu").manual_seed(7065 + seed)
+        # numbers — so that on the 252-hypothesis golden scene the scores spread (std 0.12) and the winner leads the
+        # runner-up by 1.8 sigma (0.21), ~50x the score error of an fp16 feature path.
+        g2 = torch.Generator(device="cpu").manual_seed(7310 + seed)
         _mha(g2, sd, "att_cross")
         sd["att_cross.in_proj_weight"][:1024] *= 3.0
         sd["att_cross.in_proj_bias"][:1024] *= 3.0

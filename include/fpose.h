@@ -179,6 +179,30 @@ int fp_register(fp_ctx* ctx, const float* poses_host, int N, int iterations, flo
 int fp_track(fp_ctx* ctx, const unsigned char* rgb_host, const float* depth_host, const float* K, int H, int W,
              const float* pose_in_dev, int iterations, float* pose_out_dev, float* pose_out_host, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* one process, several GPUs (the reference's process model: run_demo.py is a single script)  */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct fp_group fp_group;
+/* One fp_ctx per device (dev_ids = NULL: devices 0..ndev-1), each with its own stream; devices 1.. get peer access to
+ * device 0, where the gathered features live.  Call from one thread. */
+int fp_group_create(int ndev, const int* dev_ids, fp_group** out);
+int fp_group_destroy(fp_group* g);
+int fp_group_size(fp_group* g);
+fp_ctx* fp_group_ctx(fp_group* g, int i); /* for per-device calls of the single-context API */
+/* fp_load_network / fp_set_config / fp_set_mesh on every context of the group */
+int fp_group_load_network(fp_group* g, int which, const fp_tensor_t* tensors, int n);
+int fp_group_set_config(fp_group* g, int which, float crop_ratio, float rot_normalizer);
+int fp_group_set_mesh(fp_group* g, int V, int F, const float* pos, const float* nrm, const float* uv, const float* vcol,
+                      const int* faces, const unsigned char* tex_rgb, int Ht, int Wt, float diameter);
+/* FoundationPose.register (estimater.py:159-240) with the N hypotheses sharded contiguously over the group's devices
+ * (BASELINE.json configs[3]): HOST frame, mask (uint8 [H][W]) and rotation grid [N][16]; every device filters the frame,
+ * derives the start poses and refines / featurises its slice, writing its feature rows and refined poses straight into
+ * device 0's buffers over NVLink peer memory; device 0 runs the cross-hypothesis tail once.  Outputs (HOST): refined
+ * poses [N][16], scores [N], best index, optional info[4] = {tx, ty, tz, n_valid} of guess_translation.  Synchronises. */
+int fp_group_register(fp_group* g, const unsigned char* rgb_host, const float* depth_host, const float* K, int H, int W,
+                      const unsigned char* mask_host, const float* rot_grid_host, int N, int iterations,
+                      float* poses_out_host, float* scores_out_host, int* best_out_host, float* info_out_host);
+
 /* parity-test hooks on pre-built crops (fp16 [2N][166][2][84][8], device) */
 int fp_op_refine_net(fp_ctx* ctx, const void* crops, int N, float* trans_out, float* rot_out, void* stream);
 int fp_op_score_feats(fp_ctx* ctx, const void* crops, int N, float* feats_out, void* stream);

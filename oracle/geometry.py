@@ -113,11 +113,11 @@ def so3_exp_map(v, eps=1e-4):
     ith = 1.0 / th
     fac1 = ith * th.sin()
     fac2 = ith * ith * (1.0 - th.cos())
-    K = torch.zeros(len(v), 3, 3, dtype=v.dtype)
+    K = torch.zeros(len(v), 3, 3, dtype=v.dtype, device=v.device)
     K[:, 0, 1], K[:, 0, 2] = -v[:, 2], v[:, 1]
     K[:, 1, 0], K[:, 1, 2] = v[:, 2], -v[:, 0]
     K[:, 2, 0], K[:, 2, 1] = -v[:, 1], v[:, 0]
-    return fac1[:, None, None] * K + fac2[:, None, None] * (K @ K) + torch.eye(3, dtype=v.dtype)[None]
+    return fac1[:, None, None] * K + fac2[:, None, None] * (K @ K) + torch.eye(3, dtype=v.dtype, device=v.device)[None]
 
 
 def pose_update(poses, trans, rot, mesh_diameter, rot_normalizer):
@@ -125,7 +125,7 @@ def pose_update(poses, trans, rot, mesh_diameter, rot_normalizer):
     Returns new poses (N,4,4), trans_delta (N,3), rot_mat_delta (N,3,3)."""
     trans_delta = trans * (mesh_diameter / 2)
     rot_mat_delta = so3_exp_map(torch.tanh(rot) * rot_normalizer).permute(0, 2, 1)
-    out = torch.eye(4, dtype=torch.float32)[None].repeat(len(poses), 1, 1)
+    out = torch.eye(4, dtype=torch.float32, device=poses.device)[None].repeat(len(poses), 1, 1)
     out[:, :3, 3] = poses[:, :3, 3] + trans_delta
     out[:, :3, :3] = rot_mat_delta @ poses[:, :3, :3]
     return out, trans_delta, rot_mat_delta

@@ -52,7 +52,8 @@ def test_run_demo_unmodified(tmp_path, debug):
         p = np.loadtxt(f).reshape(4, 4)
         assert np.isfinite(p).all() and abs(np.linalg.det(p[:3, :3]) - 1) < 1e-3
         poses.append(p)
-    # the object stays in front of the camera near where the mask says it is (random-init weights: no accuracy claim)
-    assert all(0.3 < p[2, 3] < 0.9 for p in poses)
+    # random-init weights: no accuracy claim, but the seeded stand-in moves a pose by millimetres per pass, so the
+    # tracked object stays near where the first frame's mask put it
+    assert all(0.4 < p[2, 3] < 0.8 for p in poses), [p[:3, 3] for p in poses]
     if debug >= 2:
         assert os.path.exists(os.path.join(dbg, "track_vis", "000003.png"))

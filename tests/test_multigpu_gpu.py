@@ -62,3 +62,60 @@ def test_sharded_register_equals_single_gpu():
     assert np.array_equal(r0["poses"], r1["poses"]) and np.array_equal(r0["scores"], r1["scores"]) and r0["best"] == r1["best"]
     assert np.array_equal(r0["poses"], r0["poses1"]), "sharded refinement differs from single-GPU"
     assert np.array_equal(r0["scores"], r0["scores1"]) and r0["best"] == r0["best1"]
+
+
+def _group_case(device_ids):
+    """fp_group (one process, one host thread): sharded register == single-context register, bit for bit."""
+    import numpy as np
+    import torch
+
+    from foundationpose_b200 import hypotheses, synth
+    from foundationpose_b200.engine import Engine
+    from foundationpose_b200.estimater import make_mesh_tensors
+    from foundationpose_b200.group import EngineGroup
+    from foundationpose_b200.weights import random_state_dict
+
+    mesh = synth.make_mesh(3)
+    pose = np.eye(4)
+    pose[:3, :3] = synth.random_rotation(0)
+    pose[:3, 3] = [0.02, -0.01, 0.6]
+    rgb, depth, mask = synth.make_scene(mesh.visual.image, pose)
+    d = synth.mesh_diameter(mesh.vertices)
+    mt = make_mesh_tensors(mesh)
+    sd_r, sd_s = random_state_dict("refine", 0), random_state_dict("score", 0)
+    grid = hypotheses.make_rotation_grid()[:60]
+    # single context
+    e = Engine()
+    e.load_network("refine", sd_r)
+    e.load_network("score", sd_s)
+    e.set_mesh(mt["pos"], mt["normals"], mt["faces"], d, uv=mt["uv"], tex=mt["tex"])
+    e.set_frame(rgb, depth, synth.DEFAULT_K, filter_depth=True)
+    start, info1 = e.start_poses(mask, torch.from_numpy(grid).cuda())
+    p1, _, _ = e.refine(start, 2)
+    s1, b1 = e.score(p1)
+    # group
+    g = EngineGroup(device_ids)
+    g.load_network("refine", sd_r)
+    g.load_network("score", sd_s)
+    g.set_mesh(mt["pos"], mt["normals"], mt["faces"], d, uv=mt["uv"], tex=mt["tex"])
+    for _ in range(3):  # eager, capture, replay
+        p2, s2, b2, info2 = g.register(rgb, depth, synth.DEFAULT_K, mask, grid, iterations=2)
+    assert np.array_equal(p2, p1.cpu().numpy()), "sharded refinement differs"
+    assert np.array_equal(s2, s1.cpu().numpy()) and b2 == int(b1.item())
+    assert np.array_equal(info2, info1.cpu().numpy())
+    g.close()
+
+
+@pytest.mark.gpu
+def test_group_two_contexts_one_device():
+    """The sharding / gather logic of fp_group with both contexts on device 0 (runs on a 1-GPU box)."""
+    _group_case([0, 0])
+
+
+@pytest.mark.gpu
+def test_group_two_devices():
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _group_case([0, 1])

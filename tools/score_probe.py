@@ -1,0 +1,63 @@
+"""Where does the scorer-feature error come from?  For a subset of the golden final poses (tests/golden/register_252x5.npz):
+  crops: CUDA producer vs oracle (pixel statistics per channel group),
+  features: CUDA net on CUDA crops | CUDA net on ORACLE crops | oracle net on oracle crops (= golden)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from foundationpose_b200 import synth  # noqa: E402
+from foundationpose_b200.engine import Engine, crops_from_planar  # noqa: E402
+from foundationpose_b200.weights import random_state_dict  # noqa: E402
+from oracle import geometry, nets, pipeline  # noqa: E402
+
+
+def main():
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "register_252x5.npz")))
+    mesh = synth.make_mesh(3)
+    rgb, depth, mask = synth.make_scene(mesh.visual.image, g["gt_pose"])
+    d = synth.mesh_diameter(mesh.vertices)
+    mt = pipeline.mesh_tensors(mesh)
+    sd_s = random_state_dict("score", 0)
+    e = Engine()
+    e.load_network("score", sd_s)
+    e.load_network("refine", random_state_dict("refine", 0))
+    e.set_mesh(mt["pos"], mt["normals"], mt["faces"], d, uv=mt["uv"], tex=mt["tex"])
+    e.set_frame(rgb, depth, synth.DEFAULT_K, filter_depth=True)
+    depth_f = e.get_depth()[0].cpu().numpy()
+    ref_depth_f = geometry.bilateral_filter_depth(geometry.erode_depth(depth))
+    print("filtered depth max diff", np.abs(depth_f - ref_depth_f).max())
+    idx = np.arange(0, 252, 16)
+    poses = g["poses"][5][idx]
+    for mode in (1, 0):
+        _, dbg, _ = e.make_crops(poses, mode=mode, want_dbg=True)
+        xyz = geometry.depth2xyzmap(ref_depth_f, synth.DEFAULT_K)
+        A, B, _ = pipeline.make_crops(poses, mt, rgb, ref_depth_f, xyz, synth.DEFAULT_K, d, mode)
+        gA = dbg[:, 0].permute(0, 3, 1, 2).cpu()
+        gB = dbg[:, 1].permute(0, 3, 1, 2).cpu()
+        for name, x, y in (("A rgb", gA[:, :3], A[:, :3]), ("A xyz", gA[:, 3:], A[:, 3:]), ("B rgb", gB[:, :3], B[:, :3]), ("B xyz", gB[:, 3:], B[:, 3:])):
+            dd = (x - y).abs()
+            print(f"mode {mode} {name}: max {dd.max():.3e} mean {dd.mean():.3e}  pixels > 1e-3: {(dd.amax(1) > 1e-3).sum().item()} of {dd.shape[0] * 160 * 160}"
+                  f"  > 1e-2: {(dd.amax(1) > 1e-2).sum().item()}")
+        if mode == 1:
+            f_gpu = e.score_features(poses).cpu()
+            f_gpu_oraclecrops = e.op_score_feats(crops_from_planar(A.cuda(), B.cuda()), len(poses)).cpu()
+            f_gpu_gpucrops_planar = e.op_score_feats(crops_from_planar(gA.cuda(), gB.cuda()), len(poses)).cpu()
+            f_ref = nets.score_features(sd_s, A, B)
+            gold = torch.from_numpy(g["feats"][idx])
+            rms = lambda t: float(t.pow(2).mean().sqrt())
+            print("golden vs recomputed oracle feats", rms(f_ref - gold))
+            print("CUDA net + CUDA crops (product path) vs golden: rms", rms(f_gpu - gold), "max", float((f_gpu - gold).abs().max()))
+            print("CUDA net + ORACLE crops vs golden: rms", rms(f_gpu_oraclecrops - gold), "max", float((f_gpu_oraclecrops - gold).abs().max()))
+            print("CUDA net + CUDA crops re-imported (fp32 dbg) vs product path: rms", rms(f_gpu_gpucrops_planar - f_gpu))
+            f_ref_gpucrops = nets.score_features(sd_s, gA, gB)
+            print("ORACLE net + CUDA crops vs golden: rms", rms(f_ref_gpucrops - gold), "max", float((f_ref_gpucrops - gold).abs().max()))
+            print("feature spread across these hypotheses (std per dim, mean)", float(gold.std(0).mean()))
+
+
+if __name__ == "__main__":
+    main()
