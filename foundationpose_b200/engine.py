@@ -5,6 +5,7 @@ torch is used for device memory, streams and (in parallel.py) torch.distributed 
 computation on the hot path happens inside the C-ABI library.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -55,6 +56,7 @@ def _proto():
 _proto()
 
 FRAME_ON_DEVICE = 1
+_NO_PIN = os.environ.get("FPOSE_NO_PIN") == "1"  # A/B: skip the pinned staging of host frames
 FRAME_FILTER_DEPTH = 2
 
 
@@ -243,7 +245,7 @@ class Engine:
             depth = depth.contiguous()
             assert rgb.dtype == torch.uint8 and depth.dtype == torch.float32
             H, W = depth.shape
-            if not rgb.is_pinned():
+            if not rgb.is_pinned() and not _NO_PIN:
                 # pageable host memory makes cudaMemcpyAsync synchronous and staged by the driver: stage through a
                 # pinned buffer owned by the engine (the previous frame's copy has been consumed: same stream)
                 pin = getattr(self, "_pin", None)

@@ -119,3 +119,35 @@ def test_group_two_devices():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     _group_case([0, 1])
+
+
+@pytest.mark.gpu
+def test_replica_pool_matches_single_estimator():
+    """ReplicaPool (N3: independent frames over estimator replicas) returns, frame by frame, what one estimator returns."""
+    import numpy as np
+    import torch
+
+    from foundationpose_b200 import synth
+    from foundationpose_b200.engine import Engine
+    from foundationpose_b200.estimater import FoundationPose, PoseRefinePredictor, ScorePredictor
+    from foundationpose_b200.replicas import ReplicaPool
+    from foundationpose_b200.weights import random_state_dict
+
+    sds = {"refine": random_state_dict("refine", 0), "score": random_state_dict("score", 0)}
+    mesh = synth.make_mesh(3)
+    pose0 = np.eye(4)
+    pose0[:3, :3] = synth.random_rotation(0)
+    pose0[:3, 3] = [0.02, -0.01, 0.6]
+    seq = synth.track_sequence(5, pose0)
+    frames = [(synth.DEFAULT_K, *synth.make_scene(mesh.visual.image, p, seed=1 + i)) for i, p in enumerate(seq)]
+    e = Engine()
+    est = FoundationPose(model_pts=mesh.vertices, model_normals=mesh.vertex_normals, mesh=mesh,
+                         scorer=ScorePredictor(engine=e, state_dict=sds["score"]), refiner=PoseRefinePredictor(engine=e, state_dict=sds["refine"]))
+    ref = [est.register(K=K, rgb=rgb, depth=depth, ob_mask=mask, iteration=2) for (K, rgb, depth, mask) in frames]
+    ids = [0, 1] if torch.cuda.device_count() >= 2 else [0, 0]
+    pool = ReplicaPool(ids, state_dicts=sds)
+    pool.reset_object(mesh.vertices, mesh.vertex_normals, mesh=mesh)
+    got = pool.register_many(frames, iteration=2)
+    pool.close()
+    for a, b in zip(ref, got):
+        np.testing.assert_array_equal(a, b)

@@ -59,5 +59,55 @@ def main():
             print("feature spread across these hypotheses (std per dim, mean)", float(gold.std(0).mean()))
 
 
+def outliers():
+    """Per-hypothesis feature error over all 252 golden poses; stage-wise comparison for the worst ones."""
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "register_252x5.npz")))
+    mesh = synth.make_mesh(3)
+    rgb, depth, mask = synth.make_scene(mesh.visual.image, g["gt_pose"])
+    d = synth.mesh_diameter(mesh.vertices)
+    mt = pipeline.mesh_tensors(mesh)
+    sd_s = random_state_dict("score", 0)
+    e = Engine()
+    e.load_network("score", sd_s)
+    e.set_mesh(mt["pos"], mt["normals"], mt["faces"], d, uv=mt["uv"], tex=mt["tex"])
+    e.set_frame(rgb, depth, synth.DEFAULT_K, filter_depth=True)
+    poses = g["poses"][5]
+    f = e.score_features(poses).cpu().numpy()
+    err = np.abs(f - g["feats"])
+    per = err.max(1)
+    order = np.argsort(-per)
+    print("per-hypothesis max feature error: median %.2e, 90%% %.2e, worst %s" % (np.median(per), np.quantile(per, 0.9), [(int(i), float(per[i])) for i in order[:8]]))
+    # batch-size dependence: the same poses scored alone / in a small batch
+    for n in (1, 8, 64):
+        idx = order[:n] if n > 1 else order[:1]
+        fs = e.score_features(poses[idx]).cpu().numpy()
+        print(f"  worst {n} scored as a batch of {n}: max err {np.abs(fs - g['feats'][idx]).max():.2e} (in the 252 batch: {err[idx].max():.2e})")
+    worst = order[:4]
+    ref_depth_f = geometry.bilateral_filter_depth(geometry.erode_depth(depth))
+    A, B, _ = pipeline.make_crops(poses[worst], mt, rgb, ref_depth_f, None, synth.DEFAULT_K, d, 1)
+    cb = crops_from_planar(A.cuda(), B.cuda())
+    tok = e.op_tokens("score", cb, len(worst)).float().cpu()
+    x = nets.encode_a(torch.cat([A, B], 0), sd_s, "encoderA")
+    ab = nets.encode_ab(torch.cat((x[:len(worst)], x[len(worst):]), 1), sd_s, "encoderAB")
+    ref_tok = nets._tokens(ab, sd_s)
+    te = (tok - ref_tok).abs()
+    print("tokens of the worst 4: max err", te.amax(dim=(1, 2)).tolist(), "ref absmax", ref_tok.abs().amax(dim=(1, 2)).tolist())
+    f4 = e.op_score_feats(cb, len(worst)).cpu()
+    print("feats of the worst 4 through op_score_feats (batch 4, oracle crops): max err", (f4 - torch.from_numpy(g["feats"][worst])).abs().amax(1).tolist())
+    # attention on the ORACLE tokens (fp16) vs oracle attention
+    qkv = (ref_tok.half().float() @ sd_s["att.in_proj_weight"].half().float().t() + sd_s["att.in_proj_bias"])
+    from foundationpose_b200 import ops
+
+    o = ops.attention(qkv.reshape(-1, 1536).half().cuda()).float().cpu().reshape(len(worst), 400, 512)
+    q, k, v = qkv.reshape(len(worst), 400, 3, 4, 128).permute(2, 0, 3, 1, 4)
+    att = torch.softmax(q @ k.transpose(-1, -2) / 128 ** 0.5, dim=-1)
+    ref_o = (att @ v).permute(0, 2, 1, 3).reshape(len(worst), 400, 512)
+    print("attention core on oracle tokens: max err", (o - ref_o).abs().amax(dim=(1, 2)).tolist(), "absmax", ref_o.abs().amax(dim=(1, 2)).tolist(),
+          "max logit", (q @ k.transpose(-1, -2) / 128 ** 0.5).abs().amax(dim=(1, 2, 3)).tolist())
+
+
 if __name__ == "__main__":
-    main()
+    if os.environ.get("PROBE_OUTLIERS"):
+        outliers()
+    else:
+        main()
