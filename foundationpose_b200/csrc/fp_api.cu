@@ -102,7 +102,8 @@ struct fp_ctx {
   fp::DevBuf crops, act0, a1, a2, a3, ab0, ab1, ab2, c0, c1, c2, tok, qkv, att, x1pre, x1, ff, x2pre;
   fp::DevBuf head_out, poses_a, poses_b, feats, tail_qkv, tail_attn, tail_proj, scores, best;
   int tail_cap = 0;
-  float lin_b_host = 0.f;  // scorer linear.bias, kept on the host so the tail launch never syncs
+  float fold_c = 0.f;      // linear.weight . out_proj.bias + linear.bias (by-value kernel parameter)
+  fp::DevBuf fold_v, tail_counter;  // out_proj^T linear.weight [512]; arg-max ticket
   // CUDA graphs of the launch-bound inner loops, keyed by (kind, N, iterations)
   struct GraphEntry {
     cudaGraphExec_t exec = nullptr;
@@ -558,7 +559,7 @@ int fp_destroy(fp_ctx* c) {
                     &c->a3, &c->ab0, &c->ab1, &c->ab2, &c->c0, &c->c1, &c->c2, &c->tok, &c->qkv, &c->att, &c->x1pre,
                     &c->x1, &c->ff, &c->x2pre, &c->head_out, &c->poses_a, &c->poses_b, &c->feats, &c->tail_qkv,
                     &c->tail_attn, &c->tail_proj, &c->scores, &c->best, &c->lt_buf, &c->lr_buf, &c->feat_buf,
-                    &c->pose_stage, &c->mask_buf, &c->mask_stats, &c->crop_stats, &c->track_pose};
+                    &c->pose_stage, &c->mask_buf, &c->mask_stats, &c->crop_stats, &c->track_pose, &c->fold_v, &c->tail_counter};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (auto& kv : c->graphs)
@@ -607,7 +608,6 @@ int fp_load_network(fp_ctx* c, int which, const fp_tensor_t* tensors, int n) {
     auto old = net.t.find(t.name);
     if (old != net.t.end()) cudaFree(old->second.p);
     net.t[t.name] = d;
-    if (which == 1 && std::string(t.name) == "lin.b" && t.dtype == 0) c->lin_b_host = *reinterpret_cast<const float*>(t.data);
   }
   // verify that everything the execution plan needs is present, with the right size
   std::vector<std::pair<std::string, long long>> need;
@@ -646,6 +646,31 @@ int fp_load_network(fp_ctx* c, int which, const fp_tensor_t* tensors, int n) {
     FP_REQUIRE(it != net.t.end(), "fp_load_network: tensor '%s' missing", nd.first.c_str());
     FP_REQUIRE(it->second.numel == nd.second, "fp_load_network: tensor '%s' has %lld elements, expected %lld",
                nd.first.c_str(), it->second.numel, nd.second);
+  }
+  if (which == 1) {
+    // score = linear(out_proj(a)) = (W_out^T w_lin) . a + (w_lin . b_out + b_lin): fold once, in fp64
+    const float *wo = nullptr, *bo = nullptr, *wl = nullptr, *bl = nullptr;
+    for (int i = 0; i < n; ++i) {
+      const std::string nm = tensors[i].name;
+      const float* d = reinterpret_cast<const float*>(tensors[i].data);
+      if (tensors[i].dtype != 0) continue;
+      if (nm == "cross.out_w") wo = d;
+      else if (nm == "cross.out_b") bo = d;
+      else if (nm == "lin.w") wl = d;
+      else if (nm == "lin.b") bl = d;
+    }
+    FP_REQUIRE(wo && bo && wl && bl, "fp_load_network: the scorer tail tensors must be float32");
+    std::vector<float> v(512);
+    for (int i = 0; i < 512; ++i) {
+      double acc = 0.0;
+      for (int o = 0; o < 512; ++o) acc += (double)wl[o] * (double)wo[(size_t)o * 512 + i];
+      v[i] = (float)acc;
+    }
+    double cc = (double)bl[0];
+    for (int o = 0; o < 512; ++o) cc += (double)wl[o] * (double)bo[o];
+    c->fold_c = (float)cc;
+    FP_TRY(upload(c->epoch, c->fold_v, v));
+    FP_TRY(dev_alloc(c->epoch, c->tail_counter, 16, /*zero=*/true));
   }
   net.loaded = true;
   return 0;
@@ -933,16 +958,13 @@ int fp_score_tail(fp_ctx* c, const float* feats, int L, float* scores_out, int* 
   p.L = L;
   p.w_in = net.f("cross.in_w");
   p.b_in = net.f("cross.in_b");
-  p.w_out = net.f("cross.out_w");
-  p.b_out = net.f("cross.out_b");
-  p.w_lin = net.f("lin.w");
-  p.b_lin = c->lin_b_host;
+  p.fold_v = reinterpret_cast<const float*>(c->fold_v.p);
+  p.fold_c = c->fold_c;
   p.offset = 100.f;
   p.qkv = reinterpret_cast<float*>(c->tail_qkv.p);
-  p.attn = reinterpret_cast<float*>(c->tail_attn.p);
-  p.proj = reinterpret_cast<float*>(c->tail_proj.p);
   p.scores = scores_out;
   p.best = best_out;
+  p.counter = reinterpret_cast<unsigned int*>(c->tail_counter.p);
   return score_tail_launch(p, st);
   FP_API_END
 }

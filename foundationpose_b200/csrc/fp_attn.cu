@@ -5,9 +5,9 @@
 //   head_final_kernel    norm2 -> mean over the 400 tokens -> Linear(512, 3)  (refine_network.py:89-90;
 //                        the mean commutes with the final linear layer).
 //   token_mean_proj      scorer: mean over tokens of the attention output, then out_proj (score_network.py:72-74).
-//   cross_attn_kernel    scorer: attention across the L pose hypotheses (score_network.py:85-86).
-//   score_linear_kernel  Linear(512,1) + first-max argmax (score_network.py:88, predict_score.py:196,
-//                        estimater.py:226).
+//   cross_attn_score_kernel  scorer: attention across the L pose hypotheses (score_network.py:85-86), out_proj and
+//                        Linear(512,1) folded into one 512-vector, first-max argmax by the last CTA (score_network.py:87-88,
+//                        predict_score.py:196, estimater.py:226).
 //   pose_update_kernel   predict_pose_refine.py:195-231 + Utils.py:848-855 + pytorch3d so3_exp_map.
 #include "fp_attn.cuh"
 
@@ -275,10 +275,17 @@ __global__ void __launch_bounds__(256) rowwise_linear_kernel(const float* __rest
   }
 }
 
-// one CTA per query hypothesis, one warp per head
-__global__ void __launch_bounds__(128) cross_attn_kernel(const float* __restrict__ qkv, float* __restrict__ out, int L,
-                                                         float scale) {
+// One CTA per query hypothesis, one warp per head: attention across the L hypotheses (score_network.py:85-86), then
+// out_proj and Linear(512, 1) (score_network.py:87-88) folded into ONE 512-vector: score = v . attn + c with
+// v = W_out^T w_lin and c = w_lin . b_out + b_lin (both prepared in fp64 by fp_load_network).  The last CTA to
+// finish takes the arg-max (first index of the maximum = ids[0] of estimater.py:226) — two launches for the whole tail.
+__global__ void __launch_bounds__(128) cross_attn_score_kernel(const float* __restrict__ qkv, const float* __restrict__ fold_v,
+                                                               float fold_c, float offset, float* __restrict__ scores,
+                                                               int* __restrict__ best, unsigned int* __restrict__ counter,
+                                                               int L, float scale) {
   extern __shared__ float sc[];  // [4][L]
+  __shared__ float part[4];
+  __shared__ unsigned int ticket;
   const int q = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* s = sc + h * L;
   const float* qv = qkv + (size_t)q * 1536 + h * 128;
@@ -314,31 +321,26 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const float* __restrict
     o[3] += pk * vv.w;
   }
   const float inv = 1.f / sum;
-  float* op = out + (size_t)q * 512 + h * 128 + lane * 4;
-  op[0] = o[0] * inv;
-  op[1] = o[1] * inv;
-  op[2] = o[2] * inv;
-  op[3] = o[3] * inv;
-}
-
-// scores[l] = w . x[l] + b (+ offset);  then best = first index of the maximum
-__global__ void __launch_bounds__(1024) score_linear_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                            float bias, float offset, float* __restrict__ scores,
-                                                            int* __restrict__ best, int L) {
-  __shared__ float sv[1024];
-  __shared__ int si[1024];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int l = warp; l < L; l += 32) {
-    float s = 0.f;
-    for (int c = lane; c < 512; c += 32) s += x[(size_t)l * 512 + c] * __ldg(w + c);
-    s = warp_sum(s);
-    if (lane == 0) scores[l] = s + bias + offset;
+  const float4 fv = __ldg(reinterpret_cast<const float4*>(fold_v + h * 128 + lane * 4));
+  float p = (o[0] * inv) * fv.x + (o[1] * inv) * fv.y + (o[2] * inv) * fv.z + (o[3] * inv) * fv.w;
+  p = warp_sum(p);
+  if (lane == 0) part[h] = p;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    scores[q] = (((part[0] + part[1]) + part[2]) + part[3]) + fold_c + offset;
+    __threadfence();
+    ticket = atomicAdd(counter, 1u);
   }
   __syncthreads();
+  if (ticket != (unsigned)(L - 1)) return;
+  // last CTA: every score is visible; first index of the maximum
+  __threadfence();
+  __shared__ float sv[128];
+  __shared__ int si[128];
   float bv = -INFINITY;
   int bi = 0x7fffffff;
-  for (int l = threadIdx.x; l < L; l += 1024) {
-    const float v = scores[l];
+  for (int l = threadIdx.x; l < L; l += 128) {
+    const float v = __ldcg(scores + l);
     if (v > bv || (v == bv && l < bi)) {
       bv = v;
       bi = l;
@@ -347,7 +349,7 @@ __global__ void __launch_bounds__(1024) score_linear_kernel(const float* __restr
   sv[threadIdx.x] = bv;
   si[threadIdx.x] = bi;
   __syncthreads();
-  for (int st = 512; st > 0; st >>= 1) {
+  for (int st = 64; st > 0; st >>= 1) {
     if (threadIdx.x < st) {
       const float ov = sv[threadIdx.x + st];
       const int oi = si[threadIdx.x + st];
@@ -358,17 +360,25 @@ __global__ void __launch_bounds__(1024) score_linear_kernel(const float* __restr
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0 && best) *best = si[0];
+  if (threadIdx.x == 0) {
+    if (best) *best = si[0];
+    *counter = 0u;  // ready for the next launch (graph replays included)
+  }
 }
 
 int score_tail_launch(const ScoreTailParams& p, cudaStream_t stream) {
   if (p.L == 0) return 0;
   FP_REQUIRE(p.L <= 4096, "score tail: L=%d too large", p.L);
+  const size_t smem = 4 * (size_t)p.L * sizeof(float);
+  static std::atomic<unsigned long long> attr_mask{0};  // per device: the attribute is device state
+  if (!device_bit_test(attr_mask)) {
+    FP_CUDA_OK(cudaFuncSetAttribute(cross_attn_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4096 * 4));
+    device_bit_set(attr_mask);
+  }
   rowwise_linear_kernel<<<dim3((p.L + kRowBlock - 1) / kRowBlock, 8), 256, 0, stream>>>(p.feats, p.w_in, p.b_in, p.qkv, p.L, 1536);
-  cross_attn_kernel<<<p.L, 128, 4 * p.L * sizeof(float), stream>>>(p.qkv, p.attn, p.L, 0.08838834764831845f);
-  rowwise_linear_kernel<<<dim3((p.L + kRowBlock - 1) / kRowBlock, 8), 256, 0, stream>>>(p.attn, p.w_out, p.b_out, p.proj, p.L, 512);
-  score_linear_kernel<<<1, 1024, 0, stream>>>(p.proj, p.w_lin, p.b_lin, p.offset, p.scores, p.best, p.L);
-  note_launches(4);
+  cross_attn_score_kernel<<<p.L, 128, smem, stream>>>(p.qkv, p.fold_v, p.fold_c, p.offset, p.scores, p.best, p.counter, p.L,
+                                                      0.08838834764831845f);
+  note_launches(2);
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }

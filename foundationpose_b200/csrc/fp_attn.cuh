@@ -33,16 +33,13 @@ struct ScoreTailParams {
   int L;
   const float* w_in;    // att_cross.in_proj_weight  [1536][512] (fp32: the tail decides the argmax)
   const float* b_in;    // [1536]
-  const float* w_out;   // att_cross.out_proj.weight [512][512]
-  const float* b_out;
-  const float* w_lin;   // linear.weight [512]
-  float b_lin;
+  const float* fold_v;  // [512] = out_proj.weight^T linear.weight: out_proj followed by Linear(512, 1) is one dot product
+  float fold_c;         // linear.weight . out_proj.bias + linear.bias
   float offset;         // +100 of predict_score.py:207
   float* qkv;           // workspace [L][1536]
-  float* attn;          // workspace [L][512]
-  float* proj;          // workspace [L][512]
   float* scores;        // out [L]
   int* best;            // out, optional
+  unsigned int* counter;  // device word, zero between launches (the last CTA takes the arg-max and resets it)
 };
 int score_tail_launch(const ScoreTailParams& p, cudaStream_t stream);
 

@@ -94,6 +94,40 @@ def warp_perspective(src, M, dsize, mode):
     return F.grid_sample(src, grid, mode=mode, padding_mode="zeros", align_corners=False)
 
 
+def _kornia_src_coord(x, size):
+    """Closed form of the coordinate chain above for one axis, fp32 in the kernel's operation
+    order: (size-1)-normalisation, then grid_sample's align_corners=False un-normalisation."""
+    x = np.asarray(x, dtype=f32)
+    xn = ((f32(2) * x).astype(f32) / f32(size - 1)).astype(f32) - f32(1)
+    return ((((xn + f32(1)).astype(f32) * f32(size)).astype(f32) - f32(1)).astype(f32) * f32(0.5)).astype(f32)
+
+
+def unwarp_nearest(crop, win, full_hw):
+    """warp_perspective(crop, tf_to_crop^-1, (H, W), 'nearest') of h5_dataset.py:158 for the axis-aligned crop
+    transform, in CLOSED FORM: full-resolution pixel (v, u) reads crop pixel (rint(k(sy v - top sy)), rint(k(sx u - left sx))),
+    zeros outside.  Why not the op sequence of `warp_perspective` here: the crop window has integer edges, so the first
+    crop row / column maps back to EXACTLY -0.5, a rounding tie; through kornia's chain the outcome is decided by the
+    last bit of a 3x3 LU inverse (this CPU: the column survives for 151 of 228 random windows and vanishes for 77;
+    cuSOLVER rounds differently again), i.e. the reference's own result is implementation-defined there.  The closed
+    form resolves the tie the way exact arithmetic does (round-half-even: -0.5 -> 0, valid) and is what csrc/fp_crop.cu
+    evaluates.  crop (N,1,S,S) torch; win = dict(left, top, sx, sy) of float32 arrays."""
+    N, _, S, _ = crop.shape
+    H, W = full_hw
+    out = torch.zeros(N, 1, H, W, dtype=crop.dtype)
+    us = np.arange(W, dtype=f32)
+    vs = np.arange(H, dtype=f32)
+    for n in range(N):
+        sx, sy, left, top = f32(win["sx"][n]), f32(win["sy"][n]), f32(win["left"][n]), f32(win["top"][n])
+        jc = np.rint(_kornia_src_coord(((sx * us).astype(f32) + ((-left) * sx).astype(f32)).astype(f32), S)).astype(np.int64)
+        ic = np.rint(_kornia_src_coord(((sy * vs).astype(f32) + ((-top) * sy).astype(f32)).astype(f32), S)).astype(np.int64)
+        okj = (jc >= 0) & (jc < S)
+        oki = (ic >= 0) & (ic < S)
+        sub = crop[n, 0][torch.from_numpy(ic[oki])][:, torch.from_numpy(jc[okj])]
+        o = out[n, 0]
+        o[np.ix_(np.nonzero(oki)[0], np.nonzero(okj)[0])] = sub
+    return out
+
+
 def normalise_xyz(xyz, t, mesh_diameter, tau):
     """h5_dataset.py:93-99 (refiner, tau = 0.001) / :151-156 (scorer, tau = 0.1).
     xyz (B,3,H,W) torch, t (B,3)."""

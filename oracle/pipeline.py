@@ -49,7 +49,8 @@ def make_crops(poses, mt, rgb, depth, xyz_map, K, mesh_diameter, mode, crop_rati
         # predict_score.py:90 + h5_dataset.py:158-161: depth crop -> full res -> xyz -> crop (all nearest)
         d_t = torch.as_tensor(depth, dtype=torch.float32)[None, None].expand(N, -1, -1, -1)
         depthB = geometry.warp_perspective(d_t, tf_t, (S, S), "nearest")
-        depthB_ori = geometry.warp_perspective(depthB, torch.inverse(tf_t), (H, W), "nearest")
+        # the inverse warp in closed form: its border pixels are rounding ties (see geometry.unwarp_nearest)
+        depthB_ori = geometry.unwarp_nearest(depthB, win, (H, W))
         Kf = np.asarray(K, dtype=np.float32)
         xyz_ori = torch.stack([torch.from_numpy(geometry.depth2xyzmap(depthB_ori[n, 0].numpy(), Kf)) for n in range(N)]).permute(0, 3, 1, 2)
         xyzB = geometry.warp_perspective(xyz_ori, tf_t, (S, S), "nearest")

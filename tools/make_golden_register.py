@@ -90,6 +90,25 @@ def encoder_passes():
     print("cached", CACHE)
 
 
+def score_feats_only():
+    from foundationpose_b200.weights import random_state_dict
+    from oracle import geometry, nets, pipeline
+
+    torch.set_num_threads(os.cpu_count())
+    mesh, mt, gt, rgb, depth, mask, K, d = scene()
+    depth_f = geometry.bilateral_filter_depth(geometry.erode_depth(depth))
+    sd_s = random_state_dict("score", 0)
+    c = dict(np.load(CACHE))
+    poses = c["poses"][N_ITER]
+    feats = torch.empty(len(poses), 512)
+    for lo in range(0, len(poses), 42):
+        A, B, _ = pipeline.make_crops(poses[lo:lo + 42], mt, rgb, depth_f, None, K, d, 1)
+        feats[lo:lo + 42] = nets.score_features(sd_s, A, B)
+    c["feats"] = feats.numpy()
+    np.savez(CACHE, **c)
+    print("recomputed scorer features")
+
+
 def tail():
     from foundationpose_b200.weights import random_state_dict
     from oracle import nets
@@ -115,7 +134,10 @@ def tail():
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--tail", action="store_true")
+    ap.add_argument("--feats", action="store_true", help="recompute only the scorer features on the cached final poses")
     a = ap.parse_args()
-    if not a.tail or not os.path.exists(CACHE):
+    if a.feats and os.path.exists(CACHE):
+        score_feats_only()
+    elif not a.tail or not os.path.exists(CACHE):
         encoder_passes()
     tail()

@@ -106,8 +106,45 @@ def outliers():
           "max logit", (q @ k.transpose(-1, -2) / 128 ** 0.5).abs().amax(dim=(1, 2, 3)).tolist())
 
 
+def worst_crops():
+    """Pixel comparison of the CUDA and oracle scorer crops for the hypotheses with the largest feature error."""
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "register_252x5.npz")))
+    mesh = synth.make_mesh(3)
+    rgb, depth, mask = synth.make_scene(mesh.visual.image, g["gt_pose"])
+    d = synth.mesh_diameter(mesh.vertices)
+    mt = pipeline.mesh_tensors(mesh)
+    e = Engine()
+    e.load_network("score", random_state_dict("score", 0))
+    e.set_mesh(mt["pos"], mt["normals"], mt["faces"], d, uv=mt["uv"], tex=mt["tex"])
+    e.set_frame(rgb, depth, synth.DEFAULT_K, filter_depth=True)
+    poses = g["poses"][5]
+    f = e.score_features(poses).cpu().numpy()
+    per = np.abs(f - g["feats"]).max(1)
+    worst = np.argsort(-per)[:3]
+    print("worst", worst, per[worst], "poses t", poses[worst][:, :3, 3])
+    ref_depth_f = geometry.bilateral_filter_depth(geometry.erode_depth(depth))
+    for mode in (1, 0):
+        _, dbg, win = e.make_crops(poses[worst], mode=mode, want_dbg=True)
+        xyz = geometry.depth2xyzmap(ref_depth_f, synth.DEFAULT_K)
+        A, B, owin = pipeline.make_crops(poses[worst], mt, rgb, ref_depth_f, xyz, synth.DEFAULT_K, d, mode)
+        print("windows gpu", win.cpu().numpy().tolist(), "oracle", [owin[k].tolist() for k in ("left", "top", "sx", "sy")])
+        gA = dbg[:, 0].permute(0, 3, 1, 2).cpu()
+        gB = dbg[:, 1].permute(0, 3, 1, 2).cpu()
+        for name, x, y in (("A rgb", gA[:, :3], A[:, :3]), ("A xyz", gA[:, 3:], A[:, 3:]), ("B rgb", gB[:, :3], B[:, :3]), ("B xyz", gB[:, 3:], B[:, 3:])):
+            dd = (x - y).abs().amax(1)  # (n,160,160)
+            for i in range(len(worst)):
+                bad = (dd[i] > 1e-3).nonzero()
+                msg = ""
+                if len(bad):
+                    r0, r1, c0, c1 = bad[:, 0].min().item(), bad[:, 0].max().item(), bad[:, 1].min().item(), bad[:, 1].max().item()
+                    msg = f" rows {r0}-{r1} cols {c0}-{c1}; gpu-zero there: {(x[i].abs().sum(0)[bad[:, 0], bad[:, 1]] == 0).float().mean():.2f}, oracle-zero: {(y[i].abs().sum(0)[bad[:, 0], bad[:, 1]] == 0).float().mean():.2f}"
+                print(f"mode {mode} hyp {worst[i]} {name}: max {dd[i].max():.3e}, pixels > 1e-3: {len(bad)}{msg}")
+
+
 if __name__ == "__main__":
-    if os.environ.get("PROBE_OUTLIERS"):
+    if os.environ.get("PROBE_WORST"):
+        worst_crops()
+    elif os.environ.get("PROBE_OUTLIERS"):
         outliers()
     else:
         main()
