@@ -726,7 +726,7 @@ int fp_set_mesh(fp_ctx* c, int V, int F, const float* pos, const float* nrm, con
 
 int fp_set_crop_tile(fp_ctx* c, int tile) {
   FP_API_BEGIN
-  FP_REQUIRE(c && (tile == 0 || tile == 16 || tile == 32 || tile == 80), "fp_set_crop_tile: tile must be 0 (automatic), 16, 32 or 80");
+  FP_REQUIRE(c && (tile == 0 || tile == 16 || tile == 32 || tile == 40 || tile == 80), "fp_set_crop_tile: tile must be 0 (automatic), 16, 32, 40 or 80");
   c->crop_tile = tile;
   ++c->epoch;
   return 0;
