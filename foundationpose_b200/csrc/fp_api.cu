@@ -116,7 +116,7 @@ struct fp_ctx {
   bool cull_backfaces = true;  // FPOSE_NO_CULL=1: render both sides even for closed meshes (A/B checks)
   bool track_valid = false;
   int crop_tile = 0;
-  fp::DevBuf lt_buf, lr_buf, feat_buf, pose_stage;
+  fp::DevBuf lt_buf, lr_buf, feat_buf, pose_stage, tok_mean;
   fp::DevBuf mask_buf, mask_stats, crop_stats;
   // fp_track: pinned host staging (frame in, pose out) so that the whole frame is ONE graph launch
   void* stage_rgb = nullptr;
@@ -160,6 +160,7 @@ static int ensure_capacity(fp_ctx* c, int N) {
   rc |= dev_alloc(c->epoch, c->lr_buf, n * 9 * 4);
   rc |= dev_alloc(c->epoch, c->feat_buf, n * 512 * 4);
   rc |= dev_alloc(c->epoch, c->pose_stage, n * 16 * 4);
+  rc |= dev_alloc(c->epoch, c->tok_mean, n * 512 * 4);
   if (rc) return -2;
   c->cap_n = N;
   return 0;
@@ -301,8 +302,8 @@ static int run_score_feats(fp_ctx* c, const Net& net, int N, float* feats, cudaS
   ap.n_heads = 4;
   ap.scale = 0.08838834764831845f;
   FP_TRY(attn_core_launch(ap, st));
-  FP_TRY(token_mean_proj_launch(reinterpret_cast<const __half*>(c->att.p), net.h("att.out_w"), net.f("att.out_b"), feats,
-                                N, T, st));
+  FP_TRY(token_mean_proj_launch(reinterpret_cast<const __half*>(c->att.p), net.f("att.out_w32"), net.f("att.out_b"),
+                                reinterpret_cast<float*>(c->tok_mean.p), feats, N, T, st));
   return 0;
 }
 
@@ -559,7 +560,7 @@ int fp_destroy(fp_ctx* c) {
                     &c->a3, &c->ab0, &c->ab1, &c->ab2, &c->c0, &c->c1, &c->c2, &c->tok, &c->qkv, &c->att, &c->x1pre,
                     &c->x1, &c->ff, &c->x2pre, &c->head_out, &c->poses_a, &c->poses_b, &c->feats, &c->tail_qkv,
                     &c->tail_attn, &c->tail_proj, &c->scores, &c->best, &c->lt_buf, &c->lr_buf, &c->feat_buf,
-                    &c->pose_stage, &c->mask_buf, &c->mask_stats, &c->crop_stats, &c->track_pose, &c->fold_v, &c->tail_counter};
+                    &c->pose_stage, &c->mask_buf, &c->mask_stats, &c->crop_stats, &c->track_pose, &c->fold_v, &c->tail_counter, &c->tok_mean};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (auto& kv : c->graphs)
@@ -632,7 +633,7 @@ int fp_load_network(fp_ctx* c, int which, const fp_tensor_t* tensors, int n) {
   } else {
     need.push_back({"att.in_w", 1536LL * 512});
     need.push_back({"att.in_b", 1536});
-    need.push_back({"att.out_w", 512LL * 512});
+    need.push_back({"att.out_w32", 512LL * 512});
     need.push_back({"att.out_b", 512});
     need.push_back({"cross.in_w", 1536LL * 512});
     need.push_back({"cross.in_b", 1536});
@@ -726,7 +727,7 @@ int fp_set_mesh(fp_ctx* c, int V, int F, const float* pos, const float* nrm, con
 
 int fp_set_crop_tile(fp_ctx* c, int tile) {
   FP_API_BEGIN
-  FP_REQUIRE(c && (tile == 0 || tile == 16 || tile == 32 || tile == 40 || tile == 80), "fp_set_crop_tile: tile must be 0 (automatic), 16, 32, 40 or 80");
+  FP_REQUIRE(c && (tile == 0 || tile == 16 || tile == 32 || tile == 80), "fp_set_crop_tile: tile must be 0 (automatic), 16, 32 or 80");
   c->crop_tile = tile;
   ++c->epoch;
   return 0;

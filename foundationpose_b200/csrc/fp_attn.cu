@@ -2,9 +2,10 @@
 //
 //   layernorm_kernel     row LayerNorm over 512 channels (norm1 of the encoder layer; the residual add is
 //                        fused in the producing GEMM's epilogue).
-//   head_final_kernel    norm2 -> mean over the 400 tokens -> Linear(512, 3)  (refine_network.py:89-90;
-//                        the mean commutes with the final linear layer).
-//   token_mean_proj      scorer: mean over tokens of the attention output, then out_proj (score_network.py:72-74).
+//   token_reduce_kernel  a cluster of four CTAs per sequence: norm2 -> mean over the 400 tokens -> Linear(512, 3)
+//                        (refine_network.py:89-90; the mean commutes with the final linear layer), or the plain token
+//                        mean of the scorer's attention output (score_network.py:72-74; out_proj then runs over all
+//                        hypotheses at once).
 //   cross_attn_score_kernel  scorer: attention across the L pose hypotheses (score_network.py:85-86), out_proj and
 //                        Linear(512,1) folded into one 512-vector, first-max argmax by the last CTA (score_network.py:87-88,
 //                        predict_score.py:196, estimater.py:226).
@@ -17,6 +18,12 @@
 #include "fp_gemm.cuh"
 
 namespace fp {
+
+#define FP_TRY_RC(expr)  \
+  do {                   \
+    int _rc = (expr);    \
+    if (_rc) return _rc; \
+  } while (0)
 
 // attention itself lives in fp_attn_tc.cu (tcgen05); this file keeps the SIMT pieces around it
 int attn_core_launch(const AttnParams& p, cudaStream_t stream) { return attn_tc_launch(p, stream); }
@@ -110,43 +117,57 @@ int layernorm_launch(const __half* x, __half* y, const float* gamma, const float
   return 0;
 }
 
-// norm2 -> token mean -> Linear(512, out_dim<=8).  One CTA (16 warps) per sequence; every warp walks its tokens two
-// at a time so that the second row's loads overlap the first row's reductions (the kernel is latency-bound: only
-// 252 CTAs exist).  The partial sums are combined in a fixed order: the result does not depend on N or the shard.
-constexpr int kHeadWarps = 16;
-__global__ void __launch_bounds__(kHeadWarps * 32) head_final_kernel(const __half* __restrict__ x,
-                                                                     const float* __restrict__ gamma,
-                                                                     const float* __restrict__ beta,
-                                                                     const float* __restrict__ w,
-                                                                     const float* __restrict__ bias, float* __restrict__ out,
-                                                                     int T, int out_dim, float eps) {
+// Token reduction of one sequence (400 tokens x 512 channels) by a CLUSTER of four CTAs, 100 tokens each:
+//   kLN = true : norm2 -> token mean -> Linear(512, out_dim <= 8)   (refiner heads, refine_network.py:89-90; the mean
+//                commutes with the final linear layer)
+//   kLN = false: token mean of the attention output -> [512] fp32   (scorer, score_network.py:72-74; the out_proj that
+//                follows is a [N,512] x [512,512] product done by rowwise_linear_kernel for all hypotheses at once)
+// One CTA per sequence left 32 hypotheses per GPU (8-GPU shards) on 32 of 148 SMs and a single tracked pose on one.
+// The four partial sums live in the CTAs' shared memory; rank 0 reads its peers' over distributed shared memory and
+// adds them in rank order, every partial being built in a fixed order too: the result does not depend on N or the shard.
+constexpr int kHeadWarps = 8;
+constexpr int kTokSplit = 4;
+template <bool kLN>
+__global__ void __launch_bounds__(kHeadWarps * 32) token_reduce_kernel(const __half* __restrict__ x,
+                                                                       const float* __restrict__ gamma,
+                                                                       const float* __restrict__ beta,
+                                                                       const float* __restrict__ w,
+                                                                       const float* __restrict__ bias, float* __restrict__ out,
+                                                                       int T, int out_dim, float eps) {
   __shared__ float acc[kHeadWarps][512];
+  __shared__ float part[512];
   __shared__ float meanv[512];
-  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / kTokSplit, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned rank = cluster_ctarank();
   float a[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) a[i] = 0.f;
   LnAffine af;
-  ln_load_affine(af, gamma, beta, lane);
+  if (kLN) ln_load_affine(af, gamma, beta, lane);
   pdl_trigger();
   pdl_wait();
+  const int per = (T + kTokSplit - 1) / kTokSplit;
+  const int t_end = min(T, (int)(rank + 1) * per);
   const __half* xb = x + (size_t)b * T * 512;
-  int t = warp;
-  for (; t + kHeadWarps < T; t += 2 * kHeadWarps) {
+  int t = (int)rank * per + warp;
+  // two rows in flight per warp: the second row's loads overlap the first row's reductions
+  for (; t + kHeadWarps < t_end; t += 2 * kHeadWarps) {
     float v0[16], v1[16];
     load_row16(xb + (size_t)t * 512, lane, v0);
     load_row16(xb + (size_t)(t + kHeadWarps) * 512, lane, v1);
-    ln_row16(v0, af, eps);
-    ln_row16(v1, af, eps);
+    if (kLN) {
+      ln_row16(v0, af, eps);
+      ln_row16(v1, af, eps);
+    }
 #pragma unroll
     for (int i = 0; i < 16; ++i) a[i] += v0[i];
 #pragma unroll
     for (int i = 0; i < 16; ++i) a[i] += v1[i];
   }
-  if (t < T) {
+  if (t < t_end) {
     float v[16];
     load_row16(xb + (size_t)t * 512, lane, v);
-    ln_row16(v, af, eps);
+    if (kLN) ln_row16(v, af, eps);
 #pragma unroll
     for (int i = 0; i < 16; ++i) a[i] += v[i];
   }
@@ -157,75 +178,62 @@ __global__ void __launch_bounds__(kHeadWarps * 32) head_final_kernel(const __hal
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < kHeadWarps; ++k) s += acc[k][c];
-    meanv[c] = s / (float)T;
+    part[c] = s;
   }
+  cluster_sync_all();  // every CTA's `part` is complete and visible cluster-wide
+  if (rank == 0) {
+    const uint32_t mine = smem_u32(part);
+    for (int c = threadIdx.x; c < 512; c += kHeadWarps * 32) {
+      float s = 0.f;
+#pragma unroll
+      for (unsigned r = 0; r < (unsigned)kTokSplit; ++r) {
+        uint32_t remote;
+        float v;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(mine + 4u * (uint32_t)c), "r"(r));
+        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote));
+        s += v;
+      }
+      meanv[c] = s / (float)T;
+    }
+  }
+  cluster_sync_all();  // peers keep their shared memory alive until rank 0 has read it
+  if (rank != 0) return;
   __syncthreads();
-  if (warp < out_dim) {
-    float s = 0.f;
-    for (int c = lane; c < 512; c += 32) s += meanv[c] * __ldg(w + warp * 512 + c);
-    s = warp_sum(s);
-    if (lane == 0) out[b * out_dim + warp] = s + bias[warp];
+  if (kLN) {
+    if (warp < out_dim) {
+      float s = 0.f;
+      for (int c = lane; c < 512; c += 32) s += meanv[c] * __ldg(w + warp * 512 + c);
+      s = warp_sum(s);
+      if (lane == 0) out[b * out_dim + warp] = s + bias[warp];
+    }
+  } else {
+    for (int c = threadIdx.x; c < 512; c += kHeadWarps * 32) out[(size_t)b * 512 + c] = meanv[c];
   }
 }
 
 int head_final_launch(const __half* x, const float* gamma, const float* beta, const float* w, const float* bias,
                       float* out, int B, int T, int out_dim, cudaStream_t stream) {
-  FP_REQUIRE(out_dim <= 8, "head_final: out_dim %d > 8", out_dim);
+  FP_REQUIRE(out_dim <= kHeadWarps, "head_final: out_dim %d > %d", out_dim, kHeadWarps);
   if (B == 0) return 0;
-  FP_CUDA_OK(launch_pdl(head_final_kernel, dim3(B), dim3(kHeadWarps * 32), 0, stream, 1, x, gamma, beta, w, bias, out, T, out_dim,
-                        1e-5f));
+  FP_CUDA_OK(launch_pdl(token_reduce_kernel<true>, dim3(B * kTokSplit), dim3(kHeadWarps * 32), 0, stream, kTokSplit, x, gamma, beta,
+                        w, bias, out, T, out_dim, 1e-5f));
   note_launches(1);
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-// scorer: feat[b] = out_proj(mean_t attn[b, t, :])   (mean commutes with the linear projection)
-__global__ void __launch_bounds__(256) token_mean_proj_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
-                                                              const float* __restrict__ bias, float* __restrict__ out,
-                                                              int T) {
-  __shared__ float acc[8][512];
-  __shared__ float meanv[512];
-  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float a[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) a[i] = 0.f;
-  pdl_trigger();
-  pdl_wait();
-  for (int t = warp; t < T; t += 8) {
-    float v[16];
-    load_row16(x + ((size_t)b * T + t) * 512, lane, v);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) a[i] += v[i];
-  }
-#pragma unroll
-  for (int i = 0; i < 16; ++i) acc[warp][lane * 16 + i] = a[i];
-  __syncthreads();
-  for (int c = threadIdx.x; c < 512; c += 256) {
-    float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) s += acc[k][c];
-    meanv[c] = s / (float)T;
-  }
-  __syncthreads();
-  // 512 outputs, one warp per output row at a time
-  for (int o = warp; o < 512; o += 8) {
-    float v[16];
-    load_row16(w + (size_t)o * 512, lane, v);
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) s += v[i] * meanv[lane * 16 + i];
-    s = warp_sum(s);
-    if (lane == 0) out[(size_t)b * 512 + o] = s + bias[o];
-  }
-}
-
-int token_mean_proj_launch(const __half* x, const __half* w, const float* bias, float* out, int B, int T,
+// scorer: feat[b] = out_proj(mean_t attn[b, t, :])   (mean commutes with the linear projection): token means of all
+// hypotheses, then one [N,512] x [512,512]^T product in fp32
+int rowwise_linear_launch(const float* x, const float* w, const float* bias, float* y, int L, int n_out, cudaStream_t stream);
+int token_mean_proj_launch(const __half* x, const float* w_f32, const float* bias, float* mean_ws, float* out, int B, int T,
                            cudaStream_t stream) {
   if (B == 0) return 0;
-  FP_CUDA_OK(launch_pdl(token_mean_proj_kernel, dim3(B), dim3(256), 0, stream, 1, x, w, bias, out, T));
+  FP_CUDA_OK(launch_pdl(token_reduce_kernel<false>, dim3(B * kTokSplit), dim3(kHeadWarps * 32), 0, stream, kTokSplit, x,
+                        (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, mean_ws, T, 0,
+                        0.f));
   note_launches(1);
   FP_CUDA_OK(cudaGetLastError());
-  return 0;
+  return rowwise_linear_launch(mean_ws, w_f32, bias, out, B, 512, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -366,6 +374,13 @@ __global__ void __launch_bounds__(128) cross_attn_score_kernel(const float* __re
   }
 }
 
+int rowwise_linear_launch(const float* x, const float* w, const float* bias, float* y, int L, int n_out, cudaStream_t stream) {
+  rowwise_linear_kernel<<<dim3((L + kRowBlock - 1) / kRowBlock, 8), 256, 0, stream>>>(x, w, bias, y, L, n_out);
+  note_launches(1);
+  FP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int score_tail_launch(const ScoreTailParams& p, cudaStream_t stream) {
   if (p.L == 0) return 0;
   FP_REQUIRE(p.L <= 4096, "score tail: L=%d too large", p.L);
@@ -375,10 +390,10 @@ int score_tail_launch(const ScoreTailParams& p, cudaStream_t stream) {
     FP_CUDA_OK(cudaFuncSetAttribute(cross_attn_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4096 * 4));
     device_bit_set(attr_mask);
   }
-  rowwise_linear_kernel<<<dim3((p.L + kRowBlock - 1) / kRowBlock, 8), 256, 0, stream>>>(p.feats, p.w_in, p.b_in, p.qkv, p.L, 1536);
+  FP_TRY_RC(rowwise_linear_launch(p.feats, p.w_in, p.b_in, p.qkv, p.L, 1536, stream));
   cross_attn_score_kernel<<<p.L, 128, smem, stream>>>(p.qkv, p.fold_v, p.fold_c, p.offset, p.scores, p.best, p.counter, p.L,
                                                       0.08838834764831845f);
-  note_launches(2);
+  note_launches(1);
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }

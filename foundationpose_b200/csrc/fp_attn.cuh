@@ -25,7 +25,8 @@ int attn_tc_launch(const AttnParams& p, cudaStream_t stream);
 int layernorm_launch(const __half* x, __half* y, const float* gamma, const float* beta, int rows, cudaStream_t stream);
 int head_final_launch(const __half* x, const float* gamma, const float* beta, const float* w, const float* bias,
                       float* out, int B, int T, int out_dim, cudaStream_t stream);
-int token_mean_proj_launch(const __half* x, const __half* w, const float* bias, float* out, int B, int T,
+// w_f32: att.out_proj.weight as fp32 [512][512]; mean_ws: [B][512] fp32 workspace
+int token_mean_proj_launch(const __half* x, const float* w_f32, const float* bias, float* mean_ws, float* out, int B, int T,
                            cudaStream_t stream);
 
 struct ScoreTailParams {

@@ -577,19 +577,6 @@ __global__ void __launch_bounds__(kThreads, FP_CROP_MIN_CTAS) crop_tile_kernel(c
   __half* outA = p.crops + (size_t)n * img_stride;
   __half* outB = p.crops + (size_t)(p.b_img0 + n) * img_stride;
   constexpr int kBlocksX = TILE / 8, kBlocks = kBlocksX * (TILE / 4);
-  // The shade loop is bound by the latency of dependent L2 gathers (z-tile key -> face -> vertices -> texels), not by
-  // arithmetic.  Two things shorten the chain per block: the face record of the NEXT block is fetched while the current
-  // one is shaded, and the observed-crop taps (which depend on nothing but the tables) are issued before the rendered
-  // side's chain instead of after it.
-  unsigned long long key_next = 0ull;
-  int4 fi_next = make_int4(0, 0, 0, 0);
-  {
-    const int jl0 = (warp % kBlocksX) * 8 + (lane & 7), rl0 = (warp / kBlocksX) * 4 + (lane >> 3);
-    if (warp < kBlocks) {
-      key_next = sm.zt[rl0 * TILE + jl0];
-      if (key_next != 0ull) fi_next = __ldg(M.faces + (int)(0xFFFFFFFFu - (unsigned)(key_next & 0xFFFFFFFFull)));
-    }
-  }
 #pragma unroll 1
   for (int blk = warp; blk < kBlocks; blk += kWarps) {
     const int jl = (blk % kBlocksX) * 8 + (lane & 7), rl = (blk / kBlocksX) * 4 + (lane >> 3);
@@ -597,45 +584,12 @@ __global__ void __launch_bounds__(kThreads, FP_CROP_MIN_CTAS) crop_tile_kernel(c
     const float wx1 = sm.colf[jl];
     const int cxi = sm.colx[jl];
     const int unc = sm.coln[jl], uzc = sm.colz[jl];
-    // ---- B (loads only): bilinear rgb taps and the nearest geometry sample of the observed frame
-    const float wy1 = sm.rowf[rl];
-    const int ryi = sm.rowy[rl];
-    const int vn = sm.rown[rl];
-    uchar4 t00, t01, t10, t11;
-    float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
-    float bzz = 0.f;
-    {
-      const int x1 = cxi & 0x3fffffff, y1 = ryi & 0x3fffffff;
-      const int x0 = (cxi & 0x80000000) ? x1 : max(x1 - 1, 0), y0 = (ryi & 0x80000000) ? y1 : max(y1 - 1, 0);
-      const uchar4* row0 = p.rgb + (size_t)y0 * p.W;
-      const uchar4* row1 = p.rgb + (size_t)y1 * p.W;
-      t00 = __ldg(row0 + x0);
-      t01 = __ldg(row0 + x1);
-      t10 = __ldg(row1 + x0);
-      t11 = __ldg(row1 + x1);
-      if (unc >= 0 && vn >= 0) {
-        if (p.mode == 0) {
-          bq = __ldg(p.xyz_map + (size_t)vn * p.W + unc);  // refiner: xyz_map (depth2xyzmap, Utils.py:399-438) sampled nearest
-        } else {
-          const int v2 = sm.rowz[rl];
-          if (uzc >= 0 && v2 >= 0) bzz = __ldg(p.depth + (size_t)v2 * p.W + uzc);
-        }
-      }
-    }
     // ---- A: rendered crop
     float ar = 0.f, ag = 0.f, ab = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
-    const unsigned long long key = key_next;
-    const int4 fi = fi_next;
-    {
-      const int nb = blk + kWarps;
-      key_next = 0ull;
-      if (nb < kBlocks) {
-        const int jn = (nb % kBlocksX) * 8 + (lane & 7), rn = (nb / kBlocksX) * 4 + (lane >> 3);
-        key_next = sm.zt[rn * TILE + jn];
-        if (key_next != 0ull) fi_next = __ldg(M.faces + (int)(0xFFFFFFFFu - (unsigned)(key_next & 0xFFFFFFFFull)));
-      }
-    }
+    const unsigned long long key = sm.zt[rl * TILE + jl];
     if (key != 0ull) {
+      const int f = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+      const int4 fi = __ldg(M.faces + f);
       const int vid[3] = {fi.x, fi.y, fi.z};
       VtxScreen vs[3];
       float dif[3];
@@ -719,12 +673,19 @@ __global__ void __launch_bounds__(kThreads, FP_CROP_MIN_CTAS) crop_tile_kernel(c
       ab = fminf(fmaxf(cb * 0.8f + diffuse * cb * 0.5f, 0.f), 1.f);
       normalise_xyz(X, Y, Z, tvec, inv_radius, tau, ax, ay, az);
     }
-    // ---- B: observed crop (arithmetic on the taps loaded above)
+    // ---- B: observed crop
     float br = 0.f, bg = 0.f, bb = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
     {
-      // bilinear rgb, zeros padding: weights / validity come from the per-axis tables
+      // bilinear rgb, zeros padding: tap indices / weights / validity come from the per-axis tables
+      const float wy1 = sm.rowf[rl];
+      const int ryi = sm.rowy[rl];
+      const int x1 = cxi & 0x3fffffff, y1 = ryi & 0x3fffffff;
+      const int x0 = (cxi & 0x80000000) ? x1 : max(x1 - 1, 0), y0 = (ryi & 0x80000000) ? y1 : max(y1 - 1, 0);
       const float wx[2] = {(cxi & 0x40000000) ? 0.f : 1.f - wx1, (cxi & 0x80000000) ? 0.f : wx1};
       const float wy[2] = {(ryi & 0x40000000) ? 0.f : 1.f - wy1, (ryi & 0x80000000) ? 0.f : wy1};
+      const uchar4* row0 = p.rgb + (size_t)y0 * p.W;
+      const uchar4* row1 = p.rgb + (size_t)y1 * p.W;
+      const uchar4 t00 = __ldg(row0 + x0), t01 = __ldg(row0 + x1), t10 = __ldg(row1 + x0), t11 = __ldg(row1 + x1);
       const float w00 = wx[0] * wy[0], w01 = wx[1] * wy[0], w10 = wx[0] * wy[1], w11 = wx[1] * wy[1];
       br = w00 * t00.x + w01 * t01.x + w10 * t10.x + w11 * t11.x;
       bg = w00 * t00.y + w01 * t01.y + w10 * t10.y + w11 * t11.y;
@@ -733,11 +694,25 @@ __global__ void __launch_bounds__(kThreads, FP_CROP_MIN_CTAS) crop_tile_kernel(c
       bg *= (1.f / 255.f);
       bb *= (1.f / 255.f);
       // nearest geometry
-      float X = bq.x, Y = bq.y, Z = bq.z;
-      if (p.mode != 0 && bzz >= 0.001f) {  // depth2xyzmap_batch(zfar=inf): invalid z<0.001 -> 0
-        X = ((float)unc - p.cx) * bzz / p.fx;
-        Y = ((float)vn - p.cy) * bzz / p.fy;
-        Z = bzz;
+      const int vn = sm.rown[rl];
+      float X = 0.f, Y = 0.f, Z = 0.f;
+      if (unc >= 0 && vn >= 0) {
+        if (p.mode == 0) {
+          // refiner: xyz_map (depth2xyzmap, Utils.py:399-438) sampled nearest
+          const float4 q = __ldg(p.xyz_map + (size_t)vn * p.W + unc);
+          X = q.x;
+          Y = q.y;
+          Z = q.z;
+        } else {
+          const int v2 = sm.rowz[rl];
+          float zz = 0.f;
+          if (uzc >= 0 && v2 >= 0) zz = __ldg(p.depth + (size_t)v2 * p.W + uzc);
+          if (zz >= 0.001f) {  // depth2xyzmap_batch(zfar=inf): invalid z<0.001 -> 0
+            X = ((float)unc - p.cx) * zz / p.fx;
+            Y = ((float)vn - p.cy) * zz / p.fy;
+            Z = zz;
+          }
+        }
       }
       normalise_xyz(X, Y, Z, tvec, inv_radius, tau, bx, by, bz);
     }
@@ -760,7 +735,7 @@ __global__ void __launch_bounds__(kThreads, FP_CROP_MIN_CTAS) crop_tile_kernel(c
 static int g_crop_tile_override = [] {
   const char* e = getenv("FPOSE_CROP_TILE");  // 16 / 32 / 80: force one tile size (A/B measurements)
   const int v = e ? atoi(e) : 0;
-  return (v == 16 || v == 32 || v == 40 || v == 80) ? v : 0;
+  return (v == 16 || v == 32 || v == 80) ? v : 0;
 }();
 
 #define FP_TRY_RC(expr)  \
@@ -794,9 +769,8 @@ int crop_launch(const CropParams& p, cudaStream_t stream) {
   prof_mark_begin(1, (double)p.N * 2.0 * 6.0 * S * S * 2.0, stream);
   int tile = p.N >= 64 ? 80 : (p.N >= 4 ? 32 : 16);
   if (g_crop_tile_override) tile = g_crop_tile_override;
-  if (p.tile_override == 16 || p.tile_override == 32 || p.tile_override == 40 || p.tile_override == 80) tile = p.tile_override;
-  FP_TRY_RC(tile == 80 ? launch_tile<80>(p, stream)
-                       : (tile == 40 ? launch_tile<40>(p, stream) : (tile == 32 ? launch_tile<32>(p, stream) : launch_tile<16>(p, stream))));
+  if (p.tile_override == 16 || p.tile_override == 32 || p.tile_override == 80) tile = p.tile_override;
+  FP_TRY_RC(tile == 80 ? launch_tile<80>(p, stream) : (tile == 32 ? launch_tile<32>(p, stream) : launch_tile<16>(p, stream)));
   prof_mark_end(stream);
   note_launches(1);
   FP_CUDA_OK(cudaGetLastError());

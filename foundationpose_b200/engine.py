@@ -127,6 +127,9 @@ def pack_network(sd, kind):
             out[f"{dst}.in_b"] = f32(sd[f"{src}.in_proj_bias"])
             out[f"{dst}.out_w"] = cvt(sd[f"{src}.out_proj.weight"])
             out[f"{dst}.out_b"] = f32(sd[f"{src}.out_proj.bias"])
+        # `att`'s out_proj acts on the token MEAN (one 512-vector per hypothesis): a [N,512] x [512,512] product in fp32
+        out["att.out_w32"] = f32(sd["att.out_proj.weight"])
+        del out["att.out_w"]
         out["lin.w"] = f32(sd["linear.weight"].reshape(-1))
         out["lin.b"] = f32(sd["linear.bias"].reshape(-1))
     return out
