@@ -119,13 +119,13 @@ def random_state_dict(kind, seed=0, c_in=6, use_bn=True):
         # The cross-hypothesis tail decides the arg-max.  A plain random init makes att_cross attend uniformly, so all
         # 252 scores collapse to one value +- 6e-4 and "the selected index" is decided by rounding noise.  The stand-in
         # tail therefore has its own generator (the encoder / `att` weights above are untouched by it), sharper
-        # query/key projections (x3) and a larger read-out (x60), picked — tools/make_golden_register.py reports the
-        # numbers — so that on the 252-hypothesis golden scene the scores spread (std 0.12) and the winner leads the
-        # runner-up by 1.8 sigma (0.21), ~50x the score error of an fp16 feature path.
-        g2 = torch.Generator(device="cpu").manual_seed(7310 + seed)
+        # query/key projections (x2) and a larger read-out (x60), picked by tools/pick_tail_seed.py so that on BOTH the
+        # 252-hypothesis golden scene (oracle features) and the bench scene (bench.py) the winner leads the runner-up
+        # by 1.2 sigma of the score spread (0.10 of 0.085 / 0.19 of 0.16), ~50x the score error of an fp16 feature path.
+        g2 = torch.Generator(device="cpu").manual_seed(7615 + seed)
         _mha(g2, sd, "att_cross")
-        sd["att_cross.in_proj_weight"][:1024] *= 3.0
-        sd["att_cross.in_proj_bias"][:1024] *= 3.0
+        sd["att_cross.in_proj_weight"][:1024] *= 2.0
+        sd["att_cross.in_proj_bias"][:1024] *= 2.0
         _linear(g2, sd, "linear", 1, 512, gain=4.0)
         sd["linear.weight"] *= 60.0
     else:

@@ -5,7 +5,7 @@ every per-iteration pose, delta, scorer feature, score and the ranking of the or
 Bars (BASELINE.json north_star): the predicted SE(3) delta of EVERY hypothesis at EVERY iteration within 1e-3
 (translation in metres, rotation-matrix entries) when the CUDA path starts the iteration from the oracle's pose,
 and the selected hypothesis index identical — asserted unconditionally: the seeded scorer tail
-(weights.random_state_dict) gives the oracle a top-2 margin of 0.21 = 1.8 sigma of the score spread.
+(weights.random_state_dict) gives the oracle a top-2 margin of 0.10 = 1.2 sigma of the score spread, ~50x the score error.
 """
 import os
 
