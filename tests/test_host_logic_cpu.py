@@ -152,3 +152,36 @@ def test_meshprep_diameter_and_voxel_downsample():
     np.testing.assert_allclose(n[0], m.vertex_normals[sel].mean(0), atol=1e-12)
     single, _ = meshprep.voxel_down_sample(m.vertices, 10.0)
     np.testing.assert_allclose(single, m.vertices.mean(0)[None], atol=1e-12)
+
+
+def test_reference_config_defaults(tmp_path):
+    """weights/<run>/config.yml is read the way the reference predictors read it (predict_pose_refine.py:107-131,
+    predict_score.py:131-143): missing keys get the reference's backward-compatibility defaults, per predictor."""
+    from foundationpose_b200 import weights
+
+    p = tmp_path / "config.yml"
+    p.write_text("crop_ratio: 1.1\nuse_BN: true\nc_in: 6\nnormalize_xyz: true\nzfar: .inf\nrot_normalizer: 0.3\n")
+    c = weights.load_reference_config(str(p), "score")
+    assert c["crop_ratio"] == 1.1 and c["use_BN"] is True and c["zfar"] == float("inf") and c["rot_normalizer"] == 0.3
+    c = weights.load_reference_config(str(tmp_path / "missing.yml"), "refine")
+    assert c["crop_ratio"] == 1.2 and c["use_BN"] is False and c["c_in"] == 4 and c["zfar"] == 3 and c["trans_rep"] == "tracknet"
+    p.write_text("crop_ratio: null\nzfar: 'Inf'\n")
+    c = weights.load_reference_config(str(p), "refine")
+    assert c["crop_ratio"] == 1.2 and c["zfar"] == float("inf")
+
+
+def test_unsupported_config_raises():
+    """A cfg value the engine cannot honour is an error, not silently ignored."""
+    import pytest
+
+    from foundationpose_b200 import estimater, weights
+
+    sd = {}
+    with pytest.raises(ValueError):
+        estimater._load_cfg_and_weights("x", "refine", sd, {"no_such_key": 1})
+    with pytest.raises(NotImplementedError):
+        estimater._load_cfg_and_weights("x", "refine", sd, {"rot_rep": "6d"})
+    with pytest.raises(NotImplementedError):
+        estimater._load_cfg_and_weights("x", "score", sd, {"input_resize": [128, 128]})
+    cfg, _ = estimater._load_cfg_and_weights("x", "score", sd, {"crop_ratio": 1.1})
+    assert cfg["crop_ratio"] == 1.1 and cfg["rot_rep"] == weights.DEFAULT_CFG["rot_rep"]

@@ -144,3 +144,42 @@ def test_foundationpose_api(setup):
     # restore the fixture's frame/mesh state for other tests
     s["e"].set_mesh(s["mt"]["pos"], s["mt"]["normals"], s["mt"]["faces"], s["d"], uv=s["mt"]["uv"], tex=s["mt"]["tex"])
     s["e"].set_frame(s["rgb"], s["depth"], s["K"], filter_depth=False)
+
+
+def test_predict_honours_per_call_arguments(setup):
+    """PoseRefinePredictor.predict / ScorePredictor.predict with the reference's per-call arguments
+    (predict_pose_refine.py:150-177, predict_score.py:160-180): another mesh is uploaded, a caller-supplied xyz map is
+    used, each predictor keeps its own crop_ratio."""
+    from foundationpose_b200 import synth
+    from foundationpose_b200.engine import Engine
+    from foundationpose_b200.estimater import PoseRefinePredictor, ScorePredictor, make_mesh_tensors
+    from oracle import geometry
+
+    s = setup
+    e = Engine()
+    refiner = PoseRefinePredictor(engine=e, state_dict=s["sd_r"])
+    scorer = ScorePredictor(engine=e, state_dict=s["sd_s"], cfg={"crop_ratio": 1.1})
+    assert scorer.cfg["crop_ratio"] == 1.1 and refiner.cfg["crop_ratio"] == 1.2
+    poses = s["poses"][:3]
+    mt = make_mesh_tensors(s["mesh"])
+    xyz = geometry.depth2xyzmap(s["depth"], s["K"])
+    # no mesh in the context and none passed: an error, not garbage
+    with pytest.raises(ValueError):
+        refiner.predict(rgb=s["rgb"], depth=s["depth"], K=s["K"], ob_in_cams=poses, xyz_map=xyz, iteration=1)
+    a, _ = refiner.predict(rgb=s["rgb"], depth=s["depth"], K=s["K"], ob_in_cams=poses, xyz_map=xyz, mesh_tensors=mt, mesh_diameter=s["d"], iteration=1)
+    ref, _, _ = s["e"].refine(poses, 1)
+    assert torch.equal(a, ref), "same mesh / frame through the per-call arguments must give the same poses"
+    # a caller-supplied xyz map is what the observed crop is built from
+    b, _ = refiner.predict(rgb=s["rgb"], depth=s["depth"], K=s["K"], ob_in_cams=poses, xyz_map=np.zeros_like(xyz), mesh_tensors=mt,
+                           mesh_diameter=s["d"], iteration=1)
+    assert not torch.equal(a, b)
+    # another mesh passed per call replaces the one in the context
+    small = make_mesh_tensors(synth.make_mesh(2))
+    c, _ = refiner.predict(rgb=s["rgb"], depth=s["depth"], K=s["K"], ob_in_cams=poses, xyz_map=xyz, mesh_tensors=small, mesh_diameter=s["d"], iteration=1)
+    assert e.mesh_info()["F"] == 320 and not torch.equal(a, c)
+    # the scorer's own crop_ratio: scores differ from a scorer configured with the refiner's 1.2
+    sc_a, _ = scorer.predict(rgb=s["rgb"], depth=s["depth"], K=s["K"], ob_in_cams=poses, mesh_tensors=mt, mesh_diameter=s["d"])
+    e2 = Engine()
+    scorer2 = ScorePredictor(engine=e2, state_dict=s["sd_s"])
+    sc_b, _ = scorer2.predict(rgb=s["rgb"], depth=s["depth"], K=s["K"], ob_in_cams=poses, mesh_tensors=mt, mesh_diameter=s["d"])
+    assert not torch.equal(sc_a, sc_b)
