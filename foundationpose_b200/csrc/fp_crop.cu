@@ -1,13 +1,14 @@
-// fp_crop.cu — tiled "pose -> 160x160 network inputs" producer.  ONE kernel; one CTA per (pose hypothesis, 32x32-pixel
-// tile of the crop); nothing full-frame, nothing fp32 and no intermediate of any kind is materialised in HBM:
+// fp_crop.cu — tiled "pose -> 160x160 network inputs" producer.  ONE kernel; one CTA per (pose hypothesis, TILE x TILE
+// pixel tile of the crop; TILE = 80 / 32 / 16 by batch size); nothing full-frame, nothing fp32 and no intermediate of
+// any kind is materialised in HBM:
 //   1. crop window from the pose                          (Utils.py:577-621 compute_crop_window_tf_batch, 'box_3d')
 //   2. binning: every MESHLET of the mesh (<= 64 triangles, fp_meshlet.cu) is tested against the tile with its
 //      bounding sphere and — closed meshes — its normal cone; survivors go to a shared-memory list
 //   3. raster: each warp takes meshlets off the list, transforms their <= 64 vertices into shared memory, sets up
 //      their triangles from there (two per lane) and depth-tests the covered pixels into a SHARED-MEMORY z-tile
-//      (32x32 64-bit keys: interpolated 1/Z | ~face id, one atomicMax per fragment)
+//      (TILE x TILE 64-bit keys: interpolated 1/Z | ~face id, one atomicMax per fragment)
 //                                                          (Utils.py:133-219 nvdiffrast_render with bbox2d: dr.rasterize)
-//   4. shade: every thread resolves four pixels of the tile: perspective-correct attributes of the winning triangle,
+//   4. shade: warps resolve 8 x 4-pixel blocks of the tile: perspective-correct attributes of the winning triangle,
 //      bilinear wrap texture, Lambert term (dr.interpolate / dr.texture, Utils.py:183-215), the observed frame resampled
 //      into the same window (predict_pose_refine.py:63,72 / predict_score.py:89-90 kornia warp_perspective;
 //      h5_dataset.py:158-161 depth round trip for the scorer), normalisation of both (h5_dataset.py:79-127, :137-179)

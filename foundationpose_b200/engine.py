@@ -315,6 +315,8 @@ class Engine:
         crops = torch.empty(2 * N, *CROP_SHAPE, dtype=torch.float16, device="cuda") if want_crops else None
         dbg = torch.empty(N, 2, 160, 160, 6, dtype=torch.float32, device="cuda") if want_dbg else None
         win = torch.empty(N, 4, dtype=torch.float32, device="cuda")
+        if N == 0:
+            return crops, dbg, win
         _lib.check(lib.fp_make_crops(self._h, _p(poses), N, mode, _p(crops), _p(dbg), _p(win), _stream()), "fp_make_crops")
         return crops, dbg, win
 
@@ -324,6 +326,8 @@ class Engine:
         out = torch.empty_like(poses)
         lt = torch.empty(N, 3, dtype=torch.float32, device="cuda")
         lr = torch.empty(N, 3, 3, dtype=torch.float32, device="cuda")
+        if N == 0:
+            return out, lt, lr
         _lib.check(lib.fp_refine(self._h, _p(poses), N, int(iterations), _p(out), _p(lt), _p(lr), _stream()), "fp_refine")
         return out, lt, lr
 
@@ -339,6 +343,8 @@ class Engine:
         poses = self._poses(poses)
         N = len(poses)
         feats = torch.empty(N, 512, dtype=torch.float32, device="cuda")
+        if N == 0:
+            return feats
         _lib.check(lib.fp_score_features(self._h, _p(poses), N, _p(feats), _stream()), "fp_score_features")
         return feats
 

@@ -165,3 +165,53 @@ def test_start_poses_match_host_guess_translation(scene):
         p = poses.cpu().numpy()
         np.testing.assert_array_equal(p[:, :3, :3], grid.cpu().numpy()[:, :3, :3])
         np.testing.assert_allclose(p[:, :3, 3], np.tile(ref_t.astype(np.float32), (252, 1)), atol=1e-6, rtol=0)
+
+
+def test_other_frame_size_and_intrinsics():
+    """The path is not specialised to 640x480: a 1280x720 frame with its own intrinsics, crops vs the oracle."""
+    from foundationpose_b200 import synth
+    from foundationpose_b200.engine import Engine
+    from oracle import geometry, pipeline
+
+    mesh = synth.make_mesh(2)
+    K = np.array([[920.0, 0, 640.0], [0, 915.0, 360.0], [0, 0, 1.0]])
+    pose = np.eye(4)
+    pose[:3, :3] = synth.random_rotation(4)
+    pose[:3, 3] = [-0.15, 0.08, 0.7]
+    rgb, depth, mask = synth.make_scene(mesh.visual.image, pose, K=K, H=720, W=1280)
+    d = synth.mesh_diameter(mesh.vertices)
+    mt = pipeline.mesh_tensors(mesh)
+    e = Engine()
+    e.set_mesh(mt["pos"], mt["normals"], mt["faces"], d, uv=mt["uv"], tex=mt["tex"])
+    e.set_frame(rgb, depth, K, filter_depth=False)
+    poses = np.stack([pose, pose]).astype(np.float32)
+    poses[1, :3, 3] = [0.62, 0.3, 0.72]  # crop window partly outside the frame
+    xyz = geometry.depth2xyzmap(depth, K)
+    for mode in (0, 1):
+        _, dbg, win = e.make_crops(poses, mode=mode, want_dbg=True)
+        A, B, owin = pipeline.make_crops(poses, mt, rgb, depth, xyz, K, d, mode)
+        np.testing.assert_array_equal(win.cpu().numpy()[:, 0], owin["left"])
+        np.testing.assert_array_equal(win.cpu().numpy()[:, 3], owin["sy"])
+        gA = dbg[:, 0].permute(0, 3, 1, 2)
+        gB = dbg[:, 1].permute(0, 3, 1, 2)
+        _compare(gA[:, 3:], A[:, 3:], "rendered xyz", 0.999, 2e-4)
+        _compare(gA[:, :3], A[:, :3], "rendered rgb", 0.998, 2e-3)
+        _compare(gB[:, :3], B[:, :3], "observed rgb", 0.998, 2e-3)
+        _compare(gB[:, 3:], B[:, 3:], "observed xyz", 0.998, 2e-4)
+
+
+@pytest.mark.parametrize("n", [1, 3, 5, 66])
+def test_batch_size_does_not_change_a_hypothesis(scene, n):
+    """Crops of hypothesis 0 are bit-identical whatever else is in the batch (tile size 16 / 32 / 80 is chosen from the
+    batch size; the A/B image boundary is padded to a multiple of four)."""
+    e = scene["e"]
+    e.set_frame(scene["rgb"], scene["depth"], scene["K"], filter_depth=False)
+    base = scene["poses"][[0, 1, 2]]
+    poses = np.concatenate([base] * ((n + 2) // 3))[:n].astype(np.float32)
+    crops, _, _ = e.make_crops(poses, mode=0)
+    ref, _, _ = e.make_crops(poses[:1], mode=0)
+    assert torch.equal(crops[0], ref[0]) and torch.equal(crops[n], ref[1])
+    if n == 0:
+        return
+    empty, _, _ = e.make_crops(poses[:0], mode=0)
+    assert empty.shape[0] == 0
