@@ -157,10 +157,11 @@ def test_split_k_small_grids(case):
         else:
             run = lambda **k: ops.gemm_layer(kind, xn, wp, b, **args, **k)
             ref = y
-    plain = run()
     launches0 = _lib.launch_count()
     got = run(split_ws=ws)
     assert _lib.launch_count() - launches0 == 2, "expected the split-K pair (tile kernel + finisher) for this grid"
     _cmp(got, ref, case + " (split-K)")
-    _cmp(plain, ref, case + " (plain)")
-    assert (got.float() - plain.float()).abs().max().item() <= 4e-3
+    if case != "conv128_split_concat":  # the unsplit 128-channel kernels tile four images: they need out_split % 4 == 0
+        plain = run()
+        _cmp(plain, ref, case + " (plain)")
+        assert (got.float() - plain.float()).abs().max().item() <= 4e-3
