@@ -116,7 +116,7 @@ struct fp_ctx {
   bool cull_backfaces = true;  // FPOSE_NO_CULL=1: render both sides even for closed meshes (A/B checks)
   bool track_valid = false;
   int crop_tile = 0;
-  fp::DevBuf lt_buf, lr_buf, feat_buf, pose_stage, tok_mean, split_ws;
+  fp::DevBuf lt_buf, lr_buf, feat_buf, pose_stage, tok_mean;
   fp::DevBuf mask_buf, mask_stats, crop_stats;
   // fp_track: pinned host staging (frame in, pose out) so that the whole frame is ONE graph launch
   void* stage_rgb = nullptr;
@@ -161,7 +161,6 @@ static int ensure_capacity(fp_ctx* c, int N) {
   rc |= dev_alloc(c->epoch, c->feat_buf, n * 512 * 4);
   rc |= dev_alloc(c->epoch, c->pose_stage, n * 16 * 4);
   rc |= dev_alloc(c->epoch, c->tok_mean, n * 512 * 4);
-  rc |= dev_alloc(c->epoch, c->split_ws, (size_t)64 << 20);
   if (rc) return -2;
   c->cap_n = N;
   return 0;
@@ -203,13 +202,6 @@ static GemmLayer mk(int kind, int n_img, int H, int W, int Cin, int Cout, const 
   return L;
 }
 
-// every layer of the product path may use the context's split-K workspace (single-pose grids, fp_gemm.cu)
-static int gl(fp_ctx* c, GemmLayer L, cudaStream_t st) {
-  L.split_ws = reinterpret_cast<float*>(c->split_ws.p);
-  L.split_ws_bytes = c->split_ws.bytes;
-  return gemm_layer_launch(L, st);
-}
-
 #define FP_TRY(expr)         \
   do {                       \
     int _rc = (expr);        \
@@ -223,21 +215,21 @@ static int run_encoder(fp_ctx* c, const Net& net, const __half* crops, int N, cu
   auto B = [&](int i) { snprintf(bn, sizeof bn, "enc.%d.b", i); return net.f(bn); };
   const int Np = b_img0_of(N);
   const int M = Np + N;
-  FP_TRY(gl(c, mk(LK_CONV7_S2, M, S, S, 8, 64, crops, W(0), B(0), c->act0.p, 1), st));
-  FP_TRY(gl(c, mk(LK_CONV3_S2, M, 80, 80, 64, 128, c->act0.p, W(1), B(1), c->a1.p, 1), st));
-  FP_TRY(gl(c, mk(LK_CONV3_S1, M, 40, 40, 128, 128, c->a1.p, W(2), B(2), c->a2.p, 1), st));
-  FP_TRY(gl(c, mk(LK_CONV3_S1, M, 40, 40, 128, 128, c->a2.p, W(3), B(3), c->a3.p, 1, c->a1.p), st));
-  FP_TRY(gl(c, mk(LK_CONV3_S1, M, 40, 40, 128, 128, c->a3.p, W(4), B(4), c->a2.p, 1), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV7_S2, M, S, S, 8, 64, crops, W(0), B(0), c->act0.p, 1), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S2, M, 80, 80, 64, 128, c->act0.p, W(1), B(1), c->a1.p, 1), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, M, 40, 40, 128, 128, c->a1.p, W(2), B(2), c->a2.p, 1), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, M, 40, 40, 128, 128, c->a2.p, W(3), B(3), c->a3.p, 1, c->a1.p), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, M, 40, 40, 128, 128, c->a3.p, W(4), B(4), c->a2.p, 1), st));
   // last encodeA layer writes straight into the 256-channel concat buffer (refine_network.py:85)
-  FP_TRY(gl(c, mk(LK_CONV3_S1, M, 40, 40, 128, 128, c->a2.p, W(5), B(5), c->ab0.p, 1, c->a3.p, 256, Np), st));
-  FP_TRY(gl(c, mk(LK_CONV3_S1, N, 40, 40, 256, 256, c->ab0.p, W(6), B(6), c->ab1.p, 1), st));
-  FP_TRY(gl(c, mk(LK_CONV3_S1, N, 40, 40, 256, 256, c->ab1.p, W(7), B(7), c->ab2.p, 1, c->ab0.p), st));
-  FP_TRY(gl(c, mk(LK_CONV3_S1, N, 40, 40, 256, 256, c->ab2.p, W(8), B(8), c->ab1.p, 1), st));
-  FP_TRY(gl(c, mk(LK_CONV3_S1, N, 40, 40, 256, 256, c->ab1.p, W(9), B(9), c->ab0.p, 1, c->ab2.p), st));
-  FP_TRY(gl(c, mk(LK_CONV3_S2, N, 40, 40, 256, 512, c->ab0.p, W(10), B(10), c->c0.p, 1), st));
-  FP_TRY(gl(c, mk(LK_CONV3_S1, N, 20, 20, 512, 512, c->c0.p, W(11), B(11), c->c1.p, 1), st));
-  FP_TRY(gl(c, mk(LK_CONV3_S1, N, 20, 20, 512, 512, c->c1.p, W(12), B(12), c->c2.p, 1, c->c0.p), st));
-  FP_TRY(gl(c, mk(LK_CONV3_S1, N, 20, 20, 512, 512, c->c2.p, W(13), B(13), c->c1.p, 1), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, M, 40, 40, 128, 128, c->a2.p, W(5), B(5), c->ab0.p, 1, c->a3.p, 256, Np), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, N, 40, 40, 256, 256, c->ab0.p, W(6), B(6), c->ab1.p, 1), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, N, 40, 40, 256, 256, c->ab1.p, W(7), B(7), c->ab2.p, 1, c->ab0.p), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, N, 40, 40, 256, 256, c->ab2.p, W(8), B(8), c->ab1.p, 1), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, N, 40, 40, 256, 256, c->ab1.p, W(9), B(9), c->ab0.p, 1, c->ab2.p), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S2, N, 40, 40, 256, 512, c->ab0.p, W(10), B(10), c->c0.p, 1), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, N, 20, 20, 512, 512, c->c0.p, W(11), B(11), c->c1.p, 1), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, N, 20, 20, 512, 512, c->c1.p, W(12), B(12), c->c2.p, 1, c->c0.p), st));
+  FP_TRY(gemm_layer_launch(mk(LK_CONV3_S1, N, 20, 20, 512, 512, c->c2.p, W(13), B(13), c->c1.p, 1), st));
   FP_TRY(gemm_layer_launch(
       mk(LK_CONV3_S1, N, 20, 20, 512, 512, c->c1.p, W(14), B(14), c->tok.p, 1, c->c2.p, 0, 0, net.f("pe")), st));
   return 0;
@@ -247,7 +239,7 @@ static int run_encoder(fp_ctx* c, const Net& net, const __half* crops, int N, cu
 static int run_refine_heads(fp_ctx* c, const Net& net, int N, cudaStream_t st) {
   const int M = N * T;
   // both heads' in_proj as one GEMM: [M,512] x [3072,512]^T
-  FP_TRY(gl(c, mk(LK_LINEAR, 1, 1, M, 512, 3072, c->tok.p, net.h("heads.in_w"), net.f("heads.in_b"), c->qkv.p, 0), st));
+  FP_TRY(gemm_layer_launch(mk(LK_LINEAR, 1, 1, M, 512, 3072, c->tok.p, net.h("heads.in_w"), net.f("heads.in_b"), c->qkv.p, 0), st));
   AttnParams ap;
   ap.qkv = reinterpret_cast<const __half*>(c->qkv.p);
   ap.ld = 3072;
@@ -272,14 +264,14 @@ static int run_refine_heads(fp_ctx* c, const Net& net, int N, cudaStream_t st) {
     const __half* w;
     const float* b;
     w = H("out_w"); b = Fp("out_b");
-    FP_TRY(gl(c, mk(LK_LINEAR, 1, 1, M, 512, 512, att_g, w, b, c->x1pre.p, 0, c->tok.p), st));
+    FP_TRY(gemm_layer_launch(mk(LK_LINEAR, 1, 1, M, 512, 512, att_g, w, b, c->x1pre.p, 0, c->tok.p), st));
     const float* g1 = Fp("ln1_g");
     const float* b1 = Fp("ln1_b");
     FP_TRY(layernorm_launch(reinterpret_cast<const __half*>(c->x1pre.p), reinterpret_cast<__half*>(c->x1.p), g1, b1, M, st));
     w = H("ff1_w"); b = Fp("ff1_b");
-    FP_TRY(gl(c, mk(LK_LINEAR, 1, 1, M, 512, 512, c->x1.p, w, b, c->ff.p, 1), st));
+    FP_TRY(gemm_layer_launch(mk(LK_LINEAR, 1, 1, M, 512, 512, c->x1.p, w, b, c->ff.p, 1), st));
     w = H("ff2_w"); b = Fp("ff2_b");
-    FP_TRY(gl(c, mk(LK_LINEAR, 1, 1, M, 512, 512, c->ff.p, w, b, c->x2pre.p, 0, c->x1.p), st));
+    FP_TRY(gemm_layer_launch(mk(LK_LINEAR, 1, 1, M, 512, 512, c->ff.p, w, b, c->x2pre.p, 0, c->x1.p), st));
     const float* g2 = Fp("ln2_g");
     const float* b2 = Fp("ln2_b");
     const float* fw = Fp("fin_w");
@@ -293,7 +285,7 @@ static int run_refine_heads(fp_ctx* c, const Net& net, int N, cudaStream_t st) {
 // tokens -> per-hypothesis 512-d features (score_network.py:72-74)
 static int run_score_feats(fp_ctx* c, const Net& net, int N, float* feats, cudaStream_t st) {
   const int M = N * T;
-  FP_TRY(gl(c, mk(LK_LINEAR, 1, 1, M, 512, 1536, c->tok.p, net.h("att.in_w"), net.f("att.in_b"), c->qkv.p, 0), st));
+  FP_TRY(gemm_layer_launch(mk(LK_LINEAR, 1, 1, M, 512, 1536, c->tok.p, net.h("att.in_w"), net.f("att.in_b"), c->qkv.p, 0), st));
   AttnParams ap;
   ap.qkv = reinterpret_cast<const __half*>(c->qkv.p);
   ap.ld = 1536;
@@ -568,7 +560,7 @@ int fp_destroy(fp_ctx* c) {
                     &c->a3, &c->ab0, &c->ab1, &c->ab2, &c->c0, &c->c1, &c->c2, &c->tok, &c->qkv, &c->att, &c->x1pre,
                     &c->x1, &c->ff, &c->x2pre, &c->head_out, &c->poses_a, &c->poses_b, &c->feats, &c->tail_qkv,
                     &c->tail_attn, &c->tail_proj, &c->scores, &c->best, &c->lt_buf, &c->lr_buf, &c->feat_buf,
-                    &c->pose_stage, &c->mask_buf, &c->mask_stats, &c->crop_stats, &c->track_pose, &c->fold_v, &c->tail_counter, &c->tok_mean, &c->split_ws};
+                    &c->pose_stage, &c->mask_buf, &c->mask_stats, &c->crop_stats, &c->track_pose, &c->fold_v, &c->tail_counter, &c->tok_mean};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (auto& kv : c->graphs)

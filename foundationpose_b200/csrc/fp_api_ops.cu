@@ -116,17 +116,12 @@ int fp_op_attention(const void* qkv, void* out, int B, int impl, void* stream) {
   return fp::attn_tc_launch(ap, st);
 }
 
-int fp_op_gemm_layer_ws(const fp_gemm_layer_t* l, float* split_ws, size_t split_ws_bytes, void* stream);
-int fp_op_gemm_layer(const fp_gemm_layer_t* l, void* stream) { return fp_op_gemm_layer_ws(l, nullptr, 0, stream); }
-
-int fp_op_gemm_layer_ws(const fp_gemm_layer_t* l, float* split_ws, size_t split_ws_bytes, void* stream) {
+int fp_op_gemm_layer(const fp_gemm_layer_t* l, void* stream) {
   if (!l) {
     fp::set_last_error("fp_op_gemm_layer: null layer");
     return -1;
   }
   fp::GemmLayer L;
-  L.split_ws = split_ws;
-  L.split_ws_bytes = split_ws_bytes;
   L.kind = l->kind;
   L.n_img = l->n_img;
   L.Hin = l->Hin;

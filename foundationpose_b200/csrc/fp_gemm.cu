@@ -30,7 +30,6 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include <algorithm>
 #include <mutex>
 #include <vector>
 
@@ -145,16 +144,6 @@ struct GemmParams {
   int a_sbo;                    // bytes between consecutive 8-row groups of the A operand
   int odim_w;                   // coordinate of the output map that receives the tile's column
   int row_mode;                 // tile row -> pixel: 0 = (n, i, j), 1 = (i, n, j), 2 = (i, j, n)   [fastest last]
-  // ---- split-K (grids far below one wave: track_one's single pose).  A work unit is (virtual tile, K split); the
-  // epilogue writes the fp32 partial accumulators to `split_ws` [split][vt][cta][128 rows][BN] and a finishing kernel
-  // sums the splits in a fixed order and applies bias / residual / ReLU / positional embedding (non-patch tiles only)
-  int split_k;       // 1 = off
-  int kb_per_split;  // k-blocks per split (the last split may be shorter)
-  float* split_ws;
-  const void* res;   // residual / output pointers for the finishing kernel
-  int res_ld;
-  void* out;
-  int out_ld;
 };
 
 constexpr int kBlockM = 128;
@@ -220,7 +209,6 @@ __global__ void __launch_bounds__(kTileThreads, 1)
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int total_vt = ((m_tiles + CG - 1) / CG) * p.n_tiles_n;
   const int vt0 = blockIdx.x / CG, vt_step = gridDim.x / CG;
-  const int total_units = total_vt * (PATCH ? 1 : p.split_k);  // split-K exists for the non-patch tiles only
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -325,17 +313,15 @@ __global__ void __launch_bounds__(kTileThreads, 1)
       }
     } else if (lane == 0) {
       int stage = 0, phase = 0;
-      for (int u = vt0; u < total_units; u += vt_step) {
-        const int vt = u % total_vt, ks = u / total_vt;
+      for (int vt = vt0; vt < total_vt; vt += vt_step) {
         int n_tile, tw, th, tn;
         decode(vt, n_tile, tw, th, tn);
         int base[5] = {0, 0, 0, 0, 0};
         base[p.dim_w] += tw * p.bw;
         if (p.dim_h >= 0) base[p.dim_h] += th * p.bh;
         if (p.dim_n >= 0) base[p.dim_n] += tn * p.bn;
-        const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
-        int tap = kb0 / p.chunks_per_tap, chunk = kb0 % p.chunks_per_tap;
-        for (int kb = kb0; kb < kb1; ++kb) {
+        int tap = 0, chunk = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + kABytes;
@@ -414,15 +400,13 @@ __global__ void __launch_bounds__(kTileThreads, 1)
       constexpr uint32_t idesc = umma_idesc_f16(BN, 128u * CG);
       int stage = 0, phase = 0;
       int it = 0;
-      for (int u = vt0; u < total_units; u += vt_step, ++it) {
-        const int ks = u / total_vt;
-        const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+      for (int vt = vt0; vt < total_vt; vt += vt_step, ++it) {
         const int acc = it & 1;
         const int acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -433,14 +417,14 @@ __global__ void __launch_bounds__(kTileThreads, 1)
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 fp16 = 32 B along K inside the 128 B swizzle atom: +2 in (addr >> 4) units
             if (CG == 2)
-              umma_f16_2sm(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              umma_f16_2sm(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
             else
-              umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           // frees the smem slot (in both CTAs) when these MMAs retire
           if (CG == 2) umma_commit_2sm(&empty[stage]);
           else umma_commit(&empty[stage]);
-          if (kb == kb1 - 1) {
+          if (kb == p.num_kb - 1) {
             if (CG == 2) umma_commit_2sm(&tmem_full[acc]);
             else umma_commit(&tmem_full[acc]);
           }
@@ -476,37 +460,9 @@ __global__ void __launch_bounds__(kTileThreads, 1)
     const uint32_t sw = (uint32_t)(row & 7);
     int it = 0;
     uint32_t slab_ctr = 0;
-    for (int u = vt0; u < total_units; u += vt_step, ++it) {
-      const int vt = PATCH ? u : u % total_vt;
+    for (int vt = vt0; vt < total_vt; vt += vt_step, ++it) {
       const int acc = it & 1;
       const int acc_phase = (it >> 1) & 1;
-      if (!PATCH && p.split_k > 1) {
-        // split-K unit: the raw fp32 partial accumulator goes to the workspace; nothing else happens here
-        const int ks = u / total_vt;
-        mbar_wait(&tmem_full[acc], acc_phase);
-        tc_fence_after();
-        const uint32_t taddr_s = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + grp * 32;
-        float* wrow = p.split_ws + ((((size_t)ks * total_vt + vt) * CG + cta_rank) * 128 + row) * BN + grp * 32;
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 64) {
-          uint32_t v[32];
-          tmem_ld32(taddr_s + c, v);
-          tmem_ld_wait();
-          if (c + 64 >= BN) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0);
-              else mbar_arrive(&tmem_empty[acc]);
-            }
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            reinterpret_cast<float4*>(wrow + c)[k] = make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]),
-                                                                 __uint_as_float(v[4 * k + 2]), __uint_as_float(v[4 * k + 3]));
-        }
-        continue;
-      }
       int n_tile, tw, th, tn;
       decode(vt, n_tile, tw, th, tn);
       const int i = th * p.bh + ii, j = min(tw * p.bw + jj, p.Wo - 1);  // j only indexes the pos.-emb. table
@@ -1138,70 +1094,6 @@ static int ilog2(int v) {
   return l;
 }
 
-// ------------------------------------------------------------------------------------------------
-// split-K finisher: sums the fp32 partial tiles of gemm_tile_kernel's split units in a fixed order and applies the
-// epilogue (bias, residual, ReLU, positional embedding, channel-concat offset) -> fp16 NHWC / [M][ld].
-// One thread per (tile row, 8 channels).  Tile rows are in (n, i, j) order (row_mode 0; LINEAR: bw = 128).
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gemm_split_finish_kernel(const GemmParams p, int BN, int CG, int total_vt) {
-  pdl_trigger();
-  pdl_wait();
-  const int chunks = BN / 8;
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)total_vt * CG * 128 * chunks;
-  if (tid >= total) return;
-  const int q = (int)(tid % chunks);
-  const int row = (int)((tid / chunks) % 128);
-  const int cta = (int)((tid / chunks / 128) % CG);
-  const int vt = (int)(tid / chunks / 128 / CG);
-  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int n_tile = vt % p.n_tiles_n;
-  const int m_tile = (vt / p.n_tiles_n) * CG + cta;
-  if (m_tile >= m_tiles) return;
-  const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
-  const int jj = row & (p.bw - 1), ii = (row >> p.lg_bw) & (p.bh - 1), nn = row >> (p.lg_bw + p.lg_bh);
-  const int j = tw * p.bw + jj, i = th * p.bh + ii, n = tn * p.bn + nn;
-  if (j >= p.Wo || i >= p.Ho || n >= p.n_img) return;
-  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int ks = 0; ks < p.split_k; ++ks) {
-    const float4* w = reinterpret_cast<const float4*>(p.split_ws + ((((size_t)ks * total_vt + vt) * CG + cta) * 128 + row) * BN + q * 8);
-    const float4 w0 = w[0], w1 = w[1];
-    a[0] += w0.x; a[1] += w0.y; a[2] += w0.z; a[3] += w0.w;
-    a[4] += w1.x; a[5] += w1.y; a[6] += w1.z; a[7] += w1.w;
-  }
-  const int ch = n_tile * BN + q * 8;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) a[k] += __ldg(p.bias + ch + k);
-  const size_t pix = ((size_t)n * p.Ho + i) * p.Wo + j;
-  if (p.has_res) {
-    const uint4 r = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.res) + pix * p.res_ld + ch);
-    const __half2* rh = reinterpret_cast<const __half2*>(&r);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 rf = __half22float2(rh[k]);
-      a[2 * k] += rf.x;
-      a[2 * k + 1] += rf.y;
-    }
-  }
-  if (p.relu) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) a[k] = fmaxf(a[k], 0.f);
-  }
-  if (p.post_add) {
-    const float* pa = p.post_add + (size_t)(i * p.Wo + j) * p.Cout + ch;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) a[k] += __ldg(pa + k);
-  }
-  int n_o = n, coff = 0;
-  if (p.out_split > 0) {
-    n_o = n % p.out_split;
-    coff = (n / p.out_split) * p.Cout;
-  }
-  const size_t opix = ((size_t)n_o * p.Ho + i) * p.Wo + j;
-  *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + opix * p.out_ld + coff + ch) =
-      make_uint4(pack_half2(a[0], a[1]), pack_half2(a[2], a[3]), pack_half2(a[4], a[5]), pack_half2(a[6], a[7]));
-}
-
 static int g_cta_group = -1;  // FPOSE_CTA_GROUP=1 falls back to single-CTA MMAs (A/B checks)
 
 template <int BN, int CG, int SLABS, bool PATCH = false>
@@ -1222,20 +1114,12 @@ static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtenso
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int total_vt = ((m_tiles + CG - 1) / CG) * p.n_tiles_n;
   const int slots = g_num_sms / CG;
-  const int units = total_vt * (PATCH ? 1 : p.split_k);
-  const int grid = CG * (units < slots ? units : slots);
-  FP_REQUIRE(p.split_k == 1 || (!PATCH && SLABS == 2), "split-K runs on the non-patch, two-slab tile kernel only");
+  const int grid = CG * (total_vt < slots ? total_vt : slots);
   prof_mark_begin(0, p.alg_flops, stream);
   FP_CUDA_OK(launch_pdl(gemm_tile_kernel<BN, CG, SLABS, PATCH>, dim3(grid), dim3(kTileThreads), Cfg::kSmemBytes, stream, CG, ma, mb,
                         mo, mr, p));
-  note_launches(1);
-  if (p.split_k > 1) {
-    const long long threads = (long long)total_vt * CG * 128 * (BN / 8);
-    FP_CUDA_OK(launch_pdl(gemm_split_finish_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, stream, 1, p, BN, CG,
-                          total_vt));
-    note_launches(1);
-  }
   prof_mark_end(stream);
+  note_launches(1);
   FP_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -1305,41 +1189,6 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
   int BN;
   uint64_t dims[5], str[4];
   uint32_t box[5];
-  // ---- split-K for grids far below one wave (a single tracked pose): decided before the tiling, because it runs on
-  // the plain (non-patch, non-swapped) tile kernel
-  static int g_splitk = -1;
-  if (g_splitk < 0) {
-    const char* e = getenv("FPOSE_SPLITK");
-    g_splitk = (e && e[0] == '0') ? 0 : 1;
-  }
-  int split_k = 1, split_kbps = 0;
-  if (g_splitk && L.split_ws && num_sms() > 0) {
-    int mt = 0, nkb = 0;
-    if (L.kind == LK_LINEAR) {
-      mt = (L.Win + 127) / 128;
-      nkb = L.Cin / 64;
-    } else {
-      const int ho = L.kind == LK_CONV3_S2 ? L.Hin / 2 : L.Hin, wo = L.kind == LK_CONV3_S2 ? L.Win / 2 : L.Win;
-      if (wo % 8 == 0 && ho % 8 == 0) mt = (wo / 8) * (ho / 8) * ((L.n_img + 1) / 2);
-      else if (wo % 4 == 0 && ho % 4 == 0) mt = (wo / 4) * (ho / 4) * ((L.n_img + 7) / 8);
-      nkb = 9 * L.Cin / 64;
-    }
-    const int bn_ = L.Cout % 256 == 0 ? 256 : (L.Cout % 128 == 0 ? 128 : 64);
-    if (g_cta_group < 0) {
-      const char* e = getenv("FPOSE_CTA_GROUP");
-      g_cta_group = (e && e[0] == '1') ? 1 : 2;
-    }
-    const int cg_ = (g_cta_group == 2 && bn_ == 256 && nkb >= 16) ? 2 : 1;
-    const int units = ((mt + cg_ - 1) / cg_) * (L.Cout / bn_), slots = num_sms() / cg_;
-    if (mt > 0 && units * 2 <= slots && nkb >= 8 && L.Cout % 64 == 0) {
-      int sk = std::min(slots / units, nkb / 4);
-      while (sk >= 2 && (size_t)sk * units * cg_ * 128 * bn_ * 4 > L.split_ws_bytes) --sk;
-      if (sk >= 2) {
-        split_kbps = (nkb + sk - 1) / sk;
-        split_k = (nkb + split_kbps - 1) / split_kbps;
-      }
-    }
-  }
 
   switch (L.kind) {
     case LK_LINEAR: {
@@ -1370,8 +1219,8 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
       }
       // measured (profiles/r01e_gemm_probe_patch.log): +6 % on the 40 x 40 / 256-channel layers; the 20 x 20 layers
       // (three column-shifted copies, FPOSE_PATCH=2) are 2 % slower than the per-tap boxes and stay on those
-      patch = split_k == 1 && g_patch && L.Cout % 256 == 0 && (p.bw == 8 || g_patch == 2);
-      swap_patch = split_k == 1 && g_patch && g_swap_ab && L.Cout == 128 && p.bw == 8 && !L.post_add && L.out_split % 4 == 0;
+      patch = g_patch && L.Cout % 256 == 0 && (p.bw == 8 || g_patch == 2);
+      swap_patch = g_patch && g_swap_ab && L.Cout == 128 && p.bw == 8 && !L.post_add && L.out_split % 4 == 0;
       const uint64_t sw_ = (uint64_t)L.Cin * E, sh_ = sw_ * L.Win, sn_ = sh_ * L.Hin;
       if (swap_patch) {
         // gemm_swap_patch_kernel: the N side is 4 images x 8 x 8 pixels out of one (64 ch, 10 w, 4 n, 10 h) patch
@@ -1480,13 +1329,6 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
   p.out_split = L.out_split;
   p.post_add = L.post_add;
   p.relu = L.relu;
-  p.split_k = split_k;
-  p.kb_per_split = split_k > 1 ? split_kbps : p.num_kb;
-  p.split_ws = L.split_ws;
-  p.res = L.res;
-  p.res_ld = L.res_ld;
-  p.out = L.out;
-  p.out_ld = L.out_ld;
   {
     const double k_real = (double)taps * L.Cin;
     p.alg_flops = 2.0 * (double)L.n_img * Ho * Wo * L.Cout * k_real;
@@ -1508,7 +1350,7 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
   // Measured on B200 (profiles/r01_gemm_probe_cta_pair.log): the CTA-pair MMA (cta_group::2, each CTA stages half
   // of the weight tile) is 8-10 % faster on the 256-wide, deep-K convolutions (up to 1.52 PFLOP/s) and slower on
   // the narrow / shallow-K layers, whose bound is the shared-memory port, not the TMA fill.
-  const bool swap_ab = split_k == 1 && g_swap_ab && BN == 128 && L.Cout == 128 && !L.post_add &&
+  const bool swap_ab = g_swap_ab && BN == 128 && L.Cout == 128 && !L.post_add &&
                        (L.kind == LK_CONV3_S1 || L.kind == LK_CONV3_S2);
   static int cg2_min_kb = -1;
   if (cg2_min_kb < 0) {
@@ -1568,13 +1410,6 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
     }
   }
 
-  if (split_k > 1) {
-    FP_REQUIRE(!patch && !swap_patch && !swap_ab && p.row_mode == 0, "split-K planned for a patch / swapped tiling");
-    FP_REQUIRE(p.out_split == 0 || p.out_split % p.bn == 0, "split-K: out_split must be a multiple of the tile's image count");
-    if (BN == 256) return CG == 2 ? launch_bn<256, 2, 2>(ma, mb, mo, mr, p, stream) : launch_bn<256, 1, 2>(ma, mb, mo, mr, p, stream);
-    if (BN == 128) return launch_bn<128, 1, 2>(ma, mb, mo, mr, p, stream);
-    return launch_bn<64, 1, 2>(ma, mb, mo, mr, p, stream);
-  }
   if (swap_patch) return launch_swap_patch(ma, mb, mo, mr, p, stream);
   if (swap_ab) return launch_swap(ma, mb, mo, mr, p, stream);
   if (patch) {

@@ -35,8 +35,6 @@ struct GemmLayer {
                           //         (n / out_split) * Cout   (fuses torch.cat((a, b), 1))
   const float* post_add;  // optional fp32 table [Ho*Wo][Cout] added after the activation (pos. emb.)
   int relu;
-  float* split_ws = nullptr;   // optional fp32 workspace: lets grids far below one wave split the K loop over more SMs
-  size_t split_ws_bytes = 0;
 };
 
 // Enqueue one layer on `stream`.  Returns 0 or a negative error code (fp_last_error() has text).

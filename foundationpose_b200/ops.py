@@ -26,7 +26,7 @@ def _require_cuda(*ts):
 
 
 def gemm_layer(kind, x, w_packed, bias, *, n_img, Hin, Win, Cin, Cout, out=None, out_ld=None, out_split=0,
-               res=None, res_ld=0, post_add=None, relu=False, split_ws=None):
+               res=None, res_ld=0, post_add=None, relu=False):
     """Run one implicit-GEMM layer.  `x`: fp16 activation tensor in the layout the kind expects."""
     _require_cuda(x, w_packed, bias, res, post_add, out)
     assert x.dtype == torch.float16 and w_packed.dtype == torch.float16 and bias.dtype == torch.float32
@@ -41,17 +41,10 @@ def gemm_layer(kind, x, w_packed, bias, *, n_img, Hin, Win, Cin, Cout, out=None,
         out = torch.empty(n_img, Ho, Wo, Cout, dtype=torch.float16, device=x.device)
     L = _lib.GemmLayer(kind, n_img, Hin, Win, Cin, Cout, _ptr(x), _ptr(w_packed), _ptr(bias), _ptr(res),
                        res_ld, _ptr(out), out_ld, out_split, _ptr(post_add), 1 if relu else 0)
-    if split_ws is not None:
-        # fp32 workspace: small grids split the K loop (the product path always passes its context's workspace)
-        assert split_ws.dtype == torch.float32 and split_ws.is_cuda
-        _lib.check(lib.fp_op_gemm_layer_ws(C.byref(L), _ptr(split_ws), C.c_size_t(split_ws.numel() * 4), _stream()), "fp_op_gemm_layer_ws")
-    else:
-        _lib.check(lib.fp_op_gemm_layer(C.byref(L), _stream()), "fp_op_gemm_layer")
+    _lib.check(lib.fp_op_gemm_layer(C.byref(L), _stream()), "fp_op_gemm_layer")
     return out
 
 
-lib.fp_op_gemm_layer_ws.argtypes = [C.POINTER(_lib.GemmLayer), C.c_void_p, C.c_size_t, C.c_void_p]
-lib.fp_op_gemm_layer_ws.restype = C.c_int
 lib.fp_op_attention.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
 lib.fp_op_attention.restype = C.c_int
 

@@ -70,9 +70,6 @@ typedef struct fp_gemm_layer {
 
 /* Runs one layer: out = act(in (*) w + bias [+ res]) [+ post_add]. */
 int fp_op_gemm_layer(const fp_gemm_layer_t* layer, void* stream);
-/* The same with an fp32 device workspace: grids far below one wave (a single tracked pose) then split the K loop over
- * more SMs and finish (sum of the splits, bias, residual, ReLU, positional embedding) in a second kernel. */
-int fp_op_gemm_layer_ws(const fp_gemm_layer_t* layer, float* split_ws, size_t split_ws_bytes, void* stream);
 
 /* softmax(Q K^T / sqrt(128)) V of nn.MultiheadAttention (refine_network.py:56-70, score_network.py:53):
  * qkv fp16 [B*400][1536] (q | k | v, 4 heads of 128 each), out fp16 [B*400][512].

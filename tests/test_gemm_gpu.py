@@ -105,63 +105,3 @@ def test_out_split_concat():
     y = F.conv2d(x.float(), w.half().float(), b, padding=1).relu()
     ref = torch.cat((y[: n // 2], y[n // 2:]), 1).permute(0, 2, 3, 1)
     _cmp(out, ref, "out_split")
-
-
-@pytest.mark.parametrize("case", ["linear_in_proj", "linear_res", "conv512_res_pe", "conv256", "conv128_split_concat", "conv_s2_256_512", "conv_s2_64_128"])
-def test_split_k_small_grids(case):
-    """Single-pose shapes (track_one): with a workspace the K loop is split over more SMs and finished by a second
-    kernel; the result must match torch and the unsplit kernel."""
-    _lib, ops, packing = _mods()
-    ws = torch.empty(16 << 20, dtype=torch.float32, device="cuda")
-    kw = {}
-    if case.startswith("linear"):
-        M, K, Co = 400, 512, (1536 if case == "linear_in_proj" else 512)
-        x = _rand(M, K, seed=31).half()
-        w = _rand(Co, K, scale=K ** -0.5, seed=32)
-        b = _rand(Co, seed=33)
-        res = _rand(M, Co, seed=34).half() if case == "linear_res" else None
-        args = dict(n_img=1, Hin=1, Win=M, Cin=K, Cout=Co, res=res, res_ld=Co, relu=case == "linear_res")
-        run = lambda **k: ops.gemm_layer(_lib.LAYER_LINEAR, x, packing.pack_linear(w.cpu()).cuda(), b, **args, **k).reshape(M, Co)
-        ref = x.float() @ w.half().float().t() + b
-        if res is not None:
-            ref = (ref + res.float()).relu()
-    else:
-        n, H, Ci, Co, stride, use_res, use_pe, split = {"conv512_res_pe": (1, 20, 512, 512, 1, True, True, 0), "conv256": (1, 40, 256, 256, 1, False, False, 0),
-                                                       "conv128_split_concat": (3, 40, 128, 128, 1, True, False, 2), "conv_s2_256_512": (1, 40, 256, 512, 2, False, False, 0),
-                                                       "conv_s2_64_128": (2, 80, 64, 128, 2, False, False, 0)}[case]
-        x = _rand(n, Ci, H, H, seed=35).half()
-        w = _rand(Co, Ci, 3, 3, scale=(9 * Ci) ** -0.5, seed=36)
-        b = _rand(Co, seed=37)
-        Ho = H // stride
-        res = _rand(n, Ho, Ho, Co, seed=38).half() if use_res else None
-        pe = _rand(Ho * Ho, Co, seed=39) if use_pe else None
-        kind = _lib.LAYER_CONV3_S1 if stride == 1 else _lib.LAYER_CONV3_S2
-        args = dict(n_img=n, Hin=H, Win=H, Cin=Ci, Cout=Co, res=res, res_ld=Co, post_add=pe, relu=True)
-        xn = x.permute(0, 2, 3, 1).contiguous()
-        wp = packing.pack_conv3(w.cpu()).cuda()
-        y = F.conv2d(x.float(), w.half().float(), b, stride=stride, padding=1).permute(0, 2, 3, 1)
-        if use_res:
-            y = y + res.float()
-        y = y.relu()
-        if use_pe:
-            y = y + pe.reshape(1, Ho, Ho, Co)
-        if split:
-            # images 0..1 -> channels [0, Co), image 2 -> channels [Co, 2 Co) of image 0 (the A/B concat at one pose)
-            def run(**k):
-                out = torch.zeros(split, Ho, Ho, 2 * Co, dtype=torch.float16, device="cuda")
-                ops.gemm_layer(kind, xn, wp, b, **args, out=out, out_ld=2 * Co, out_split=split, **k)
-                return out
-            ref = torch.zeros(split, Ho, Ho, 2 * Co, device="cuda")
-            ref[:, :, :, :Co] = y[:split]
-            ref[: n - split, :, :, Co:] = y[split:]
-        else:
-            run = lambda **k: ops.gemm_layer(kind, xn, wp, b, **args, **k)
-            ref = y
-    launches0 = _lib.launch_count()
-    got = run(split_ws=ws)
-    assert _lib.launch_count() - launches0 == 2, "expected the split-K pair (tile kernel + finisher) for this grid"
-    _cmp(got, ref, case + " (split-K)")
-    if case != "conv128_split_concat":  # the unsplit 128-channel kernels tile four images: they need out_split % 4 == 0
-        plain = run()
-        _cmp(plain, ref, case + " (plain)")
-        assert (got.float() - plain.float()).abs().max().item() <= 4e-3
