@@ -65,6 +65,7 @@ void set_last_error(const char* fmt, ...);
 // the stream have completed and flushed).  FPOSE_PDL=0 falls back to plain stream order.
 // ----------------------------------------------------------------------------------------------
 bool pdl_enabled();
+void pdl_skip_next();  // the next launch_pdl on this thread omits the programmatic-serialisation attribute
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,

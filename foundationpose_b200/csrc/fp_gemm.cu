@@ -108,7 +108,14 @@ void set_last_error(const char* fmt, ...) {
 }
 const char* get_last_error() { return t_last_error; }
 
+static thread_local int t_pdl_skip = 0;
+void pdl_skip_next() { t_pdl_skip = 1; }
+
 bool pdl_enabled() {
+  if (t_pdl_skip) {  // consumed by exactly one launch_pdl
+    t_pdl_skip = 0;
+    return false;
+  }
   static int on = -1;
   if (on < 0) {
     const char* e = getenv("FPOSE_PDL");

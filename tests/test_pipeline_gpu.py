@@ -183,3 +183,25 @@ def test_predict_honours_per_call_arguments(setup):
     scorer2 = ScorePredictor(engine=e2, state_dict=s["sd_s"])
     sc_b, _ = scorer2.predict(rgb=s["rgb"], depth=s["depth"], K=s["K"], ob_in_cams=poses, mesh_tensors=mt, mesh_diameter=s["d"])
     assert not torch.equal(sc_a, sc_b)
+
+
+def test_decoder_heads_on_two_streams_is_bitwise_serial(setup, monkeypatch):
+    """The two refiner decoder heads run on two streams at small batches (fp_api.cu run_refine_heads, fork / join
+    captured into the graph).  Same kernels on the same data: the poses must be bit-identical to the serial order,
+    eagerly (first call), while capturing (second) and on graph replay (third)."""
+    from foundationpose_b200.engine import Engine
+
+    s = setup
+    outs = {}
+    for fork in ("0", "1000"):
+        monkeypatch.setenv("FPOSE_FORK_MAX_N", fork)  # read by fp_create
+        e = Engine()
+        e.load_network("refine", s["sd_r"])
+        e.set_mesh(s["mt"]["pos"], s["mt"]["normals"], s["mt"]["faces"], s["d"], uv=s["mt"]["uv"], tex=s["mt"]["tex"])
+        e.set_frame(s["rgb"], s["depth"], s["K"], filter_depth=False)
+        outs[fork] = [tuple(t.cpu().clone() for t in e.refine(s["poses"], 3)) for _ in range(3)]
+    for call in range(3):
+        for a, b in zip(outs["0"][call], outs["1000"][call]):
+            assert torch.equal(a, b)
+        for a, b in zip(outs["0"][0], outs["0"][call]):
+            assert torch.equal(a, b)
