@@ -151,7 +151,32 @@ struct GemmParams {
   int a_sbo;                    // bytes between consecutive 8-row groups of the A operand
   int odim_w;                   // coordinate of the output map that receives the tile's column
   int row_mode;                 // tile row -> pixel: 0 = (n, i, j), 1 = (i, n, j), 2 = (i, j, n)   [fastest last]
+  int trace_idx;                // -DFP_GEMM_TRACE builds only: slot of this launch in g_gemm_trace
+  int b_pre;                    // issue the first tile's weight stages BEFORE the dependency wait (weights never change inside a pass)
 };
+
+// -DFP_GEMM_TRACE (tools/gemm_trace.py): CTA 0 of every gemm_tile_kernel launch stamps its phases with the SM clock
+// (slots 0-7) and the global timer (8: entry, 9: exit) so that the fixed cost of a launch at one pose can be read
+// phase by phase.  Compiles to nothing in the product build.
+#ifdef FP_GEMM_TRACE
+__device__ unsigned long long g_gemm_trace[512][10];
+__device__ __forceinline__ unsigned long long trace_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define FP_TRACE(slot)                                                              \
+  do {                                                                              \
+    if (blockIdx.x == 0) g_gemm_trace[p.trace_idx & 511][slot] = (unsigned long long)clock64(); \
+  } while (0)
+#define FP_TRACE_G(slot)                                                  \
+  do {                                                                    \
+    if (blockIdx.x == 0) g_gemm_trace[p.trace_idx & 511][slot] = trace_gtime(); \
+  } while (0)
+#else
+#define FP_TRACE(slot)
+#define FP_TRACE_G(slot)
+#endif
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
@@ -182,7 +207,8 @@ struct TileCfg {
   static constexpr int kBStages = (kBRing / kBBytes) > 8 ? 8 : (kBRing / kBBytes);
   static constexpr int kOperandBytes = PATCH ? (kPatchStages * kPatchSlot + kBStages * kBBytes) : (kStages * kStageBytes);
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-  static constexpr int kSmemBytes = kOperandBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kOperandBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias tile*/;
+  static_assert(kSmemBytes <= 232448, "tile configuration exceeds the 227 KB opt-in shared memory");
 };
 
 template <int BN, int CG, int SLABS, bool PATCH = false>
@@ -208,6 +234,7 @@ __global__ void __launch_bounds__(kTileThreads, 1)
   uint64_t* a_full = bars + 2 * S + 8;      // [SA]  (patch mode)
   uint64_t* a_empty = bars + 2 * S + 8 + SA;  // [SA]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 8 + 2 * SA);
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [BN]: this tile's bias
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -218,6 +245,8 @@ __global__ void __launch_bounds__(kTileThreads, 1)
   const int vt0 = blockIdx.x / CG, vt_step = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
+    FP_TRACE(0);
+    FP_TRACE_G(8);
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     for (int s = 0; s < S; ++s) {
@@ -249,8 +278,26 @@ __global__ void __launch_bounds__(kTileThreads, 1)
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) FP_TRACE(1);
   pdl_trigger();
+  int pre = 0;
+  if (!PATCH && p.b_pre && warp == 0 && lane == 0 && vt0 < total_vt) {
+    // the weight half of the first ring stages does not depend on the previous kernel: fetch it under its tail
+    const int n_tile0 = vt0 % p.n_tiles_n;
+    pre = min(S, p.num_kb);
+    for (int kb = 0; kb < pre; ++kb) {
+      uint8_t* sb = smem + kb * Cfg::kStageBytes + kABytes;
+      if (CG == 2) {
+        if (cta_rank == 0) mbar_expect_tx(&full[kb], 2 * Cfg::kStageBytes);
+        tma_load_2d_2sm(&map_b, &full[kb], sb, kb * kBlockK, n_tile0 * BN + cta_rank * (BN / 2));
+      } else {
+        mbar_expect_tx(&full[kb], Cfg::kStageBytes);
+        tma_load_2d(&map_b, &full[kb], sb, kb * kBlockK, n_tile0 * BN);
+      }
+    }
+  }
   pdl_wait();  // everything above overlapped the previous kernel's tail; activations are touched only from here on
+  if (threadIdx.x == 0) FP_TRACE(2);
 
   // decode this CTA's tile of virtual tile vt; an odd leftover M tile is parked out of range (TMA zero-fills
   // its loads and clips its stores)
@@ -334,15 +381,16 @@ __global__ void __launch_bounds__(kTileThreads, 1)
           uint8_t* sb = sa + kABytes;
           const int c0 = base[0] + p.tap_off[tap][0] + chunk * kBlockK, c1 = base[1] + p.tap_off[tap][1],
                     c2 = base[2] + p.tap_off[tap][2], c3 = base[3] + p.tap_off[tap][3], c4 = base[4] + p.tap_off[tap][4];
+          const bool b_done = (vt == vt0 && kb < pre);  // armed, and its weights requested, before the dependency wait
           if (CG == 2) {
             // both CTAs' bytes land on the leader's barrier; the leader alone arms it (for both)
-            if (cta_rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+            if (cta_rank == 0 && !b_done) mbar_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
             tma_load_5d_2sm(&map_a, &full[stage], sa, c0, c1, c2, c3, c4);
-            tma_load_2d_2sm(&map_b, &full[stage], sb, kb * kBlockK, n_tile * BN + cta_rank * (BN / 2));
+            if (!b_done) tma_load_2d_2sm(&map_b, &full[stage], sb, kb * kBlockK, n_tile * BN + cta_rank * (BN / 2));
           } else {
-            mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+            if (!b_done) mbar_expect_tx(&full[stage], Cfg::kStageBytes);
             tma_load_5d(&map_a, &full[stage], sa, c0, c1, c2, c3, c4);
-            tma_load_2d(&map_b, &full[stage], sb, kb * kBlockK, n_tile * BN);
+            if (!b_done) tma_load_2d(&map_b, &full[stage], sb, kb * kBlockK, n_tile * BN);
           }
           if (++chunk == p.chunks_per_tap) {
             chunk = 0;
@@ -375,6 +423,7 @@ __global__ void __launch_bounds__(kTileThreads, 1)
               for (int t = 0; t < tps; ++t) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
+                if (it == 0 && cs == 0 && q == 0 && t == 0) FP_TRACE(3);
                 // the tap's rows start tap_aoff bytes into the segment; 8-row groups are a_sbo bytes apart
                 const uint64_t da = umma_desc_sw128_sbo(seg + (uint32_t)p.tap_aoff[q * tps + t], (uint32_t)p.a_sbo);
                 const uint64_t db = umma_desc_sw128(smem_u32(b_ring + stage * Cfg::kBBytes));
@@ -402,6 +451,7 @@ __global__ void __launch_bounds__(kTileThreads, 1)
           if (CG == 2) umma_commit_2sm(&tmem_full[acc]);
           else umma_commit(&tmem_full[acc]);
         }
+        FP_TRACE(4);
       }
     } else if (lane == 0 && cta_rank == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(BN, 128u * CG);
@@ -416,6 +466,7 @@ __global__ void __launch_bounds__(kTileThreads, 1)
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
+          if (it == 0 && kb == 0) FP_TRACE(3);
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + kABytes;
           const uint64_t da = umma_desc_sw128(sa);
@@ -441,6 +492,7 @@ __global__ void __launch_bounds__(kTileThreads, 1)
           }
         }
       }
+      FP_TRACE(4);
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9)
@@ -479,8 +531,21 @@ __global__ void __launch_bounds__(kTileThreads, 1)
         n_o0 = n0 % p.out_split;
         coff = (n0 / p.out_split) * p.Cout;
       }
-      const float* pap = p.post_add ? p.post_add + (size_t)(i * p.Wo + j) * p.Cout + n_tile * BN : nullptr;
-      const float* bp = p.bias + n_tile * BN;
+      // Everything the epilogue reads from global memory is fetched NOW, while the tile's MMAs still run: at one
+      // tile per CTA (small batches) the epilogue is exposed and an L2 round trip per 64-channel slab was 2/3 of it
+      // (tools/gemm_trace.py: 4.6 -> 1.x us per launch).  The bias goes to shared memory (every row uses the same
+      // values; the previous tile's readers are behind that tile's last bar.sync), the positional embedding of the
+      // first slab to registers.
+      const float* pap = p.post_add ? p.post_add + (size_t)(i * p.Wo + j) * p.Cout + n_tile * BN + grp * 32 : nullptr;
+      {
+        const int et = (int)threadIdx.x - 64;
+        if (et < BN) bias_s[et] = __ldg(p.bias + n_tile * BN + et);
+      }
+      float4 pe[8];
+      if (pap) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) pe[k] = __ldg(reinterpret_cast<const float4*>(pap) + k);
+      }
       // output / residual box coordinates (dim 0 = channel is added per slab)
       int oc[5] = {0, 0, 0, 0, 0}, rc[5] = {0, 0, 0, 0, 0};
       oc[p.odim_w] = rc[p.odim_w] = tw * p.bw;
@@ -506,6 +571,7 @@ __global__ void __launch_bounds__(kTileThreads, 1)
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (leader && it == 0) FP_TRACE(5);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + grp * 32;
 #pragma unroll 1
       for (int c = 0; c < BN; c += 64, ++slab_ctr) {
@@ -522,6 +588,11 @@ __global__ void __launch_bounds__(kTileThreads, 1)
             mbar_expect_tx(&res_full[buf], kSlabBytes);
             tma_load_5d(&map_res, &res_full[buf], slab, n_tile * BN + c, rc[1], rc[2], rc[3], rc[4]);
           }
+        }
+        float4 pe_next[8];
+        if (pap && c + 64 < BN) {  // the next slab's positional embedding travels under this slab's work
+#pragma unroll
+          for (int k = 0; k < 8; ++k) pe_next[k] = __ldg(reinterpret_cast<const float4*>(pap + c + 64) + k);
         }
         uint32_t v[32];
         tmem_ld32(taddr + c, v);
@@ -542,8 +613,8 @@ __global__ void __launch_bounds__(kTileThreads, 1)
           uint4* cell = reinterpret_cast<uint4*>(slab + row_off + (((uint32_t)q ^ sw) << 4));
           float a[8];
           {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp + c + q * 8));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bp + c + q * 8) + 1);
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c + q * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c + q * 8 + 4);
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int k = 0; k < 8; ++k) a[k] = __uint_as_float(v[q4 * 8 + k]) + bb[k];
@@ -563,12 +634,15 @@ __global__ void __launch_bounds__(kTileThreads, 1)
             for (int k = 0; k < 8; ++k) a[k] = fmaxf(a[k], 0.f);
           }
           if (pap) {
-            const float4 p0 = __ldg(reinterpret_cast<const float4*>(pap + c + q * 8));
-            const float4 p1 = __ldg(reinterpret_cast<const float4*>(pap + c + q * 8) + 1);
+            const float4 p0 = pe[2 * q4], p1 = pe[2 * q4 + 1];
             a[0] += p0.x; a[1] += p0.y; a[2] += p0.z; a[3] += p0.w;
             a[4] += p1.x; a[5] += p1.y; a[6] += p1.z; a[7] += p1.w;
           }
           *cell = make_uint4(pack_half2(a[0], a[1]), pack_half2(a[2], a[3]), pack_half2(a[4], a[5]), pack_half2(a[6], a[7]));
+        }
+        if (pap && c + 64 < BN) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) pe[k] = pe_next[k];
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -578,7 +652,11 @@ __global__ void __launch_bounds__(kTileThreads, 1)
         }
       }
     }
-    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // smem must outlive the stores
+    if (leader) {
+      FP_TRACE(6);
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // smem must outlive the stores
+      FP_TRACE(7);
+    }
   }
 
   tc_fence_before();
@@ -589,6 +667,7 @@ __global__ void __launch_bounds__(kTileThreads, 1)
     if (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
     else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+  if (threadIdx.x == 0) FP_TRACE_G(9);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1103,6 +1182,33 @@ static int ilog2(int v) {
 
 static int g_cta_group = -1;  // FPOSE_CTA_GROUP=1 falls back to single-CTA MMAs (A/B checks)
 
+#ifdef FP_GEMM_TRACE
+struct TraceInfo {
+  int bn, cg, slabs, patch, grid, total_vt, num_kb, m_tiles, cout, has_res;
+};
+static TraceInfo g_trace_info[512];
+static int g_trace_next = 0;
+static int trace_note(int bn, int cg, int slabs, int patch, int grid, int total_vt, const GemmParams& p) {
+  const int i = g_trace_next++ & 511;
+  g_trace_info[i] = {bn, cg, slabs, patch, grid, total_vt, p.num_kb, p.tiles_w * p.tiles_h * p.tiles_n, p.Cout, p.has_res};
+  return i;
+}
+}  // namespace fp
+extern "C" int fp_op_gemm_trace_reset() {
+  fp::g_trace_next = 0;
+  return 0;
+}
+// out: [n][10] stamps, info: [n][10] ints; returns the number of launches noted since the reset
+extern "C" int fp_op_gemm_trace_read(unsigned long long* out, int* info, int max_n) {
+  const int n = fp::g_trace_next < max_n ? fp::g_trace_next : max_n;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, fp::g_gemm_trace, (size_t)n * 10 * sizeof(unsigned long long));
+  memcpy(info, fp::g_trace_info, (size_t)n * sizeof(fp::TraceInfo));
+  return n;
+}
+namespace fp {
+#endif
+
 template <int BN, int CG, int SLABS, bool PATCH = false>
 static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mr,
                      const GemmParams& p, cudaStream_t stream) {
@@ -1123,8 +1229,15 @@ static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtenso
   const int slots = g_num_sms / CG;
   const int grid = CG * (total_vt < slots ? total_vt : slots);
   prof_mark_begin(0, p.alg_flops, stream);
+#ifdef FP_GEMM_TRACE
+  GemmParams pt = p;
+  pt.trace_idx = trace_note(BN, CG, SLABS, PATCH ? 1 : 0, grid, total_vt, p);
+  FP_CUDA_OK(launch_pdl(gemm_tile_kernel<BN, CG, SLABS, PATCH>, dim3(grid), dim3(kTileThreads), Cfg::kSmemBytes, stream, CG, ma, mb,
+                        mo, mr, pt));
+#else
   FP_CUDA_OK(launch_pdl(gemm_tile_kernel<BN, CG, SLABS, PATCH>, dim3(grid), dim3(kTileThreads), Cfg::kSmemBytes, stream, CG, ma, mb,
                         mo, mr, p));
+#endif
   prof_mark_end(stream);
   note_launches(1);
   FP_CUDA_OK(cudaGetLastError());
@@ -1196,6 +1309,21 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
   int BN;
   uint64_t dims[5], str[4];
   uint32_t box[5];
+  // Grids far below one wave (a single tracked pose, up to ~8 hypotheses): per-CTA time is the K loop at the MMA
+  // rate of the tile (tools/gemm_trace.py: 274 ns per k-block for 256 x 256), so HALVING the tile width doubles the
+  // CTAs and halves the layer's latency; the extra operand traffic is irrelevant with most SMs idle.  Decided per
+  // convolution before its tiling, because the narrow tiles run on the plain (non-patch) kernel.
+  static int g_narrow = -1;
+  if (g_narrow < 0) {
+    const char* e = getenv("FPOSE_NARROW");
+    g_narrow = (e && e[0] == '0') ? 0 : 1;
+  }
+  bool narrow = false;
+  auto is_narrow = [&](int ho, int wo, int bw, int bh, int bn) {
+    if (!g_narrow || L.Cout % 256 != 0 || 9 * L.Cin / 64 < 16) return false;
+    const int mt = (wo / bw) * (ho / bh) * ((L.n_img + bn - 1) / bn);
+    return ((mt + 1) / 2) * (L.Cout / 256) * 4 <= num_sms();  // <= half of the CTA-pair slots
+  };
 
   switch (L.kind) {
     case LK_LINEAR: {
@@ -1226,7 +1354,8 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
       }
       // measured (profiles/r01e_gemm_probe_patch.log): +6 % on the 40 x 40 / 256-channel layers; the 20 x 20 layers
       // (three column-shifted copies, FPOSE_PATCH=2) are 2 % slower than the per-tap boxes and stay on those
-      patch = g_patch && L.Cout % 256 == 0 && (p.bw == 8 || g_patch == 2);
+      narrow = is_narrow(Ho, Wo, p.bw, p.bh, p.bn);
+      patch = !narrow && g_patch && L.Cout % 256 == 0 && (p.bw == 8 || g_patch == 2);
       swap_patch = g_patch && g_swap_ab && L.Cout == 128 && p.bw == 8 && !L.post_add && L.out_split % 4 == 0;
       const uint64_t sw_ = (uint64_t)L.Cin * E, sh_ = sw_ * L.Win, sn_ = sh_ * L.Hin;
       if (swap_patch) {
@@ -1298,6 +1427,7 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
       if (Wo % 8 == 0 && Ho % 8 == 0) { p.bw = 8; p.bh = 8; p.bn = 2; }
       else if (Wo % 4 == 0 && Ho % 4 == 0) { p.bw = 4; p.bh = 4; p.bn = 8; }
       else FP_REQUIRE(false, "CONV3_S2: unsupported output size %dx%d", Ho, Wo);
+      narrow = is_narrow(Ho, Wo, p.bw, p.bh, p.bn);
       p.dim_w = 1; p.dim_h = 3; p.dim_n = 4;
       // view (N, H, W, C) as (N, H/2, 2, W/2, [2, C]): every (tap, chunk) is a dense box
       dims[0] = 2 * L.Cin; dims[1] = Wo; dims[2] = 2; dims[3] = Ho; dims[4] = L.n_img;
@@ -1324,7 +1454,8 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
   p.lg_bw = ilog2(p.bw);
   p.lg_bh = ilog2(p.bh);
 
-  if (L.Cout % 256 == 0) BN = 256;
+  if (narrow) BN = 128;
+  else if (L.Cout % 256 == 0) BN = 256;
   else if (L.Cout % 128 == 0) BN = 128;
   else if (L.Cout % 64 == 0) BN = 64;
   else FP_REQUIRE(false, "Cout=%d must be a multiple of 64", L.Cout);
@@ -1364,7 +1495,7 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
     const char* e = getenv("FPOSE_CG2_MIN_KB");
     cg2_min_kb = e ? atoi(e) : 16;
   }
-  const int CG = (g_cta_group == 2 && BN == 256 && p.num_kb >= cg2_min_kb) ? 2 : 1;
+  const int CG = (g_cta_group == 2 && (BN == 256 || narrow) && p.num_kb >= cg2_min_kb) ? 2 : 1;
   uint32_t wb[2] = {64, (uint32_t)(BN / CG)};
   rc = encode_map(&mb, L.w, 2, wd, ws, wb);
   if (rc) return rc;
@@ -1417,8 +1548,18 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
     }
   }
 
+  static int g_bpre = -1;
+  if (g_bpre < 0) {
+    const char* e = getenv("FPOSE_GEMM_BPRE");
+    g_bpre = e ? atoi(e) : 0;
+  }
+  p.b_pre = g_bpre;
   if (swap_patch) return launch_swap_patch(ma, mb, mo, mr, p, stream);
   if (swap_ab) return launch_swap(ma, mb, mo, mr, p, stream);
+  if (narrow) {
+    if (CG == 2) return L.res ? launch_bn<128, 2, 4>(ma, mb, mo, mr, p, stream) : launch_bn<128, 2, 2>(ma, mb, mo, mr, p, stream);
+    return launch_bn<128, 1, 2>(ma, mb, mo, mr, p, stream);
+  }
   if (patch) {
     FP_REQUIRE(BN == 256, "patch mode is built for the 256-wide tile only");
     if (L.res) return CG == 2 ? launch_bn<256, 2, 4, true>(ma, mb, mo, mr, p, stream) : launch_bn<256, 1, 4, true>(ma, mb, mo, mr, p, stream);
