@@ -117,14 +117,17 @@ int layernorm_launch(const __half* x, __half* y, const float* gamma, const float
   return 0;
 }
 
-// Token reduction of one sequence (400 tokens x 512 channels) by a CLUSTER of four CTAs, 100 tokens each:
+// Token reduction of one sequence (400 tokens x 512 channels), always as FOUR token ranges of 100:
 //   kLN = true : norm2 -> token mean -> Linear(512, out_dim <= 8)   (refiner heads, refine_network.py:89-90; the mean
 //                commutes with the final linear layer)
 //   kLN = false: token mean of the attention output -> [512] fp32   (scorer, score_network.py:72-74; the out_proj that
 //                follows is a [N,512] x [512,512] product done by rowwise_linear_kernel for all hypotheses at once)
-// One CTA per sequence left 32 hypotheses per GPU (8-GPU shards) on 32 of 148 SMs and a single tracked pose on one.
-// The four partial sums live in the CTAs' shared memory; rank 0 reads its peers' over distributed shared memory and
-// adds them in rank order, every partial being built in a fixed order too: the result does not depend on N or the shard.
+// The launch decides who owns the ranges: a CLUSTER of four CTAs (one range each) at small batches — one CTA per
+// sequence left 32 hypotheses per GPU (8-GPU shards) on 32 of 148 SMs and a single tracked pose on one — or ONE CTA
+// walking the four ranges at large batches, where 4x the CTAs only add fixed cost (252 hypotheses: 56 -> 44 us).
+// Either way each range's partial sum is built in the same fixed order and the four partials are added in range
+// order (rank 0 reads its peers' over distributed shared memory): the result is bit-identical for both launches and
+// does not depend on N or the shard.
 constexpr int kHeadWarps = 8;
 constexpr int kTokSplit = 4;
 template <bool kLN>
@@ -135,68 +138,79 @@ __global__ void __launch_bounds__(kHeadWarps * 32) token_reduce_kernel(const __h
                                                                        const float* __restrict__ bias, float* __restrict__ out,
                                                                        int T, int out_dim, float eps) {
   __shared__ float acc[kHeadWarps][512];
-  __shared__ float part[512];
+  __shared__ float part[kTokSplit][512];  // [range owned by this CTA][channel]
   __shared__ float meanv[512];
-  const int b = blockIdx.x / kTokSplit, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned csize = cluster_nctarank();  // 4 (one range per CTA) or 1 (this CTA walks all four)
   const unsigned rank = cluster_ctarank();
-  float a[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) a[i] = 0.f;
+  const int per_cta = kTokSplit / (int)csize;  // launches use a cluster of 4 or of 1
+  const int b = blockIdx.x / (int)csize, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   LnAffine af;
   if (kLN) ln_load_affine(af, gamma, beta, lane);
   pdl_trigger();
   pdl_wait();
   const int per = (T + kTokSplit - 1) / kTokSplit;
-  const int t_end = min(T, (int)(rank + 1) * per);
   const __half* xb = x + (size_t)b * T * 512;
-  int t = (int)rank * per + warp;
-  // two rows in flight per warp: the second row's loads overlap the first row's reductions
-  for (; t + kHeadWarps < t_end; t += 2 * kHeadWarps) {
-    float v0[16], v1[16];
-    load_row16(xb + (size_t)t * 512, lane, v0);
-    load_row16(xb + (size_t)(t + kHeadWarps) * 512, lane, v1);
-    if (kLN) {
-      ln_row16(v0, af, eps);
-      ln_row16(v1, af, eps);
+  for (int ql = 0; ql < per_cta; ++ql) {
+    const int q = (int)rank * per_cta + ql;
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = 0.f;
+    const int t_end = min(T, (q + 1) * per);
+    int t = q * per + warp;
+    // two rows in flight per warp: the second row's loads overlap the first row's reductions
+    for (; t + kHeadWarps < t_end; t += 2 * kHeadWarps) {
+      float v0[16], v1[16];
+      load_row16(xb + (size_t)t * 512, lane, v0);
+      load_row16(xb + (size_t)(t + kHeadWarps) * 512, lane, v1);
+      if (kLN) {
+        ln_row16(v0, af, eps);
+        ln_row16(v1, af, eps);
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] += v0[i];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] += v1[i];
     }
+    if (t < t_end) {
+      float v[16];
+      load_row16(xb + (size_t)t * 512, lane, v);
+      if (kLN) ln_row16(v, af, eps);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) a[i] += v0[i];
+      for (int i = 0; i < 16; ++i) a[i] += v[i];
+    }
+    if (ql > 0) __syncthreads();  // the previous range's cross-warp sums have been read
 #pragma unroll
-    for (int i = 0; i < 16; ++i) a[i] += v1[i];
-  }
-  if (t < t_end) {
-    float v[16];
-    load_row16(xb + (size_t)t * 512, lane, v);
-    if (kLN) ln_row16(v, af, eps);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) a[i] += v[i];
-  }
-#pragma unroll
-  for (int i = 0; i < 16; ++i) acc[warp][lane * 16 + i] = a[i];
-  __syncthreads();
-  for (int c = threadIdx.x; c < 512; c += kHeadWarps * 32) {
-    float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < kHeadWarps; ++k) s += acc[k][c];
-    part[c] = s;
-  }
-  cluster_sync_all();  // every CTA's `part` is complete and visible cluster-wide
-  if (rank == 0) {
-    const uint32_t mine = smem_u32(part);
+    for (int i = 0; i < 16; ++i) acc[warp][lane * 16 + i] = a[i];
+    __syncthreads();
     for (int c = threadIdx.x; c < 512; c += kHeadWarps * 32) {
       float s = 0.f;
 #pragma unroll
-      for (unsigned r = 0; r < (unsigned)kTokSplit; ++r) {
-        uint32_t remote;
+      for (int k = 0; k < kHeadWarps; ++k) s += acc[k][c];
+      part[ql][c] = s;
+    }
+  }
+  if (csize > 1) cluster_sync_all();  // every CTA's `part` is complete and visible cluster-wide
+  else __syncthreads();
+  if (rank == 0) {
+    const uint32_t mine = smem_u32(&part[0][0]);
+    for (int c = threadIdx.x; c < 512; c += kHeadWarps * 32) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < kTokSplit; ++q) {
         float v;
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(mine + 4u * (uint32_t)c), "r"(r));
-        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote));
+        if (csize == 1) {
+          v = part[q][c];
+        } else {
+          uint32_t remote;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(mine + 4u * (uint32_t)c), "r"((unsigned)q));
+          asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote));
+        }
         s += v;
       }
       meanv[c] = s / (float)T;
     }
   }
-  cluster_sync_all();  // peers keep their shared memory alive until rank 0 has read it
+  if (csize > 1) cluster_sync_all();  // peers keep their shared memory alive until rank 0 has read it
   if (rank != 0) return;
   __syncthreads();
   if (kLN) {
@@ -211,11 +225,15 @@ __global__ void __launch_bounds__(kHeadWarps * 32) token_reduce_kernel(const __h
   }
 }
 
+// cluster of four below this many sequences (2 x 148 SMs' worth of CTAs), one CTA per sequence above
+static inline int token_split_for(int B) { return B <= 74 ? kTokSplit : 1; }
+
 int head_final_launch(const __half* x, const float* gamma, const float* beta, const float* w, const float* bias,
                       float* out, int B, int T, int out_dim, cudaStream_t stream) {
   FP_REQUIRE(out_dim <= kHeadWarps, "head_final: out_dim %d > %d", out_dim, kHeadWarps);
   if (B == 0) return 0;
-  FP_CUDA_OK(launch_pdl(token_reduce_kernel<true>, dim3(B * kTokSplit), dim3(kHeadWarps * 32), 0, stream, kTokSplit, x, gamma, beta,
+  const int split = token_split_for(B);
+  FP_CUDA_OK(launch_pdl(token_reduce_kernel<true>, dim3(B * split), dim3(kHeadWarps * 32), 0, stream, split, x, gamma, beta,
                         w, bias, out, T, out_dim, 1e-5f));
   note_launches(1);
   FP_CUDA_OK(cudaGetLastError());
@@ -228,7 +246,8 @@ int rowwise_linear_launch(const float* x, const float* w, const float* bias, flo
 int token_mean_proj_launch(const __half* x, const float* w_f32, const float* bias, float* mean_ws, float* out, int B, int T,
                            cudaStream_t stream) {
   if (B == 0) return 0;
-  FP_CUDA_OK(launch_pdl(token_reduce_kernel<false>, dim3(B * kTokSplit), dim3(kHeadWarps * 32), 0, stream, kTokSplit, x,
+  const int split = token_split_for(B);
+  FP_CUDA_OK(launch_pdl(token_reduce_kernel<false>, dim3(B * split), dim3(kHeadWarps * 32), 0, stream, split, x,
                         (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, mean_ws, T, 0,
                         0.f));
   note_launches(1);

@@ -166,6 +166,11 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 // ---- 2-CTA (cta_group::2) variants: the CTA pair of a cluster drives one M=256 MMA; TMA bytes of both
 // CTAs are accounted on the leader's (rank 0) mbarrier, MMA completion is multicast to both.
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

@@ -67,6 +67,24 @@ def test_refine_net_outputs(engine):
     np.testing.assert_allclose(rot.cpu().numpy(), ref["rot"].numpy(), atol=5e-3, rtol=0)
 
 
+def test_token_reduction_is_bitwise_the_same_as_cluster_or_single_cta(engine):
+    """fp_attn.cu token_reduce_kernel: a cluster of four CTAs per hypothesis up to 74 hypotheses, one CTA walking the
+    same four token ranges above.  Same partial sums, same order: the read-outs of the first 72 hypotheses must not
+    change by a bit when 8 more are appended (refiner heads and scorer features)."""
+    from foundationpose_b200.engine import crops_from_planar
+
+    e, _, _ = engine
+    A, B = _crops(80, 21)
+    big = crops_from_planar(A.cuda(), B.cuda())
+    small = crops_from_planar(A[:72].cuda(), B[:72].cuda())
+    t80, r80 = e.op_refine_net(big, 80)
+    t72, r72 = e.op_refine_net(small, 72)
+    assert torch.equal(t80[:72], t72) and torch.equal(r80[:72], r72)
+    f80 = e.op_score_feats(big, 80)
+    f72 = e.op_score_feats(small, 72)
+    assert torch.equal(f80[:72], f72)
+
+
 def test_refine_net_golden(engine):
     """Same crops as the reference-generated golden fixture (tools/make_golden.py)."""
     import os
