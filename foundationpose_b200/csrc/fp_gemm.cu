@@ -152,7 +152,6 @@ struct GemmParams {
   int odim_w;                   // coordinate of the output map that receives the tile's column
   int row_mode;                 // tile row -> pixel: 0 = (n, i, j), 1 = (i, n, j), 2 = (i, j, n)   [fastest last]
   int trace_idx;                // -DFP_GEMM_TRACE builds only: slot of this launch in g_gemm_trace
-  int b_pre;                    // issue the first tile's weight stages BEFORE the dependency wait (weights never change inside a pass)
 };
 
 // -DFP_GEMM_TRACE (tools/gemm_trace.py): CTA 0 of every gemm_tile_kernel launch stamps its phases with the SM clock
@@ -280,22 +279,6 @@ __global__ void __launch_bounds__(kTileThreads, 1)
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) FP_TRACE(1);
   pdl_trigger();
-  int pre = 0;
-  if (!PATCH && p.b_pre && warp == 0 && lane == 0 && vt0 < total_vt) {
-    // the weight half of the first ring stages does not depend on the previous kernel: fetch it under its tail
-    const int n_tile0 = vt0 % p.n_tiles_n;
-    pre = min(S, p.num_kb);
-    for (int kb = 0; kb < pre; ++kb) {
-      uint8_t* sb = smem + kb * Cfg::kStageBytes + kABytes;
-      if (CG == 2) {
-        if (cta_rank == 0) mbar_expect_tx(&full[kb], 2 * Cfg::kStageBytes);
-        tma_load_2d_2sm(&map_b, &full[kb], sb, kb * kBlockK, n_tile0 * BN + cta_rank * (BN / 2));
-      } else {
-        mbar_expect_tx(&full[kb], Cfg::kStageBytes);
-        tma_load_2d(&map_b, &full[kb], sb, kb * kBlockK, n_tile0 * BN);
-      }
-    }
-  }
   pdl_wait();  // everything above overlapped the previous kernel's tail; activations are touched only from here on
   if (threadIdx.x == 0) FP_TRACE(2);
 
@@ -381,16 +364,15 @@ __global__ void __launch_bounds__(kTileThreads, 1)
           uint8_t* sb = sa + kABytes;
           const int c0 = base[0] + p.tap_off[tap][0] + chunk * kBlockK, c1 = base[1] + p.tap_off[tap][1],
                     c2 = base[2] + p.tap_off[tap][2], c3 = base[3] + p.tap_off[tap][3], c4 = base[4] + p.tap_off[tap][4];
-          const bool b_done = (vt == vt0 && kb < pre);  // armed, and its weights requested, before the dependency wait
           if (CG == 2) {
             // both CTAs' bytes land on the leader's barrier; the leader alone arms it (for both)
-            if (cta_rank == 0 && !b_done) mbar_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+            if (cta_rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
             tma_load_5d_2sm(&map_a, &full[stage], sa, c0, c1, c2, c3, c4);
-            if (!b_done) tma_load_2d_2sm(&map_b, &full[stage], sb, kb * kBlockK, n_tile * BN + cta_rank * (BN / 2));
+            tma_load_2d_2sm(&map_b, &full[stage], sb, kb * kBlockK, n_tile * BN + cta_rank * (BN / 2));
           } else {
-            if (!b_done) mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+            mbar_expect_tx(&full[stage], Cfg::kStageBytes);
             tma_load_5d(&map_a, &full[stage], sa, c0, c1, c2, c3, c4);
-            if (!b_done) tma_load_2d(&map_b, &full[stage], sb, kb * kBlockK, n_tile * BN);
+            tma_load_2d(&map_b, &full[stage], sb, kb * kBlockK, n_tile * BN);
           }
           if (++chunk == p.chunks_per_tap) {
             chunk = 0;
@@ -1548,12 +1530,6 @@ int gemm_layer_launch(const GemmLayer& L, cudaStream_t stream) {
     }
   }
 
-  static int g_bpre = -1;
-  if (g_bpre < 0) {
-    const char* e = getenv("FPOSE_GEMM_BPRE");
-    g_bpre = e ? atoi(e) : 0;
-  }
-  p.b_pre = g_bpre;
   if (swap_patch) return launch_swap_patch(ma, mb, mo, mr, p, stream);
   if (swap_ab) return launch_swap(ma, mb, mo, mr, p, stream);
   if (narrow) {
