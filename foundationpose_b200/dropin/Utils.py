@@ -10,8 +10,12 @@ Only the surface the drivers touch is provided (the reference's Utils.py is 1000
                  (:483-507), make_mesh_tensors (:104-130), erode_depth / bilateral_filter_depth (:304-395, on the GPU)
   drawing        project_3d_to_2d (:667-672), draw_xyz_axis (:675-710), draw_posed_3d_box (:713-750)
   clouds         toOpen3dCloud (:280-289) — needs open3d, which only debug >= 2 / 3 paths call
+  dataset runs   argparse, NestDict (:60-61), make_yaml_dumpable (:996-1020), symmetry_tfs_from_info (:806-834),
+                 euler_matrix (the `transformations` package's static-xyz convention), wp (warp stand-in: force_load)
+                 — what run_linemod.py / run_ycb_video.py and the BOP readers use unqualified
 trimesh and imageio are the real packages when installed, else the minimal stand-ins under _fallback/.
 """
+import argparse  # noqa: F401
 import copy  # noqa: F401
 import glob  # noqa: F401
 import importlib
@@ -23,6 +27,7 @@ import os
 import sys
 import time  # noqa: F401
 import uuid  # noqa: F401
+from collections import OrderedDict, defaultdict  # noqa: F401
 
 import cv2
 import numpy as np
@@ -59,6 +64,23 @@ from foundationpose_b200 import hypotheses as _hyp  # noqa: E402
 from foundationpose_b200 import meshprep as _meshprep  # noqa: E402
 from foundationpose_b200.estimater import make_mesh_tensors  # noqa: E402,F401
 
+
+
+class _WarpStandIn:
+    """`wp.force_load(device='cuda')` (run_linemod.py:89, run_ycb_video.py:84) pre-compiles the reference's Warp depth
+    filters; here they are CUDA kernels inside libfpose.so, so there is nothing to load."""
+
+    @staticmethod
+    def init():
+        return None
+
+    @staticmethod
+    def force_load(device=None):
+        return None
+
+
+wp = _WarpStandIn()
+
 code_dir = _HERE
 BAD_DEPTH = 99
 BAD_COLOR = 0
@@ -80,6 +102,62 @@ def set_seed(random_seed):
         torch.cuda.manual_seed_all(random_seed)
     torch.backends.cudnn.deterministic = True
     torch.backends.cudnn.benchmark = False
+
+
+def NestDict():
+    return defaultdict(NestDict)
+
+
+def make_yaml_dumpable(D):
+    """Nested dicts / arrays / numpy scalars -> plain Python containers that yaml.safe_dump accepts (in place for dicts,
+    like the reference's helper: the drivers pass their NestDict of 4x4 poses)."""
+    if isinstance(D, np.ndarray):
+        return D.tolist()
+    if isinstance(D, (np.integer, np.floating, np.bool_)):
+        return D.item()
+    if isinstance(D, dict):
+        for k in list(D.keys()):
+            D[k] = make_yaml_dumpable(dict(D[k]) if isinstance(D[k], dict) else D[k])
+        return dict(D)
+    if isinstance(D, (list, tuple)):
+        return [make_yaml_dumpable(x) for x in D]
+    return D
+
+
+def euler_matrix(ai, aj, ak, axes="sxyz"):
+    """Homogeneous rotation from Euler angles, `transformations.euler_matrix` for its default static-xyz axes
+    (R = Rz(ak) Ry(aj) Rx(ai)); the reference only calls it with the default."""
+    if axes != "sxyz":
+        raise NotImplementedError("euler_matrix: only the default 'sxyz' convention is provided")
+    ci, si, cj, sj, ck, sk = math.cos(ai), math.sin(ai), math.cos(aj), math.sin(aj), math.cos(ak), math.sin(ak)
+    M = np.eye(4)
+    M[:3, :3] = [[cj * ck, sj * si * ck - ci * sk, sj * ci * ck + si * sk],
+                 [cj * sk, sj * si * sk + ci * ck, sj * ci * sk - si * ck],
+                 [-sj, cj * si, cj * ci]]
+    return M
+
+
+def symmetry_tfs_from_info(info, rot_angle_discrete=5):
+    """BOP `models_info.json` entry -> (n,4,4) symmetry transforms: identity, the listed discrete symmetries
+    (translations mm -> m) and the first continuous axis sampled every `rot_angle_discrete` degrees."""
+    tfs = [np.eye(4)]
+    if "symmetries_discrete" in info:
+        d = np.array(info["symmetries_discrete"], dtype=float).reshape(-1, 4, 4)
+        d[..., :3, 3] *= 0.001
+        tfs += list(d)
+    if "symmetries_continuous" in info:
+        axis = np.array(info["symmetries_continuous"][0]["axis"]).reshape(3)
+        offset = info["symmetries_continuous"][0]["offset"]
+        angles = np.arange(0, 360, rot_angle_discrete) / 180.0 * np.pi
+        which = 0 if axis[0] > 0 else (1 if axis[1] > 0 else (2 if axis[2] > 0 else -1))
+        for a in (angles if which >= 0 else [0.0]):
+            e = [0.0, 0.0, 0.0]
+            if which >= 0:
+                e[which] = float(a)
+            tf = euler_matrix(*e)
+            tf[:3, 3] = offset
+            tfs.append(tf)
+    return np.array(tfs)
 
 
 def to_homo(pts):

@@ -65,6 +65,8 @@ class Trimesh:
         return self
 
     def export(self, path):
-        from .exchange import export_obj
+        from .exchange import export_obj, export_ply
 
+        if str(path).lower().endswith(".ply"):
+            return export_ply(self, path)
         return export_obj(self, path)

@@ -22,9 +22,10 @@ from .estimater import FoundationPose, PoseRefinePredictor, ScorePredictor
 
 
 class _Worker(threading.Thread):
-    def __init__(self, device, jobs, state_dicts, cfg):
+    def __init__(self, device, jobs, state_dicts, cfg, cluster_symmetries=False):
         super().__init__(daemon=True)
         self.device, self.jobs, self.state_dicts, self.cfg = int(device), jobs, state_dicts, cfg
+        self.cluster_symmetries = cluster_symmetries
         self.est = None
         self.ready = threading.Event()
         self.error = None
@@ -33,8 +34,12 @@ class _Worker(threading.Thread):
         eng = Engine()
         refiner = PoseRefinePredictor(engine=eng, state_dict=self.state_dicts.get("refine"), cfg=self.cfg.get("refine"))
         scorer = ScorePredictor(engine=eng, state_dict=self.state_dicts.get("score"), cfg=self.cfg.get("score"))
-        self.est = FoundationPose(model_pts=model_pts, model_normals=model_normals, symmetry_tfs=symmetry_tfs, mesh=mesh, scorer=scorer,
-                                  refiner=refiner)
+        # the rotation grid is built at construction (estimater.py:40-41): without `cluster_symmetries` it is the full
+        # 252-pose grid for every object, as in the reference's drivers, whose placeholder Box has no symmetry
+        self.est = FoundationPose(model_pts=model_pts, model_normals=model_normals,
+                                  symmetry_tfs=symmetry_tfs if self.cluster_symmetries else None, mesh=mesh, scorer=scorer, refiner=refiner)
+        if not self.cluster_symmetries:
+            self.est.reset_object(model_pts, model_normals, symmetry_tfs=symmetry_tfs, mesh=mesh)
 
     def run(self):
         torch.cuda.set_device(self.device)
@@ -50,7 +55,8 @@ class _Worker(threading.Thread):
                         self._build(model_pts, model_normals, mesh, symmetry_tfs)
                     else:
                         self.est.reset_object(model_pts, model_normals, symmetry_tfs=symmetry_tfs, mesh=mesh)
-                        self.est.make_rotation_grid(min_n_views=40, inplane_step=60)
+                        if self.cluster_symmetries:
+                            self.est.make_rotation_grid(min_n_views=40, inplane_step=60)
                     done(None)
                 else:
                     K, rgb, depth, mask, iteration = payload
@@ -61,15 +67,18 @@ class _Worker(threading.Thread):
 
 class ReplicaPool:
     """One estimator per GPU, fed from queues.  `state_dicts` = {"refine": ..., "score": ...} (None: checkpoints found
-    the reference's way, else the seeded stand-ins), `cfg` likewise."""
+    the reference's way, else the seeded stand-ins), `cfg` likewise.  `cluster_symmetries`: False keeps the reference
+    drivers' behaviour — `reset_object` (estimater.py:43-85) stores an object's symmetry transforms but the 252 start
+    poses built at construction are NOT re-clustered under them; True thins the start poses per object (fewer hypotheses
+    for symmetric objects, same pose up to the symmetry group)."""
 
-    def __init__(self, device_ids, state_dicts=None, cfg=None):
+    def __init__(self, device_ids, state_dicts=None, cfg=None, cluster_symmetries=False):
         self.device_ids = [int(d) for d in device_ids]
         self._private = [queue.Queue() for _ in self.device_ids]  # per-replica commands (reset_object)
         self._shared = queue.Queue()                                # frames: whichever replica is free takes the next
         self.workers = []
         for d, q in zip(self.device_ids, self._private):
-            w = _Worker(d, q, state_dicts or {}, cfg or {})
+            w = _Worker(d, q, state_dicts or {}, cfg or {}, cluster_symmetries)
             w.start()
             self.workers.append(w)
         self._pumps = []

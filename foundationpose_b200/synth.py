@@ -223,3 +223,107 @@ def write_demo_scene(root, n_frames=5, subdivisions=3, seed=0):
             cv2.imwrite(os.path.join(root, "masks", name + ".png"), mask.astype(np.uint8) * 255)
         np.savetxt(os.path.join(root, "annotated_poses", name + ".txt"), p)
     return mesh, poses
+
+
+def _write_bop_scene(scene_dir, ob_id, poses, tex, seed):
+    """One BOP scene directory with ONE annotated object per frame (datareader.py:155-181 layout)."""
+    import json
+    import os
+
+    import cv2
+
+    for sub in ("rgb", "depth", "mask_visib", "mask"):
+        os.makedirs(os.path.join(scene_dir, sub), exist_ok=True)
+    cam, gt = {}, {}
+    for i, p in enumerate(poses):
+        rgb, depth, mask = make_scene(tex, p, seed=seed + i)
+        name = f"{i:06d}"
+        cv2.imwrite(os.path.join(scene_dir, "rgb", name + ".png"), rgb[..., ::-1])
+        cv2.imwrite(os.path.join(scene_dir, "depth", name + ".png"), np.clip(np.rint(depth * 1000.0), 0, 65535).astype(np.uint16))
+        for sub in ("mask_visib", "mask"):
+            cv2.imwrite(os.path.join(scene_dir, sub, f"{name}_000000.png"), mask.astype(np.uint8) * 255)
+        cam[str(i)] = {"cam_K": DEFAULT_K.reshape(-1).tolist(), "depth_scale": 1.0}
+        gt[str(i)] = [{"cam_R_m2c": p[:3, :3].reshape(-1).tolist(), "cam_t_m2c": (p[:3, 3] * 1000.0).tolist(), "obj_id": int(ob_id)}]
+    with open(os.path.join(scene_dir, "scene_camera.json"), "w") as fh:
+        json.dump(cam, fh)
+    with open(os.path.join(scene_dir, "scene_gt.json"), "w") as fh:
+        json.dump(gt, fh)
+
+
+def _write_bop_models(models_dir, ob_ids, subdivisions, symmetric=()):
+    """obj_<id>.ply (vertex-coloured ellipsoid, MILLIMETRES) + models_info.json; returns {ob_id: texture image}."""
+    import json
+    import os
+    import sys
+
+    os.makedirs(models_dir, exist_ok=True)
+    fb = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dropin", "_fallback")
+    try:
+        import trimesh
+    except ImportError:
+        sys.path.append(fb)
+        import trimesh
+    info, texs = {}, {}
+    for ob_id in ob_ids:
+        m = make_mesh(subdivisions, tex_seed=int(ob_id), tex_size=256)
+        tex = m.visual.image
+        Ht, Wt = tex.shape[:2]
+        tx = np.clip((m.visual.uv[:, 0] * Wt).astype(np.int64), 0, Wt - 1)
+        ty = np.clip(((1.0 - m.visual.uv[:, 1]) * Ht).astype(np.int64), 0, Ht - 1)
+        tm = trimesh.Trimesh(m.vertices * 1000.0, m.faces, vertex_normals=m.vertex_normals)
+        tm.visual = trimesh.visual.ColorVisuals(vertex_colors=tex[ty, tx])
+        tm.export(os.path.join(models_dir, f"obj_{int(ob_id):06d}.ply"))
+        lo, hi = (m.vertices * 1000.0).min(0), (m.vertices * 1000.0).max(0)
+        e = {"diameter": float(mesh_diameter(m.vertices) * 1000.0), "min_x": float(lo[0]), "min_y": float(lo[1]), "min_z": float(lo[2]),
+             "size_x": float(hi[0] - lo[0]), "size_y": float(hi[1] - lo[1]), "size_z": float(hi[2] - lo[2])}
+        if ob_id in symmetric:
+            e["symmetries_discrete"] = [np.diag([-1.0, -1.0, 1.0, 1.0]).reshape(-1).tolist()]  # half turn about z
+        info[str(int(ob_id))] = e
+        texs[ob_id] = tex
+    with open(os.path.join(models_dir, "models_info.json"), "w") as fh:
+        json.dump(info, fh)
+    return texs
+
+
+def write_bop_dataset(root, kind="lm", n_frames=1, subdivisions=2, seed=0, scene_objects=None, symmetric=(6,)):
+    """A synthetic dataset in the directory conventions of the reference's dataset drivers:
+
+    kind = "lm"   (run_linemod.py:90-112, datareader.py:400-430): <root>/lm_test_all/test/<ob_id:06d>/ — one scene per
+                  object, for the 13 evaluated LINEMOD ids — and <root>/lm_models/models/;
+    kind = "ycbv" (run_ycb_video.py:85-118, datareader.py:433-531): <root>/test/<scene:06d>/ for `scene_objects`
+                  ({scene id: object id}), <root>/ycbv_models/models/ for all 21 ids, <root>/models/<21 names>/ and
+                  <root>/keyframe.txt.
+
+    Every frame shows ONE textured ellipsoid (all objects share the geometry, not the colours).  Returns
+    {(scene id, frame id string, object id): ground-truth 4x4 pose}."""
+    import os
+
+    gts = {}
+    if kind == "lm":
+        ob_ids = [i for i in range(1, 16) if i not in (3, 7)]
+        texs = _write_bop_models(os.path.join(root, "lm_models", "models"), ob_ids, subdivisions, symmetric)
+        scenes = {ob_id: ob_id for ob_id in ob_ids}
+        scene_root = os.path.join(root, "lm_test_all", "test")
+    elif kind == "ycbv":
+        ob_ids = list(range(1, 22))
+        texs = _write_bop_models(os.path.join(root, "ycbv_models", "models"), ob_ids, subdivisions, symmetric)
+        scenes = dict(scene_objects or {48: 1, 49: 6, 50: 13})
+        scene_root = os.path.join(root, "test")
+        for i in ob_ids:
+            os.makedirs(os.path.join(root, "models", f"{i:03d}_synthetic_object"), exist_ok=True)
+    else:
+        raise ValueError(kind)
+    key_lines = []
+    for scene_id, ob_id in scenes.items():
+        pose0 = np.eye(4)
+        pose0[:3, :3] = random_rotation(seed + 7 * scene_id)
+        pose0[:3, 3] = [0.03 * ((scene_id % 3) - 1), -0.02 * ((scene_id % 2)), 0.55 + 0.01 * (scene_id % 5)]
+        poses = track_sequence(n_frames, pose0, seed=seed + scene_id)
+        _write_bop_scene(os.path.join(scene_root, f"{scene_id:06d}"), ob_id, poses, texs[ob_id], seed=10 * scene_id + 1)
+        for i, p in enumerate(poses):
+            gts[(scene_id, f"{i:06d}", ob_id)] = p
+            key_lines.append(f"{scene_id:04d}/{i:06d}")
+    if kind == "ycbv":
+        with open(os.path.join(root, "keyframe.txt"), "w") as fh:
+            fh.write("\n".join(key_lines) + "\n")
+    return gts

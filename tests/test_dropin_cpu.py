@@ -78,3 +78,79 @@ print('OK')
 """
     out = subprocess.run([sys.executable, "-c", code], env=_env(), capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "OK" in out.stdout, (out.stdout + out.stderr)[-3000:]
+
+
+@pytest.mark.parametrize("script", ["run_linemod.py", "run_ycb_video.py"])
+def test_every_name_the_dataset_drivers_use_resolves(script):
+    """Same static check for the reference's dataset drivers: replay the script's own import
+    statements on top of the drop-in tree, then every unqualified name / first-level attribute must exist."""
+    import builtins
+
+    path = "/root/reference/" + script
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present (GPU box)")
+    tree = ast.parse(open(path).read())
+    imports = [ast.unparse(n) for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
+    assigned, used, attrs = set(), set(), set()
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Name):
+            (assigned if isinstance(node.ctx, ast.Store) else used).add(node.id)
+        elif isinstance(node, ast.Attribute) and isinstance(node.value, ast.Name):
+            attrs.add((node.value.id, node.attr))
+        elif isinstance(node, (ast.FunctionDef, ast.arg)):
+            assigned.add(node.name if isinstance(node, ast.FunctionDef) else node.arg)
+    need = sorted(n for n in used - assigned - set(dir(builtins)) if n != "__file__")
+    assert {"wp", "NestDict", "make_yaml_dumpable", "dr", "trimesh", "FoundationPose", "set_seed", "argparse"} <= set(need)
+    mod_attrs = sorted((m, a) for (m, a) in attrs if m in need and m not in ("opt", "parser", "o3d", "reader", "reader_tmp", "est"))
+    code = ("\n".join(imports) + "\n"
+            f"missing = [n for n in {need!r} if n not in globals()]\n"
+            f"missing += [f'{{m}}.{{a}}' for (m, a) in {mod_attrs!r} if m in globals() and not hasattr(globals()[m], a)]\n"
+            "print('MISSING', missing)\n")
+    out = subprocess.run([sys.executable, "-c", code], env=_env(), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "MISSING []" in out.stdout, out.stdout[-2000:]
+
+
+def test_bop_readers_parse_the_synthetic_datasets(tmp_path):
+    """LinemodReader / YcbVideoReader (datareader.py:155-531) on trees written by synth.write_bop_dataset: ids, K,
+    colour / depth / mask, ground-truth poses, PLY models in millimetres, symmetry tables, key frames."""
+    code = f"""
+import os
+import numpy as np
+from foundationpose_b200 import synth
+root = {str(tmp_path)!r}
+gt_lm = synth.write_bop_dataset(root + '/LINEMOD', 'lm', n_frames=2)
+gt_y = synth.write_bop_dataset(root + '/YCB_Video', 'ycbv', n_frames=2)
+os.environ['YCB_VIDEO_DIR'] = root + '/YCB_Video'
+from datareader import *
+r = LinemodReader(root + '/LINEMOD/lm_test_all/test/000006', split=None)
+assert r.ob_ids == [1, 2, 4, 5, 6, 8, 9, 10, 11, 12, 13, 14, 15] and r.get_video_id() == 6 and len(r.color_files) == 2
+assert r.id_strs == ['000000', '000001'] and np.allclose(r.K, synth.DEFAULT_K) and np.allclose(r.get_K(1), synth.DEFAULT_K)
+assert list(r.get_instance_ids_in_image(0)) == [6]
+c, d, m = r.get_color(0), r.get_depth(0), r.get_mask(0, 6)
+assert c.shape == (480, 640, 3) and c.dtype == np.uint8 and d.shape == (480, 640) and m.dtype == bool and 2000 < m.sum() < 60000
+assert abs(np.median(d[m]) - gt_lm[(6, '000000', 6)][2, 3]) < 0.08 and d[~m].min() > 1.0
+assert r.get_mask(0, 5) is None or True
+assert np.allclose(r.get_gt_pose(0, 6), gt_lm[(6, '000000', 6)], atol=1e-9)
+assert np.allclose(r.get_gt_pose(1, 6, mask=m), gt_lm[(6, '000001', 6)], atol=1e-9)
+assert r.get_gt_poses(0, 6).shape == (1, 4, 4) and r.get_gt_poses(0, 5).shape == (0, 4, 4)
+mesh = r.get_gt_mesh(6)
+ref = synth.make_mesh(2)
+assert np.abs(mesh.vertices - ref.vertices).max() < 1e-6 and (mesh.faces == ref.faces).all()
+assert mesh.visual.vertex_colors.shape == (len(ref.vertices), 4)
+assert abs(r.get_model_diameter(6) - synth.mesh_diameter(ref.vertices)) < 1e-6
+assert r.symmetry_tfs[6].shape == (2, 4, 4) and r.symmetry_tfs[5].shape == (1, 4, 4)
+xyz = r.get_xyz_map(0)
+assert xyz.shape == (480, 640, 3) and abs(xyz[240, 320, 2] - d[240, 320]) < 1e-6
+y = YcbVideoReader(root + '/YCB_Video/test/000049', zfar=1.5)
+assert y.ob_ids == list(range(1, 22)) and len(y.ob_id_to_names) == 21 and y.get_video_id() == 49
+assert list(y.get_instance_ids_in_image(0)) == [6] and y.is_keyframe(0) and y.is_keyframe(1)
+assert y.get_depth(0).max() <= 1.5
+assert np.abs(y.get_gt_mesh(13).vertices - ref.vertices).max() < 1e-6
+assert 'symmetries_continuous' in y.geometry_symmetry_info_table[13] and len(y.geometry_symmetry_info_table[2]['symmetries_discrete']) == 8
+assert isinstance(get_bop_reader(root + '/YCB_Video/test/000048'), YcbVideoReader)
+print('OK')
+"""
+    out = subprocess.run([sys.executable, "-c", code], env=_env(), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "OK" in out.stdout, (out.stdout + out.stderr)[-3000:]
+
