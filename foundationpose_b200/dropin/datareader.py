@@ -16,8 +16,8 @@ and the BOP-format readers its dataset drivers use (run_linemod.py:90-112, run_y
     <models>/obj_<id:06d>.ply (+ models_info.json: diameter [mm], symmetries)   model units: millimetres
 
 `BopBaseReader`, `LinemodOcclusionReader`, `LinemodReader`, `YcbVideoReader` keep the reference's method names, argument
-orders and directory conventions; the remaining BOP datasets (T-LESS, HB, ITODD, IC-BIN, TUD-L) differ only in their
-model directory and are not provided.
+orders and directory conventions; the remaining BOP datasets (T-LESS, HB, ITODD, IC-BIN, TUD-L: datareader.py:533-613)
+differ only in their object count and model directory and are generated from one table.
 """
 from Utils import *  # noqa: F401,F403
 import copy
@@ -106,11 +106,27 @@ class YcbineoatReader:
 
 
 def get_bop_reader(video_dir, zfar=np.inf):
+    """Reader class by substring of the scene path (datareader.py:17-33)."""
     if "ycbv" in video_dir or "YCB" in video_dir:
         return YcbVideoReader(video_dir, zfar=zfar)
     if "lmo" in video_dir or "LINEMOD-O" in video_dir:
         return LinemodOcclusionReader(video_dir, zfar=zfar)
-    raise RuntimeError(f"no reader for {video_dir}: this drop-in provides the LINEMOD(-O) and YCB-Video readers")
+    if "tless" in video_dir or "TLESS" in video_dir:
+        return TlessReader(video_dir, zfar=zfar)
+    for key, cls in (("hb", "HomebrewedReader"), ("tudl", "TudlReader"), ("icbin", "IcbinReader"), ("itodd", "ItoddReader")):
+        if key in video_dir:
+            return globals()[cls](video_dir, zfar=zfar)
+    raise RuntimeError(f"no BOP reader for {video_dir}")
+
+
+def get_bop_video_dirs(dataset):
+    """Scene directories of a BOP'19 test split under $BOP_DIR (datareader.py:36-53)."""
+    sub = {"ycbv": "ycbv/test", "lmo": "lmo/lmo_test_bop19/test", "tless": "tless/tless_test_primesense_bop19/test_primesense",
+           "hb": "hb/hb_test_primesense_bop19/test_primesense", "tudl": "tudl/tudl_test_bop19/test", "icbin": "icbin/icbin_test_bop19/test",
+           "itodd": "itodd/itodd_test_bop19/test"}
+    if dataset not in sub:
+        raise RuntimeError(f"unknown BOP dataset {dataset}")
+    return sorted(glob.glob(f"{BOP_DIR}/{sub[dataset]}/*"))
 
 
 class BopBaseReader:
@@ -372,4 +388,56 @@ class YcbVideoReader(BopBaseReader):
             return True
         frame_id = int(os.path.basename(self.color_files[i]).split(".")[0])
         return f"{self.get_video_id():04d}/{frame_id:06d}" in self.keyframe_lines
+
+
+def _simple_bop_reader(name, dataset_name, n_objects, models_subdir, targets=False, doc=""):
+    """The five BOP readers that differ only by object count and model directory (datareader.py:533-613)."""
+
+    class _Reader(BopBaseReader):
+        def __init__(self, base_dir, zfar=np.inf):
+            super().__init__(base_dir, zfar=zfar)
+            self.dataset_name = dataset_name
+            self.ob_ids = list(range(1, n_objects + 1))
+            self.load_symmetry_tfs()
+            if targets:  # no scene_gt.json in the test split: object ids per frame come from the challenge's target list
+                self.make_scene_ob_ids_dict()
+
+        def get_gt_mesh_file(self, ob_id):
+            return f"{self.base_dir}/../../../{models_subdir}/obj_{ob_id:06d}.ply"
+
+    _Reader.__name__ = _Reader.__qualname__ = name
+    _Reader.__doc__ = doc
+    return _Reader
+
+
+_TlessBase = _simple_bop_reader("TlessReader", "tless", 30, "models_cad")
+
+
+class TlessReader(_TlessBase):
+    """T-LESS: texture-less CAD models, rendered with a uniform grey (datareader.py:547-551)."""
+
+    def get_gt_mesh(self, ob_id):
+        mesh = trimesh.load(self.get_gt_mesh_file(ob_id))
+        mesh.vertices *= 1e-3
+        grey = np.tile(np.array([[200, 200, 200, 255]], dtype=np.uint8), (len(mesh.vertices), 1))
+        mesh.visual = trimesh.visual.ColorVisuals(vertex_colors=grey) if hasattr(trimesh.visual, "ColorVisuals") else mesh.visual
+        if getattr(mesh.visual, "vertex_colors", None) is None or len(mesh.visual.vertex_colors) != len(mesh.vertices):
+            mesh.visual.vertex_colors = grey
+        return mesh
+
+
+_HbBase = _simple_bop_reader("HomebrewedReader", "hb", 33, "hb_models/models", targets=True)
+
+
+class HomebrewedReader(_HbBase):
+    """HomebrewedDB: the test split has no public ground truth (datareader.py:568-570)."""
+
+    def get_gt_pose(self, i_frame, ob_id, use_my_correction=False):
+        logging.info("WARN HomeBrewed doesn't have GT pose")
+        return np.eye(4)
+
+
+ItoddReader = _simple_bop_reader("ItoddReader", "itodd", 28, "itodd_models/models", targets=True, doc="ITODD (grey-scale frames under gray/)")
+IcbinReader = _simple_bop_reader("IcbinReader", "icbin", 2, "icbin_models/models", doc="IC-BIN")
+TudlReader = _simple_bop_reader("TudlReader", "tudl", 3, "tudl_models/models", doc="TUD-L")
 

@@ -154,3 +154,37 @@ print('OK')
     out = subprocess.run([sys.executable, "-c", code], env=_env(), capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "OK" in out.stdout, (out.stdout + out.stderr)[-3000:]
 
+
+def test_remaining_bop_readers(tmp_path):
+    """TUD-L / T-LESS style readers (datareader.py:533-613): dispatch by path, model directory three levels up, uniform
+    grey for the texture-less CAD models."""
+    code = f"""
+import json, os, shutil
+import numpy as np
+from foundationpose_b200 import synth
+d = {str(tmp_path)!r}
+synth.write_bop_dataset(d + '/LM', 'lm')
+def info(path, n):
+    json.dump({{str(i): {{"diameter": 100.0}} for i in range(1, n + 1)}}, open(path, 'w'))
+os.makedirs(d + '/tudl/tudl_test_bop19/test')
+shutil.copytree(d + '/LM/lm_test_all/test/000001', d + '/tudl/tudl_test_bop19/test/000001')
+shutil.copytree(d + '/LM/lm_models/models', d + '/tudl/tudl_models/models')
+info(d + '/tudl/tudl_models/models/models_info.json', 3)
+os.makedirs(d + '/tless/split/test_primesense')
+shutil.copytree(d + '/LM/lm_test_all/test/000002', d + '/tless/split/test_primesense/000002')
+shutil.copytree(d + '/LM/lm_models/models', d + '/tless/models_cad')
+info(d + '/tless/models_cad/models_info.json', 30)
+from datareader import *
+r = get_bop_reader(d + '/tudl/tudl_test_bop19/test/000001')
+assert type(r).__name__ == 'TudlReader' and r.ob_ids == [1, 2, 3] and r.dataset_name == 'tudl'
+assert r.get_gt_mesh(1).vertices.shape[1] == 3 and r.symmetry_tfs[2].shape == (1, 4, 4) and abs(r.get_model_diameter(1) - 0.1) < 1e-12
+t = get_bop_reader(d + '/tless/split/test_primesense/000002')
+assert type(t).__name__ == 'TlessReader' and len(t.ob_ids) == 30
+m = t.get_gt_mesh(2)
+assert (np.asarray(m.visual.vertex_colors)[:, :3] == 200).all() and np.abs(m.vertices).max() < 0.2
+assert IcbinReader.__name__ == 'IcbinReader' and issubclass(HomebrewedReader, BopBaseReader) and issubclass(ItoddReader, BopBaseReader)
+print('OK')
+"""
+    out = subprocess.run([sys.executable, "-c", code], env=_env(), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "OK" in out.stdout, (out.stdout + out.stderr)[-3000:]
+
