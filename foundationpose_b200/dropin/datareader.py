@@ -184,7 +184,8 @@ class BopBaseReader:
     # ---- frame data
     def get_K(self, i_frame):
         K = self.K_table[self.id_strs[i_frame]]
-        if self.resize != 1:
+        if self.resize != 1:  # a scaled COPY (scaling the table entry in place would compound over calls)
+            K = K.copy()
             K[:2, :2] *= self.resize
         return K
 
