@@ -188,3 +188,45 @@ print('OK')
     out = subprocess.run([sys.executable, "-c", code], env=_env(), capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "OK" in out.stdout, (out.stdout + out.stderr)[-3000:]
 
+
+def test_bop_reader_multi_instance_and_missing_files(tmp_path):
+    """datareader.py:266-350 edge cases: two instances of one object in a frame (the `mask` argument picks the
+    annotation by visible-mask IoU), a second object's mask index, a missing mask file (None), frames without
+    scene_gt.json (ids from the mask file names)."""
+    code = f"""
+import json, os
+import cv2
+import numpy as np
+from foundationpose_b200 import synth
+d = {str(tmp_path)!r}
+synth.write_bop_dataset(d + '/LM', 'lm')
+scene = d + '/LM/lm_test_all/test/000001'
+gt = json.load(open(scene + '/scene_gt.json'))
+a = dict(gt['0'][0]); b = dict(a); c = dict(a)
+b['cam_t_m2c'] = [100.0, 0.0, 700.0]           # second instance of object 1
+c['obj_id'] = 5; c['cam_t_m2c'] = [-100.0, 50.0, 650.0]
+gt['0'] = [a, c, b]
+json.dump(gt, open(scene + '/scene_gt.json', 'w'))
+m0 = cv2.imread(scene + '/mask_visib/000000_000000.png', -1)
+m1 = np.zeros_like(m0); m1[100:200, 400:500] = 255   # object 5
+m2 = np.zeros_like(m0); m2[300:400, 100:200] = 255   # second instance of object 1
+cv2.imwrite(scene + '/mask_visib/000000_000001.png', m1)
+cv2.imwrite(scene + '/mask_visib/000000_000002.png', m2)
+from datareader import *
+r = LinemodReader(scene, split=None)
+assert list(r.get_instance_ids_in_image(0)) == [1, 5, 1]
+assert r.get_gt_poses(0, 1).shape == (2, 4, 4) and r.get_gt_poses(0, 5).shape == (1, 4, 4)
+assert np.allclose(r.get_gt_pose(0, 1)[:3, 3], np.array(a['cam_t_m2c']) / 1e3)          # first annotation without a mask
+assert np.allclose(r.get_gt_pose(0, 1, mask=m2 > 0)[:3, 3], [0.1, 0.0, 0.7])            # IoU picks the second instance
+assert np.allclose(r.get_gt_pose(0, 1, mask=m0 > 0)[:3, 3], np.array(a['cam_t_m2c']) / 1e3)
+assert (r.get_mask(0, 5) == (m1 > 0)).all() and (r.get_mask(0, 1) == (m0 > 0)).all()
+assert r.get_mask(0, 5, type='mask') is None                                              # no such file: None, not an exception
+assert np.allclose(r.get_gt_pose(0, 9), np.eye(4))                                        # object not in the frame
+os.remove(scene + '/scene_gt.json')
+r2 = LinemodReader(scene, split=None)
+assert r2.scene_gt is None and list(r2.get_instance_ids_in_image(0)) == [0, 1, 2]         # annotation slots from the mask files
+print('OK')
+"""
+    out = subprocess.run([sys.executable, "-c", code], env=_env(), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "OK" in out.stdout, (out.stdout + out.stderr)[-3000:]
+
