@@ -1,7 +1,6 @@
 """GPU: the reference's own run_demo.py, UNMODIFIED, on top of foundationpose_b200/dropin and a synthetic scene in
 the reference's demo-data layout.  The script is staged by __graft_entry__.build() into oracle/_ref/ (git-ignored,
-never committed) because the GPU box has no /root/reference; without it the test falls back to
-examples/run_demo_dropin.py, which walks the same call sequence (run_demo.py:26-79) with the same star-imports."""
+never committed) because the GPU box has no /root/reference; without it the tests are skipped."""
 import os
 import subprocess
 import sys
@@ -19,7 +18,7 @@ def _driver():
     for cand in ("/root/reference/run_demo.py", os.path.join(ROOT, "oracle", "_ref", "run_demo.py")):
         if os.path.exists(cand):
             return cand, True
-    return os.path.join(ROOT, "examples", "run_demo_dropin.py"), False
+    pytest.skip("reference driver not staged (run __graft_entry__.build() where /root/reference exists)")
 
 
 @pytest.mark.parametrize("debug", [0, 2])
