@@ -482,15 +482,27 @@ static int set_frame_launches(fp_ctx* c, const unsigned char* rgb_dev, const flo
                               cudaStream_t st) {
   const int H = c->H, W = c->W;
   const size_t npix = (size_t)H * W;
-  FP_TRY(rgb_to_rgba_launch(rgb_dev, reinterpret_cast<uchar4*>(c->rgba.p), (int)npix, st));
-  if (flags & FP_FRAME_FILTER_DEPTH) {
-    // estimater.py:173-174: erode_depth(radius=2) then bilateral_filter_depth(radius=2)
+  static int fused = -1;  // FPOSE_FUSED_PREP=0: the four separate launches (A/B)
+  if (fused < 0) {
+    const char* e = getenv("FPOSE_FUSED_PREP");
+    fused = (e && e[0] == '0') ? 0 : 1;
+  }
+  if ((flags & FP_FRAME_FILTER_DEPTH) && !fused) {
+    FP_TRY(rgb_to_rgba_launch(rgb_dev, reinterpret_cast<uchar4*>(c->rgba.p), (int)npix, st));
     FP_TRY(erode_depth_launch(depth_dev, reinterpret_cast<float*>(c->depth_a.p), H, W, 2, 0.001f, 0.8f, 100.f, st));
     FP_TRY(bilateral_depth_launch(reinterpret_cast<const float*>(c->depth_a.p), reinterpret_cast<float*>(c->depth_b.p), H,
                                   W, 2, 100.f, 2.f, 100000.f, st));
-  } else {
-    FP_CUDA_OK(cudaMemcpyAsync(c->depth_b.p, depth_dev, npix * 4, cudaMemcpyDeviceToDevice, st));
+    c->depth_cur = reinterpret_cast<const float*>(c->depth_b.p);
+    return depth_to_xyz_launch(c->depth_cur, reinterpret_cast<float4*>(c->xyz.p), H, W, c->K[0], c->K[4], c->K[2], c->K[5], zfar, st);
   }
+  if (flags & FP_FRAME_FILTER_DEPTH) {
+    // estimater.py:173-174 erode_depth(radius=2), bilateral_filter_depth(radius=2); :214 depth2xyzmap: one launch
+    c->depth_cur = reinterpret_cast<const float*>(c->depth_b.p);
+    return frame_prep_launch(rgb_dev, depth_dev, reinterpret_cast<uchar4*>(c->rgba.p), reinterpret_cast<float*>(c->depth_b.p),
+                             reinterpret_cast<float4*>(c->xyz.p), H, W, c->K[0], c->K[4], c->K[2], c->K[5], zfar, st);
+  }
+  FP_TRY(rgb_to_rgba_launch(rgb_dev, reinterpret_cast<uchar4*>(c->rgba.p), (int)npix, st));
+  FP_CUDA_OK(cudaMemcpyAsync(c->depth_b.p, depth_dev, npix * 4, cudaMemcpyDeviceToDevice, st));
   c->depth_cur = reinterpret_cast<const float*>(c->depth_b.p);
   FP_TRY(depth_to_xyz_launch(c->depth_cur, reinterpret_cast<float4*>(c->xyz.p), H, W, c->K[0], c->K[4], c->K[2], c->K[5],
                              zfar, st));
