@@ -2,7 +2,7 @@
 //
 //   layernorm_kernel     row LayerNorm over 512 channels (norm1 of the encoder layer; the residual add is
 //                        fused in the producing GEMM's epilogue).
-//   token_reduce_kernel  a cluster of four CTAs per sequence: norm2 -> mean over the 400 tokens -> Linear(512, 3)
+//   token_reduce_kernel  a cluster of eight CTAs per sequence (or one CTA walking the same eight ranges): norm2 -> mean over the 400 tokens -> Linear(512, 3)
 //                        (refine_network.py:89-90; the mean commutes with the final linear layer), or the plain token
 //                        mean of the scorer's attention output (score_network.py:72-74; out_proj then runs over all
 //                        hypotheses at once).
@@ -117,19 +117,19 @@ int layernorm_launch(const __half* x, __half* y, const float* gamma, const float
   return 0;
 }
 
-// Token reduction of one sequence (400 tokens x 512 channels), always as FOUR token ranges of 100:
+// Token reduction of one sequence (400 tokens x 512 channels), always as EIGHT token ranges of 50:
 //   kLN = true : norm2 -> token mean -> Linear(512, out_dim <= 8)   (refiner heads, refine_network.py:89-90; the mean
 //                commutes with the final linear layer)
 //   kLN = false: token mean of the attention output -> [512] fp32   (scorer, score_network.py:72-74; the out_proj that
 //                follows is a [N,512] x [512,512] product done by rowwise_linear_kernel for all hypotheses at once)
-// The launch decides who owns the ranges: a CLUSTER of four CTAs (one range each) at small batches — one CTA per
+// The launch decides who owns the ranges: a CLUSTER of eight CTAs (one range each) at small batches — one CTA per
 // sequence left 32 hypotheses per GPU (8-GPU shards) on 32 of 148 SMs and a single tracked pose on one — or ONE CTA
-// walking the four ranges at large batches, where 4x the CTAs only add fixed cost (252 hypotheses: 56 -> 44 us).
-// Either way each range's partial sum is built in the same fixed order and the four partials are added in range
+// walking the eight ranges at large batches, where 8x the CTAs only add fixed cost.
+// Either way each range's partial sum is built in the same fixed order and the eight partials are added in range
 // order (rank 0 reads its peers' over distributed shared memory): the result is bit-identical for both launches and
 // does not depend on N or the shard.
 constexpr int kHeadWarps = 8;
-constexpr int kTokSplit = 4;
+constexpr int kTokSplit = 8;
 template <bool kLN>
 __global__ void __launch_bounds__(kHeadWarps * 32) token_reduce_kernel(const __half* __restrict__ x,
                                                                        const float* __restrict__ gamma,
@@ -140,9 +140,9 @@ __global__ void __launch_bounds__(kHeadWarps * 32) token_reduce_kernel(const __h
   __shared__ float acc[kHeadWarps][512];
   __shared__ float part[kTokSplit][512];  // [range owned by this CTA][channel]
   __shared__ float meanv[512];
-  const unsigned csize = cluster_nctarank();  // 4 (one range per CTA) or 1 (this CTA walks all four)
+  const unsigned csize = cluster_nctarank();  // kTokSplit (one range per CTA) or 1 (this CTA walks all of them)
   const unsigned rank = cluster_ctarank();
-  const int per_cta = kTokSplit / (int)csize;  // launches use a cluster of 4 or of 1
+  const int per_cta = kTokSplit / (int)csize;  // launches use a cluster of kTokSplit or of 1
   const int b = blockIdx.x / (int)csize, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   LnAffine af;
   if (kLN) ln_load_affine(af, gamma, beta, lane);
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(kHeadWarps * 32) token_reduce_kernel(const __h
   }
 }
 
-// cluster of four below this many sequences (2 x 148 SMs' worth of CTAs), one CTA per sequence above
+// cluster of eight (the portable maximum) below this many sequences, one CTA per sequence above
 static inline int token_split_for(int B) { return B <= 74 ? kTokSplit : 1; }
 
 int head_final_launch(const __half* x, const float* gamma, const float* beta, const float* w, const float* bias,
