@@ -64,6 +64,9 @@ class ShardedRegister:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._packed = {}
+        # the engine's tensors live on its CUDA device; a test double may say otherwise (tests/test_host_logic_cpu.py
+        # runs this class over gloo with a host-side stand-in for the engine)
+        self.device = torch.device(getattr(engine, "tensor_device", "cuda"))
 
     def run(self, poses_all, iterations):
         """poses_all: (N,4,4) identical on every rank (host or device).  Returns refined poses (N,4,4),
@@ -72,18 +75,18 @@ class ShardedRegister:
         N = len(poses_all)
         lo, hi = shard_bounds(N, self.world, self.rank)
         local = torch.as_tensor(poses_all[lo:hi], dtype=torch.float32)
-        if not local.is_cuda:
-            local = local.cuda(non_blocking=True)
+        if local.device.type != self.device.type:
+            local = local.to(self.device, non_blocking=True)
         if hi > lo:
             refined, _, _ = e.refine(local, iterations)
             feats = e.score_features(refined)
             packed = self._packed.get(hi - lo)
             if packed is None:
-                packed = self._packed[hi - lo] = torch.empty(hi - lo, 528, dtype=torch.float32, device="cuda")
+                packed = self._packed[hi - lo] = torch.empty(hi - lo, 528, dtype=torch.float32, device=self.device)
             packed[:, :512].copy_(feats)
             packed[:, 512:].copy_(refined.reshape(-1, 16))
         else:
-            packed = torch.empty(0, 528, dtype=torch.float32, device="cuda")
+            packed = torch.empty(0, 528, dtype=torch.float32, device=self.device)
         allp = gather_rows(packed, N, self.group)
         scores, best = e.score_tail(allp[:, :512].contiguous())
         return allp[:, 512:].reshape(N, 4, 4), scores, best

@@ -22,15 +22,19 @@ from .estimater import FoundationPose, PoseRefinePredictor, ScorePredictor
 
 
 class _Worker(threading.Thread):
-    def __init__(self, device, jobs, state_dicts, cfg, cluster_symmetries=False):
+    def __init__(self, device, jobs, state_dicts, cfg, cluster_symmetries=False, make_estimator=None):
         super().__init__(daemon=True)
         self.device, self.jobs, self.state_dicts, self.cfg = int(device), jobs, state_dicts, cfg
         self.cluster_symmetries = cluster_symmetries
+        self.make_estimator = make_estimator
         self.est = None
         self.ready = threading.Event()
         self.error = None
 
     def _build(self, model_pts, model_normals, mesh, symmetry_tfs):
+        if self.make_estimator is not None:
+            self.est = self.make_estimator(self.device, model_pts, model_normals, mesh, symmetry_tfs)
+            return
         eng = Engine()
         refiner = PoseRefinePredictor(engine=eng, state_dict=self.state_dicts.get("refine"), cfg=self.cfg.get("refine"))
         scorer = ScorePredictor(engine=eng, state_dict=self.state_dicts.get("score"), cfg=self.cfg.get("score"))
@@ -42,7 +46,8 @@ class _Worker(threading.Thread):
             self.est.reset_object(model_pts, model_normals, symmetry_tfs=symmetry_tfs, mesh=mesh)
 
     def run(self):
-        torch.cuda.set_device(self.device)
+        if self.make_estimator is None or torch.cuda.is_available():
+            torch.cuda.set_device(self.device)
         while True:
             job = self.jobs.get()
             if job is None:
@@ -70,18 +75,18 @@ class ReplicaPool:
     the reference's way, else the seeded stand-ins), `cfg` likewise.  `cluster_symmetries`: False keeps the reference
     drivers' behaviour — `reset_object` (estimater.py:43-85) stores an object's symmetry transforms but the 252 start
     poses built at construction are NOT re-clustered under them; True thins the start poses per object (fewer hypotheses
-    for symmetric objects, same pose up to the symmetry group)."""
+    for symmetric objects, same pose up to the symmetry group).  `make_estimator(device, model_pts, model_normals, mesh,
+    symmetry_tfs)`: build each replica's estimator some other way (an object with `reset_object` / `register`; the
+    scheduling tests use it with a host-side double)."""
 
-    def __init__(self, device_ids, state_dicts=None, cfg=None, cluster_symmetries=False):
+    def __init__(self, device_ids, state_dicts=None, cfg=None, cluster_symmetries=False, make_estimator=None):
         self.device_ids = [int(d) for d in device_ids]
         self._private = [queue.Queue() for _ in self.device_ids]  # per-replica commands (reset_object)
-        self._shared = queue.Queue()                                # frames: whichever replica is free takes the next
         self.workers = []
         for d, q in zip(self.device_ids, self._private):
-            w = _Worker(d, q, state_dicts or {}, cfg or {}, cluster_symmetries)
+            w = _Worker(d, q, state_dicts or {}, cfg or {}, cluster_symmetries, make_estimator)
             w.start()
             self.workers.append(w)
-        self._pumps = []
 
     def close(self):
         for q in self._private:

@@ -1,8 +1,9 @@
-"""CPU: host-side logic — BN folding / weight packing, hypothesis grid, sharding arithmetic and the
-world_size-2 gather (gloo)."""
+"""CPU: host-side logic — BN folding / weight packing, hypothesis grid, sharding arithmetic, the world_size-2 gather
+and the whole sharded register over gloo (host-side engine double), the replica pool's scheduling."""
 import os
 
 import numpy as np
+import pytest
 import torch
 import torch.nn as nn
 
@@ -124,6 +125,129 @@ def test_gather_rows_world2_gloo():
         for p in procs:
             p.join(timeout=60)
         assert all(ok for _, ok in res), res
+
+
+class _HostEngine:
+    """Test double for engine.Engine: same three entry points ShardedRegister drives, computed on the host with a
+    per-hypothesis refine / featurise step and a tail that couples ALL hypotheses (like att_cross,
+    score_network.py:84-88) — so a wrong shard order, a dropped row or a rank-dependent tail shows up in the result."""
+    tensor_device = "cpu"
+
+    def refine(self, poses, iterations):
+        out = poses.clone()
+        for _ in range(iterations):
+            out[:, :3, 3] += 0.01 * torch.tanh(out[:, :3, :3].sum(-1))
+        return out, None, None
+
+    def score_features(self, poses):
+        g = torch.Generator().manual_seed(0)
+        W = torch.randn(16, 512, generator=g)
+        # row by row: the same vector-matrix product whatever the shard height (bit-exact comparison below)
+        return torch.stack([torch.sin(r @ W) for r in poses.reshape(-1, 16)]) if len(poses) else poses.new_zeros(0, 512)
+
+    def score_tail(self, feats):
+        att = torch.softmax(feats @ feats.T / 512 ** 0.5, dim=-1)
+        scores = (att @ feats).sum(-1) + 100.0
+        return scores, scores.argmax().reshape(1).to(torch.int32)
+
+
+def _sharded_worker(rank, world, n_total, port, q):
+    import torch.distributed as dist
+
+    from foundationpose_b200.parallel import ShardedRegister
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(1)
+    poses = torch.eye(4).repeat(n_total, 1, 1) + 0.1 * torch.randn(n_total, 4, 4)
+    sr = ShardedRegister(_HostEngine())
+    outs = [sr.run(poses, 3) for _ in range(2)]  # twice: the second call reuses the cached gather workspaces
+    q.put((rank, [tuple(t.clone().numpy() for t in o) for o in outs]))
+    dist.destroy_process_group()
+
+
+def test_sharded_register_world2_gloo_matches_single_process():
+    """shard -> refine + featurise locally -> ONE gather -> identical tail on every rank.  Both ranks must
+    return the single-process result bit for bit, for even, ragged and empty shards."""
+    import torch.multiprocessing as mp
+
+    from foundationpose_b200.parallel import ShardedRegister
+
+    ctx = mp.get_context("spawn")
+    for n_total in (8, 7, 1):
+        torch.manual_seed(1)
+        poses = torch.eye(4).repeat(n_total, 1, 1) + 0.1 * torch.randn(n_total, 4, 4)
+        ref = [t.numpy() for t in ShardedRegister(_HostEngine()).run(poses, 3)]
+        q = ctx.Queue()
+        port = 29470 + n_total
+        procs = [ctx.Process(target=_sharded_worker, args=(r, 2, n_total, port, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        res = dict(q.get(timeout=120) for _ in procs)
+        for p in procs:
+            p.join(timeout=60)
+        assert sorted(res) == [0, 1]
+        for rank, outs in res.items():
+            for o in outs:
+                for got, want in zip(o, ref):
+                    assert np.array_equal(got, want), (n_total, rank)
+
+
+class _HostEstimator:
+    """Test double for FoundationPose inside replicas.ReplicaPool: records what it is asked and answers with a pose
+    that encodes (frame tag, object tag); slow on one replica so that the dynamic scheduling is exercised."""
+    log = []
+
+    def __init__(self, device, model_pts, model_normals, mesh, symmetry_tfs):
+        self.device, self.obj = device, mesh
+        _HostEstimator.log.append(("build", device, mesh))
+
+    def reset_object(self, model_pts, model_normals, symmetry_tfs=None, mesh=None):
+        self.obj = mesh
+        _HostEstimator.log.append(("reset", self.device, mesh))
+
+    def register(self, K, rgb, depth, ob_mask, iteration):
+        import time
+
+        if rgb == "bad":
+            raise RuntimeError("frame could not be processed")
+        time.sleep(0.02 if self.device == 0 else 0.002)
+        pose = np.eye(4)
+        pose[0, 3], pose[1, 3], pose[2, 3] = rgb, self.obj, iteration
+        _HostEstimator.log.append(("register", self.device, rgb))
+        return pose
+
+
+def test_replica_pool_scheduling_order_and_errors():
+    """SURVEY 8f N3 host logic: one estimator per replica, frames handed out dynamically, results in input order, every
+    replica re-targeted by reset_object, a failing frame surfaces as the caller's exception (run_ycb_video.py:116-121 is
+    the sequential loop this replaces)."""
+    from foundationpose_b200.replicas import ReplicaPool
+
+    _HostEstimator.log = []
+    pool = ReplicaPool([0, 1, 2], make_estimator=_HostEstimator)
+    try:
+        for obj in (11, 12):
+            pool.reset_object(None, None, mesh=obj)
+            frames = [(None, i, None, None) for i in range(40)]
+            poses = pool.register_many(frames, iteration=5)
+            assert [int(p[0, 3]) for p in poses] == list(range(40))  # input order
+            assert all(int(p[1, 3]) == obj and int(p[2, 3]) == 5 for p in poses)  # every replica saw the reset
+        builds = [e for e in _HostEstimator.log if e[0] == "build"]
+        resets = [e for e in _HostEstimator.log if e[0] == "reset"]
+        assert sorted(d for _, d, _ in builds) == [0, 1, 2] and sorted(d for _, d, _ in resets) == [0, 1, 2]
+        per_dev = {d: sum(1 for e in _HostEstimator.log if e[0] == "register" and e[1] == d) for d in (0, 1, 2)}
+        assert sum(per_dev.values()) == 80 and all(per_dev.values())
+        assert per_dev[0] < per_dev[1] and per_dev[0] < per_dev[2]  # the slow replica took fewer frames
+        assert pool.register_many([]) == []
+        with pytest.raises(RuntimeError, match="could not be processed"):
+            pool.register_many([(None, 0, None, None), (None, "bad", None, None), (None, 2, None, None)])
+        # the pool survives a failed frame
+        assert int(pool.register_many([(None, 7, None, None)])[0][0, 3]) == 7
+    finally:
+        pool.close()
+    assert not any(w.is_alive() for w in pool.workers)
 
 
 def test_meshprep_diameter_and_voxel_downsample():
