@@ -113,7 +113,7 @@ def make_yaml_dumpable(D):
     like the reference's helper: the drivers pass their NestDict of 4x4 poses)."""
     if isinstance(D, np.ndarray):
         return D.tolist()
-    if isinstance(D, (np.integer, np.floating, np.bool_)):
+    if isinstance(D, np.generic):  # numpy scalars, np.str_ included (a str subclass that yaml.safe_dump rejects)
         return D.item()
     if isinstance(D, dict):
         for k in list(D.keys()):
@@ -166,10 +166,11 @@ def to_homo(pts):
 
 
 def transform_pts(pts, tf):
-    """(..., N, 3) points through a (..., 4, 4) transform (numpy or torch)."""
+    """(..., N, d) points through a (..., d+1, d+1) homogeneous transform, d = 3 or 2 (numpy or torch): the
+    predictors also push 2-D window corners through 3x3 crop transforms (predict_pose_refine.py:44-45)."""
     if len(tf.shape) >= 3 and tf.shape[-3] != pts.shape[-2]:
         tf = tf[..., None, :, :]
-    return (tf[..., :3, :3] @ pts[..., None] + tf[..., :3, 3:])[..., 0]
+    return (tf[..., :-1, :-1] @ pts[..., None] + tf[..., :-1, -1:])[..., 0]
 
 
 def depth2xyzmap(depth, K, uvs=None):
@@ -273,14 +274,20 @@ def draw_xyz_axis(color, ob_in_cam, scale=0.1, K=np.eye(3), thickness=3, transpa
 
 
 def draw_posed_3d_box(K, img, ob_in_cam, bbox, line_color=(0, 255, 0), linewidth=2):
-    """Draws the 12 edges of the box `bbox` ((2,3) min / max corners in the object frame) posed by `ob_in_cam`."""
+    """Draws the 12 edges of the box `bbox` ((2,3) min / max corners in the object frame) posed by `ob_in_cam`.
+    Edge order as in the reference (Utils.py:713-749: the four x-edges, then y, then z; each from the low to the high
+    corner): the anti-aliased lines overlap at the corners, so the order shows in the pixels."""
+    K, ob_in_cam = np.asarray(K), np.asarray(ob_in_cam)
     lo, hi = np.asarray(bbox).min(axis=0), np.asarray(bbox).max(axis=0)
-    corners = np.array([[x, y, z] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])], dtype=float)
-    cam = (np.asarray(ob_in_cam) @ to_homo(corners).T).T[:, :3]
-    proj = (np.asarray(K) @ cam.T).T
-    uv = np.round(proj[:, :2] / proj[:, 2:3]).astype(int)
-    for a in range(8):
-        for b in range(a + 1, 8):
-            if bin(a ^ b).count("1") == 1:  # corners differing along exactly one axis share an edge
-                img = cv2.line(img, uv[a].tolist(), uv[b].tolist(), color=line_color, thickness=linewidth, lineType=cv2.LINE_AA)
+    for axis in range(3):
+        u_ax, v_ax = [a for a in range(3) if a != axis]
+        for u in (lo[u_ax], hi[u_ax]):
+            for v in (lo[v_ax], hi[v_ax]):
+                ends = np.empty((2, 3))
+                ends[:, u_ax], ends[:, v_ax] = u, v
+                ends[0, axis], ends[1, axis] = lo[axis], lo[axis] + (hi[axis] - lo[axis])
+                cam = (ob_in_cam @ to_homo(ends).T).T[:, :3]
+                proj = (K @ cam.T).T
+                uv = np.round(proj[:, :2] / proj[:, 2:3]).astype(int)
+                img = cv2.line(img, uv[0].tolist(), uv[1].tolist(), color=line_color, thickness=linewidth, lineType=cv2.LINE_AA)
     return img
