@@ -215,3 +215,18 @@ def bilateral_filter_depth(depth, radius=2, zfar=100, sigmaD=2, sigmaR=100000):
     with np.errstate(invalid="ignore", divide="ignore"):
         out = np.where((sw > 0) & (nvalid > 0), s / sw, f32(0))
     return out.astype(f32)
+
+
+def guess_translation(depth, mask, K):
+    """estimater.py:137-156: centre of the mask's bounding box back-projected at the median valid masked depth; zeros for
+    an empty mask or a mask without valid depth.  (The product's host copy, hypotheses.guess_translation, and the device
+    kernel are held to the same reference body by tests/test_geometry_golden_cpu.py.)"""
+    vs, us = np.where(np.asarray(mask) > 0)
+    if len(us) == 0:
+        return np.zeros(3)
+    uc, vc = (us.min() + us.max()) / 2.0, (vs.min() + vs.max()) / 2.0
+    valid = np.asarray(mask).astype(bool) & (np.asarray(depth) >= 0.001)
+    if not valid.any():
+        return np.zeros(3)
+    zc = np.median(np.asarray(depth)[valid])
+    return ((np.linalg.inv(K) @ np.asarray([uc, vc, 1.0]).reshape(3, 1)) * zc).reshape(3)

@@ -84,3 +84,43 @@ def score(sd, poses, mt, rgb, depth, K, mesh_diameter):
     logits = nets.score_forward(sd, A, B, L=len(A)).reshape(-1)
     scores = logits + 100
     return scores, int(scores.argmax())
+
+
+def _to_centered(model_center):
+    tf = torch.eye(4, dtype=torch.float32)
+    tf[:3, 3] = -torch.as_tensor(np.asarray(model_center), dtype=torch.float32)
+    return tf
+
+
+def register(sd_r, sd_s, rot_grid, mt, rgb, depth, mask, K, mesh_diameter, model_center, iterations=5):
+    """FoundationPose.register (estimater.py:159-240): depth filters, the < 4 valid pixels early-out, start poses =
+    rotation grid + guessed translation, K refine iterations, scoring, argsort(descending), best pose in the frame of the
+    ORIGINAL (un-centred) mesh.  Returns a dict: pose (4,4) float64 numpy; and unless `early`: ids, poses / scores in
+    ranked order, pose_last, last_trans / last_rot.  Held to the reference's own method sources by
+    tests/test_flow_golden_cpu.py (tools/make_golden_flow.py)."""
+    depth = geometry.bilateral_filter_depth(geometry.erode_depth(np.asarray(depth)))
+    center = geometry.guess_translation(depth, mask, K)
+    if ((depth >= 0.001) & (np.asarray(mask) > 0)).sum() < 4:
+        pose = np.eye(4)
+        pose[:3, 3] = center
+        return dict(pose=pose, early=True)
+    poses = torch.as_tensor(np.asarray(rot_grid), dtype=torch.float32).clone()
+    poses[:, :3, 3] = torch.as_tensor(center.reshape(1, 3), dtype=torch.float32)
+    xyz_map = geometry.depth2xyzmap(depth, K)
+    poses, lt, lr = refine(sd_r, poses, mt, rgb, depth, K, mesh_diameter, iterations, xyz_map=xyz_map)
+    scores, _ = score(sd_s, poses.numpy(), mt, rgb, depth, K, mesh_diameter)
+    ids = scores.argsort(descending=True)
+    poses, scores = poses[ids], scores[ids]
+    best = poses[0] @ _to_centered(model_center)
+    return dict(pose=best.numpy(), early=False, ids=ids, poses=poses, scores=scores, pose_last=poses[0], last_trans=lt, last_rot=lr)
+
+
+def track_one(sd_r, pose_last, mt, rgb, depth, K, mesh_diameter, model_center, iterations=2):
+    """FoundationPose.track_one (estimater.py:250-268): depth filters, xyz map with zfar = inf, `iterations` refiner passes
+    from the previous pose (centred-mesh frame).  Returns (pose (4,4) numpy in the original mesh frame, new pose_last,
+    last_trans)."""
+    depth = geometry.bilateral_filter_depth(geometry.erode_depth(np.asarray(depth, dtype=np.float32)))
+    xyz_map = geometry.depth2xyzmap(depth, K, zfar=np.inf)
+    pose, lt, _ = refine(sd_r, torch.as_tensor(np.asarray(pose_last), dtype=torch.float32).reshape(1, 4, 4), mt, rgb, depth, K, mesh_diameter,
+                         iterations, xyz_map=xyz_map)
+    return (pose @ _to_centered(model_center)).numpy().reshape(4, 4), pose, lt

@@ -294,6 +294,33 @@ def test_reference_config_defaults(tmp_path):
     assert c["crop_ratio"] == 1.2 and c["zfar"] == float("inf")
 
 
+def test_reference_config_defaults_match_the_reference_statements(tmp_path):
+    """The same, against what the reference's own `if '<key>' not in self.cfg` statements produce
+    (tests/golden/predictor_defaults.json, extracted from the two constructors by tools/make_golden_config.py): every key
+    the reference sets has the reference's value, for both predictors and five partial configs."""
+    import json
+
+    import yaml
+
+    from foundationpose_b200 import weights
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cases = json.load(open(os.path.join(root, "tests", "golden", "predictor_defaults.json")))
+    assert len(cases) == 10
+    for name, case in cases.items():
+        kind = name.split(".")[0]
+        p = tmp_path / (name + ".yml")
+        p.write_text(yaml.safe_dump(case["in"]))
+        got = weights.load_reference_config(str(p), kind)
+        for k, want in case["out"].items():
+            have = got[k]
+            if isinstance(have, float) and np.isinf(have):
+                have = "inf"
+            if isinstance(want, str) and want.lower() == "inf":
+                want = "inf"  # the reference's scorer keeps a textual 'inf'; every consumer treats it as infinity
+            assert have == want, (name, k, have, want)
+
+
 def test_unsupported_config_raises():
     """A cfg value the engine cannot honour is an error, not silently ignored."""
     import pytest
