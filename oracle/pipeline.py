@@ -1,7 +1,12 @@
-"""CPU restatement of the predictors' data path (TEST INFRASTRUCTURE; PARITY UNPINNED, see
+"""CPU restatement of the predictors' data path and of the estimator's flow (TEST INFRASTRUCTURE, see
 oracle/__init__.py): make_crop_data_batch for the refiner (predict_pose_refine.py:25-89) and the scorer
 (predict_score.py:56-114), PoseRefinePredictor.predict's iteration (predict_pose_refine.py:182-239),
-ScorePredictor.predict (predict_score.py:160-214) and the ranking of estimater.py:226-235.
+ScorePredictor.predict (predict_score.py:160-214), the ranking of estimater.py:226-235, register (estimater.py:159-240)
+and track_one (:250-268).
+
+Pinning: everything in this file EXCEPT the two third-party primitives it calls (raster.render_crop for nvdiffrast,
+geometry.warp_perspective for kornia — PARITY UNPINNED, those packages are absent) is held to the reference's own
+unmodified sources, executed by tools/make_golden_flow.py (tests/test_flow_golden_cpu.py).
 """
 import numpy as np
 import torch
