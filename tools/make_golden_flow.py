@@ -288,5 +288,49 @@ def main():
     print(f"wrote {dst}: {len(out)} entries")
 
 
+def headline():
+    """The reference's own `register` over the WHOLE headline configuration — 252 start poses x 5 refine iterations +
+    scoring + ranking on the scene of tools/make_golden_register.py — written to
+    tests/golden/register_252x5_reference_flow.npz (~15 min on 8 cores: the crops come from the Python rasteriser).
+    tests/test_flow_golden_cpu.py compares the committed oracle golden the GPU test uses (register_252x5.npz) with it."""
+    import time
+
+    import make_golden_register as mgr
+    from foundationpose_b200.weights import DEFAULT_CFG, random_state_dict
+
+    torch.set_num_threads(os.cpu_count())
+    mesh, mt, gt, rgb, depth, mask, K, d = mgr.scene()
+    gold = dict(np.load(os.path.join(ROOT, "tests", "golden", "register_252x5.npz")))
+    cfg = Cfg(DEFAULT_CFG, input_resize=(160, 160))
+    est, refiner, scorer = reference_objects(random_state_dict("refine", 0), random_state_dict("score", 0), cfg)
+    est.mesh, est.mesh_tensors, est.diameter, est.model_center = mesh, mt, d, np.zeros(3)
+    est.rot_grid = torch.from_numpy(gold["start"].copy())  # register() overwrites the translation column itself
+    seen = {}
+    inner = scorer.predict
+
+    def recording_predict(*a, **kw):  # the scorer's input poses and its UNSORTED scores (register only keeps them sorted)
+        scores, vis = inner(*a, **kw)
+        seen["poses"], seen["scores"] = np.asarray(kw["ob_in_cams"]).copy(), scores.numpy().copy()
+        return scores, vis
+
+    scorer.predict = recording_predict
+    t0 = time.time()
+    with torch.inference_mode():
+        best = est.register(K=K, rgb=rgb, depth=depth, ob_mask=mask, iteration=5)
+    print(f"reference register over 252 x 5: {time.time() - t0:.0f} s; best id {int(est.best_id)}")
+    out = dict(best_pose=best, best_id=np.int64(est.best_id), poses=seen["poses"], scores=seen["scores"], scores_sorted=est.scores.numpy(),
+               last_trans=refiner.last_trans_update.numpy(), last_rot=refiner.last_rot_update.numpy())
+    dst = os.path.join(ROOT, "tests", "golden", "register_252x5_reference_flow.npz")
+    np.savez_compressed(dst, **out)
+    print(f"wrote {dst}")
+    dp = np.abs(out["poses"] - gold["poses"][5]).max()
+    ds = out["scores"] - gold["scores"]
+    print(f"vs the oracle golden: final poses max |diff| {dp:.2e}; scores offset {ds.mean():+.4f}, rank-relevant {np.abs(ds - ds.mean()).max():.4f}; "
+          f"best {int(est.best_id)} vs {int(gold['best'][0])}; argsort equal: {np.array_equal(np.argsort(-out['scores'], kind='stable'), gold['ids'])}")
+
+
 if __name__ == "__main__":
-    main()
+    if "--headline" in sys.argv:
+        headline()
+    else:
+        main()
