@@ -144,3 +144,14 @@ def test_headline_golden_equals_the_reference_register():
     assert abs(margin - float(g["top2_margin"][0])) < 5e-3 and margin > 0.09
     # the returned pose = best refined pose @ T(-model_center) with model_center = 0 here
     assert np.abs(r["best_pose"] - r["poses"][13]).max() < 1e-6
+
+
+def test_track_golden_equals_the_reference_track_one():
+    """The committed 49-frame oracle golden of the GPU track test (track_seq.npz) vs the reference's own `track_one`
+    executed over the same frames and over the 5-frame fed-back chain (`tools/make_golden_flow.py --track`): 2e-7."""
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "track_seq.npz")))
+    r = dict(np.load(os.path.join(ROOT, "tests", "golden", "track_seq_reference_flow.npz")))
+    assert r["pose_out"].shape == g["pose_out"].shape == (49, 4, 4)
+    assert np.abs(r["pose_out"] - g["pose_out"]).max() < 5e-6
+    assert np.abs(r["last_trans"] - g["last_trans"]).max() < 2e-6
+    assert np.abs(r["chain"] - g["chain"]).max() < 5e-6

@@ -329,8 +329,47 @@ def headline():
           f"best {int(est.best_id)} vs {int(gold['best'][0])}; argsort equal: {np.array_equal(np.argsort(-out['scores'], kind='stable'), gold['ids'])}")
 
 
+def track():
+    """The reference's own `track_one` over the 49 tracked frames (and the 5-frame chain) of tools/make_golden_track.py
+    -> tests/golden/track_seq_reference_flow.npz; compared with the committed oracle golden (track_seq.npz) by
+    tests/test_flow_golden_cpu.py."""
+    from foundationpose_b200 import synth
+    from foundationpose_b200.weights import DEFAULT_CFG, random_state_dict
+
+    torch.set_num_threads(os.cpu_count())
+    gold = dict(np.load(os.path.join(ROOT, "tests", "golden", "track_seq.npz")))
+    mesh = synth.make_mesh(3)
+    from oracle import pipeline
+
+    mt, d, K = pipeline.mesh_tensors(mesh), synth.mesh_diameter(mesh.vertices), synth.DEFAULT_K
+    cfg = Cfg(DEFAULT_CFG, input_resize=(160, 160))
+    est, refiner, scorer = reference_objects(random_state_dict("refine", 0), random_state_dict("score", 0), cfg)
+    est.mesh, est.mesh_tensors, est.diameter, est.model_center = mesh, mt, d, np.zeros(3)
+    gt = gold["gt"]
+    frame = lambda i: synth.make_scene(mesh.visual.image, gt[i], seed=1 + i)[:2]
+    pose_out, lt = [], []
+    with torch.inference_mode():
+        for i in range(1, len(gt)):
+            rgb, depth = frame(i)
+            est.pose_last = torch.from_numpy(gold["pose_in"][i - 1].copy())
+            pose_out.append(est.track_one(rgb=rgb, depth=depth, K=K, iteration=2))
+            lt.append(refiner.last_trans_update.numpy()[0].copy())
+        est.pose_last = torch.from_numpy(gold["chain"][0].copy())
+        chain = [gold["chain"][0]]
+        for i in range(1, 6):
+            rgb, depth = frame(i)
+            chain.append(est.track_one(rgb=rgb, depth=depth, K=K, iteration=2))
+    out = dict(pose_out=np.stack(pose_out), last_trans=np.stack(lt), chain=np.stack(chain))
+    dst = os.path.join(ROOT, "tests", "golden", "track_seq_reference_flow.npz")
+    np.savez_compressed(dst, **out)
+    print(f"wrote {dst}; vs the oracle golden: poses max |diff| {np.abs(out['pose_out'] - gold['pose_out']).max():.2e}, "
+          f"last_trans {np.abs(out['last_trans'] - gold['last_trans']).max():.2e}, chain {np.abs(out['chain'] - gold['chain']).max():.2e}")
+
+
 if __name__ == "__main__":
     if "--headline" in sys.argv:
         headline()
+    elif "--track" in sys.argv:
+        track()
     else:
         main()
